@@ -1,0 +1,362 @@
+// C ABI of the rasterizer (include/gsr_b200.h): host orchestration of the sm_100a kernels.
+//
+// Replaces CudaRasterizer::Rasterizer::{forward, backward, markVisible}
+// (reference cuda_rasterizer/rasterizer_impl.cu:197-339, 343-444, 141-153) and the
+// buffer-carving helpers (rasterizer_impl.cu:155-193, rasterizer_impl.h:21-27,66-72).
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/gsr_b200.h"
+#include "gsr_kernels.cuh"
+
+namespace gsr {
+std::atomic<unsigned long long> g_launch_count{0};
+}
+using namespace gsr;
+
+namespace {
+thread_local std::string t_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_error = buf;
+  return code;
+}
+
+#define GSR_CUDA(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (expr);                                                                  \
+    if (e__ != cudaSuccess) return fail(GSR_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+// mirrors CHECK_CUDA (reference auxiliary.h:166-173): with debug, synchronise after each stage and surface errors
+#define GSR_STAGE(name, debug, stream)                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                                       \
+    if (e__ == cudaSuccess && (debug)) e__ = cudaStreamSynchronize(stream);                     \
+    if (e__ != cudaSuccess) return fail(GSR_ERR_CUDA, "stage %s: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+struct BinningLayout {
+  uint64_t* keys[2];
+  uint32_t* vals[2];
+  char* sort_temp;
+};
+
+int sort_end_bit(int W, int H) {
+  const uint32_t gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+  return 32 + (int)get_higher_msb(gx * gy);   // reference rasterizer_impl.cu:301,309
+}
+
+char* carve_binning(char* base, long long R, int W, int H, BinningLayout& b) {
+  char* p = base;
+  carve(p, b.keys[0], (size_t)R);
+  carve(p, b.keys[1], (size_t)R);
+  carve(p, b.vals[0], (size_t)R);
+  carve(p, b.vals[1], (size_t)R);
+  p = (char*)align_up((size_t)p, 128);
+  b.sort_temp = p;
+  p += sort_temp_bytes(R, sort_passes(sort_end_bit(W, H)));
+  return p;
+}
+
+// pinned 4-byte mailbox for num_rendered, one per host thread
+uint32_t* pinned_mailbox() {
+  thread_local uint32_t* box = nullptr;
+  if (!box) {
+    if (cudaHostAlloc((void**)&box, 64, cudaHostAllocDefault) != cudaSuccess) box = nullptr;
+  }
+  return box;
+}
+}  // namespace
+
+extern "C" {
+
+int gsr_abi_version(void) { return GSR_ABI_VERSION; }
+const char* gsr_last_error(void) { return t_error.c_str(); }
+unsigned long long gsr_launch_count(void) { return g_launch_count.load(); }
+
+size_t gsr_geometry_bytes(int P) {
+  GeometryView g;
+  char* end = carve_geometry(nullptr, P, g);
+  return (size_t)end + 128;
+}
+size_t gsr_image_bytes(int width, int height) {
+  ImageView im;
+  char* end = carve_image(nullptr, width, height, im);
+  return (size_t)end + 128;
+}
+size_t gsr_binning_bytes(long long num_rendered, int width, int height) {
+  BinningLayout b;
+  char* end = carve_binning(nullptr, num_rendered, width, height, b);
+  return (size_t)end + 128;
+}
+
+long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binning_alloc, gsr_alloc_fn image_alloc, void* user,
+                                int P, int D, int M, const float* background, int width, int height, const float* means3D,
+                                const float* shs, const float* colors_precomp, const float* opacities, const float* scales,
+                                float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                                const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                                float tan_fovy, int prefiltered, float* out_color, float* out_depth, float* out_alpha,
+                                int* radii, int* n_touched, int debug, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (P < 0 || width <= 0 || height <= 0) return fail(GSR_ERR_INVALID_ARGUMENT, "bad sizes P=%d W=%d H=%d", P, width, height);
+  if (!geometry_alloc || !binning_alloc || !image_alloc) return fail(GSR_ERR_INVALID_ARGUMENT, "allocation callbacks are required");
+  if (!background || !viewmatrix || !projmatrix || !cam_pos || !out_color || !out_depth || !out_alpha)
+    return fail(GSR_ERR_INVALID_ARGUMENT, "null required pointer");
+  if (P > 0) {
+    if (!means3D || !opacities || !radii) return fail(GSR_ERR_INVALID_ARGUMENT, "means3D, opacities and radii are required");
+    if (!shs && !colors_precomp) return fail(GSR_ERR_UNSUPPORTED, "provide either SHs or precomputed colors");
+    if (!cov3D_precomp && (!scales || !rotations)) return fail(GSR_ERR_INVALID_ARGUMENT, "provide scales+rotations or cov3D_precomp");
+    if (!colors_precomp && (M <= 0 || (D + 1) * (D + 1) > M || D > 3))
+      return fail(GSR_ERR_INVALID_ARGUMENT, "SH degree %d needs %d coefficients, %d stored", D, (D + 1) * (D + 1), M);
+    if (width > 16 * 65535 || height > 16 * 65535) return fail(GSR_ERR_INVALID_ARGUMENT, "image too large");
+  }
+  const uint32_t gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+  const int T = (int)(gx * gy);
+
+  char* img_base = image_alloc(gsr_image_bytes(width, height), user);
+  if (!img_base) return fail(GSR_ERR_ALLOC, "image_alloc returned NULL");
+  ImageView im;
+  carve_image(img_base, width, height, im);
+
+  long long R = 0;
+  GeometryView g{};
+  BinningLayout bl{};
+  int final_buf = 0;
+  if (P > 0) {
+    char* geom_base = geometry_alloc(gsr_geometry_bytes(P), user);
+    if (!geom_base) return fail(GSR_ERR_ALLOC, "geometry_alloc returned NULL");
+    carve_geometry(geom_base, P, g);
+    // scan status words + counters are contiguous: one small memset
+    GSR_CUDA(cudaMemsetAsync(g.scan_status, 0, (size_t)((char*)(g.counters + 32) - (char*)g.scan_status), stream));
+
+    PreprocessParams pp{};
+    pp.P = P, pp.D = D, pp.M = M, pp.W = width, pp.H = height, pp.grid_x = gx, pp.grid_y = gy;
+    pp.means3D = means3D, pp.scales = scales, pp.rotations = rotations, pp.opacities = opacities, pp.shs = shs;
+    pp.cov3D_precomp = cov3D_precomp, pp.colors_precomp = colors_precomp;
+    pp.viewmatrix = viewmatrix, pp.projmatrix = projmatrix, pp.campos = cam_pos;
+    pp.scale_modifier = scale_modifier, pp.tan_fovx = tan_fovx, pp.tan_fovy = tan_fovy;
+    pp.focal_y = height / (2.0f * tan_fovy);   // reference rasterizer_impl.cu:223-224
+    pp.focal_x = width / (2.0f * tan_fovx);
+    pp.prefiltered = prefiltered;
+    pp.sh_vec4 = shs && (M % 4 == 0) && ((uintptr_t)shs % 16 == 0);
+    pp.radii = radii, pp.n_touched = n_touched, pp.geom = g;
+    launch_preprocess_fwd(pp, stream);
+    GSR_STAGE("preprocess", debug, stream);
+
+    // num_rendered -> host (the one sync the reference also has, rasterizer_impl.cu:282)
+    uint32_t* box = pinned_mailbox();
+    if (!box) return fail(GSR_ERR_CUDA, "cudaHostAlloc failed");
+    GSR_CUDA(cudaMemcpyAsync(box, g.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    GSR_CUDA(cudaStreamSynchronize(stream));
+    R = (long long)*box;
+  }
+
+  if (R > 0) {
+    char* bin_base = binning_alloc(gsr_binning_bytes(R, width, height), user);
+    if (!bin_base) return fail(GSR_ERR_ALLOC, "binning_alloc returned NULL");
+    carve_binning(bin_base, R, width, height, bl);
+    const int end_bit = sort_end_bit(width, height);
+    const int passes = sort_passes(end_bit);
+    SortTemp st;
+    carve_sort_temp(bl.sort_temp, R, passes, st);
+    sort_temp_reset(bl.sort_temp, R, passes, stream);
+    launch_duplicate_with_keys(P, g, bl.keys[0], bl.vals[0], gx, end_bit, st.hist, stream);
+    GSR_STAGE("duplicate_with_keys", debug, stream);
+    final_buf = launch_onesweep(bl.keys, bl.vals, R, end_bit, st, stream);
+    GSR_STAGE("radix_sort", debug, stream);
+  } else {
+    // keep the callback contract: the binning buffer exists (possibly tiny) even when nothing is visible
+    char* bin_base = binning_alloc(gsr_binning_bytes(0, width, height), user);
+    if (!bin_base) return fail(GSR_ERR_ALLOC, "binning_alloc returned NULL");
+    carve_binning(bin_base, 0, width, height, bl);
+  }
+  launch_identify_tile_ranges(R, bl.keys[final_buf], im.ranges, T, stream);
+  GSR_STAGE("identify_tile_ranges", debug, stream);
+
+  RenderParams rp{};
+  rp.W = width, rp.H = height, rp.grid_x = gx, rp.grid_y = gy;
+  rp.ranges = im.ranges, rp.point_list = bl.vals[final_buf];
+  rp.means2D = g.means2D, rp.conic_opacity = g.conic_opacity, rp.rgbd = g.rgbd;
+  rp.bg = background, rp.out_color = out_color, rp.out_depth = out_depth, rp.out_alpha = out_alpha;
+  rp.n_contrib = im.n_contrib, rp.n_touched = (P > 0) ? n_touched : nullptr;
+  launch_render_fwd(rp, stream);
+  GSR_STAGE("render", debug, stream);
+  return R;
+}
+
+int gsr_rasterize_backward(int P, int D, int M, long long R, const float* background, int width, int height,
+                           const float* means3D, const float* shs, const float* colors_precomp, const float* out_alpha,
+                           const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                           const float* viewmatrix, const float* projmatrix, const float* projmatrix_raw, const float* cam_pos,
+                           float tan_fovx, float tan_fovy, const int* radii, char* geometry_buffer, char* binning_buffer,
+                           char* image_buffer, const float* dL_dpix, const float* dL_ddepth, const float* dL_dalpha,
+                           float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D,
+                           float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot, float* dL_dtau, int debug,
+                           void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (P < 0 || width <= 0 || height <= 0 || R < 0) return fail(GSR_ERR_INVALID_ARGUMENT, "bad sizes");
+  if (dL_dtau) GSR_CUDA(cudaMemsetAsync(dL_dtau, 0, 6 * sizeof(float), stream));
+  if (P == 0) return GSR_OK;   // reference rasterize_points.cu:168
+  if (!geometry_buffer || !image_buffer || !binning_buffer) return fail(GSR_ERR_INVALID_ARGUMENT, "scratch buffers are required");
+  if (!background || !means3D || !out_alpha || !viewmatrix || !projmatrix || !cam_pos || !radii || !dL_dpix || !dL_ddepth || !dL_dalpha)
+    return fail(GSR_ERR_INVALID_ARGUMENT, "null required pointer");
+  if (dL_dtau && !projmatrix_raw) return fail(GSR_ERR_INVALID_ARGUMENT, "projmatrix_raw is required for the pose gradient");
+  (void)colors_precomp;
+  const uint32_t gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+
+  GeometryView g;
+  carve_geometry(geometry_buffer, P, g);
+  ImageView im;
+  carve_image(image_buffer, width, height, im);
+  BinningLayout bl;
+  carve_binning(binning_buffer, R, width, height, bl);
+  const int final_buf = R > 0 ? (sort_passes(sort_end_bit(width, height)) & 1) : 0;
+
+  GSR_CUDA(cudaMemsetAsync(g.grad_acc, 0, sizeof(float) * 12 * (size_t)P, stream));
+  if (R > 0) {
+    RenderBwdParams rb{};
+    rb.W = width, rb.H = height, rb.grid_x = gx, rb.grid_y = gy;
+    rb.ranges = im.ranges, rb.point_list = bl.vals[final_buf];
+    rb.means2D = g.means2D, rb.conic_opacity = g.conic_opacity, rb.rgbd = g.rgbd;
+    rb.bg = background, rb.out_alpha = out_alpha, rb.n_contrib = im.n_contrib;
+    rb.dL_dpix = dL_dpix, rb.dL_ddepth = dL_ddepth, rb.dL_dalpha = dL_dalpha, rb.grad_acc = g.grad_acc;
+    launch_render_bwd(rb, stream);
+    GSR_STAGE("render_backward", debug, stream);
+  }
+
+  PreBwdParams pb{};
+  pb.P = P, pb.D = D, pb.M = M, pb.W = width, pb.H = height;
+  pb.means3D = means3D, pb.radii = radii, pb.shs = shs, pb.scales = scales, pb.rotations = rotations;
+  pb.cov3D_precomp = cov3D_precomp, pb.viewmatrix = viewmatrix, pb.projmatrix = projmatrix;
+  pb.projmatrix_raw = projmatrix_raw, pb.campos = cam_pos;
+  pb.scale_modifier = scale_modifier, pb.tan_fovx = tan_fovx, pb.tan_fovy = tan_fovy;
+  pb.focal_y = height / (2.0f * tan_fovy), pb.focal_x = width / (2.0f * tan_fovx);
+  pb.geom = g;
+  pb.dL_dmean2D = dL_dmean2D, pb.dL_dconic = dL_dconic, pb.dL_dopacity = dL_dopacity, pb.dL_dcolor = dL_dcolor;
+  pb.dL_dmean3D = dL_dmean3D, pb.dL_dcov3D = dL_dcov3D, pb.dL_dsh = dL_dsh, pb.dL_dscale = dL_dscale, pb.dL_drot = dL_drot;
+  pb.dL_dtau = dL_dtau;
+  launch_preprocess_bwd(pb, stream);
+  GSR_STAGE("preprocess_backward", debug, stream);
+  return GSR_OK;
+}
+
+int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix, unsigned char* present,
+                     void* stream_) {
+  (void)projmatrix;   // the reference's test only uses the view matrix (auxiliary.h:154)
+  if (P < 0) return fail(GSR_ERR_INVALID_ARGUMENT, "P < 0");
+  if (P == 0) return GSR_OK;
+  if (!means3D || !viewmatrix || !present) return fail(GSR_ERR_INVALID_ARGUMENT, "null pointer");
+  launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream_);
+  GSR_STAGE("mark_visible", 0, (cudaStream_t)stream_);
+  return GSR_OK;
+}
+
+}  // extern "C"
+
+// ----------------------------------------------------------------------------- state export (tests)
+namespace {
+__global__ void export_geometry_kernel(int P, GeometryView g, float* depths, float* means2D, float* cov3D, float* conic_opacity,
+                                       float* rgb, unsigned char* clamped, uint32_t* tiles_touched, uint32_t* point_offsets) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const bool vis = g.tiles_touched[i] != 0;   // culled slots of the scratch are uninitialised: export zeros
+  if (depths) depths[i] = vis ? g.depths[i] : 0.f;
+  if (means2D) {
+    means2D[2 * i] = vis ? g.means2D[i].x : 0.f;
+    means2D[2 * i + 1] = vis ? g.means2D[i].y : 0.f;
+  }
+  if (cov3D)
+    for (int k = 0; k < 6; k++) cov3D[6 * (size_t)i + k] = vis ? g.cov3D[6 * (size_t)i + k] : 0.f;
+  if (conic_opacity) {
+    const float4 c = vis ? g.conic_opacity[i] : make_float4(0, 0, 0, 0);
+    conic_opacity[4 * i] = c.x, conic_opacity[4 * i + 1] = c.y, conic_opacity[4 * i + 2] = c.z, conic_opacity[4 * i + 3] = c.w;
+  }
+  if (rgb) {
+    const float4 c = vis ? g.rgbd[i] : make_float4(0, 0, 0, 0);
+    rgb[3 * (size_t)i] = c.x, rgb[3 * (size_t)i + 1] = c.y, rgb[3 * (size_t)i + 2] = c.z;
+  }
+  if (clamped) {
+    const uint8_t m = vis ? g.clamped[i] : 0;
+    clamped[3 * (size_t)i] = m & 1, clamped[3 * (size_t)i + 1] = (m >> 1) & 1, clamped[3 * (size_t)i + 2] = (m >> 2) & 1;
+  }
+  if (tiles_touched) tiles_touched[i] = g.tiles_touched[i];
+  if (point_offsets) point_offsets[i] = g.point_offsets[i];
+}
+}  // namespace
+
+extern "C" {
+
+int gsr_export_state(int P, long long R, int width, int height, const char* geometry_buffer, const char* binning_buffer,
+                     const char* image_buffer, float* depths, float* means2D, float* cov3D, float* conic_opacity, float* rgb,
+                     unsigned char* clamped, uint32_t* tiles_touched, uint32_t* point_offsets, uint64_t* keys_unsorted,
+                     uint32_t* list_unsorted, uint64_t* keys, uint32_t* list, uint32_t* ranges, uint32_t* n_contrib,
+                     void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const uint32_t gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+  GeometryView g{};
+  if (P > 0 && geometry_buffer) {
+    carve_geometry(const_cast<char*>(geometry_buffer), P, g);
+    export_geometry_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g, depths, means2D, cov3D, conic_opacity, rgb, clamped,
+                                                              tiles_touched, point_offsets);
+  }
+  if (R > 0 && binning_buffer) {
+    BinningLayout bl;
+    carve_binning(const_cast<char*>(binning_buffer), R, width, height, bl);
+    const int end_bit = sort_end_bit(width, height);
+    const int fb = sort_passes(end_bit) & 1;
+    if (keys) GSR_CUDA(cudaMemcpyAsync(keys, bl.keys[fb], sizeof(uint64_t) * (size_t)R, cudaMemcpyDeviceToDevice, stream));
+    if (list) GSR_CUDA(cudaMemcpyAsync(list, bl.vals[fb], sizeof(uint32_t) * (size_t)R, cudaMemcpyDeviceToDevice, stream));
+    if (keys_unsorted && list_unsorted && P > 0 && geometry_buffer)   // regenerated: the sort's ping-pong overwrote them
+      launch_duplicate_with_keys(P, g, keys_unsorted, list_unsorted, gx, end_bit, nullptr, stream);
+  }
+  if (image_buffer) {
+    ImageView im;
+    carve_image(const_cast<char*>(image_buffer), width, height, im);
+    if (ranges) GSR_CUDA(cudaMemcpyAsync(ranges, im.ranges, sizeof(uint2) * (size_t)gx * gy, cudaMemcpyDeviceToDevice, stream));
+    if (n_contrib) GSR_CUDA(cudaMemcpyAsync(n_contrib, im.n_contrib, sizeof(uint32_t) * (size_t)width * height, cudaMemcpyDeviceToDevice, stream));
+  }
+  GSR_STAGE("export_state", 1, stream);
+  return GSR_OK;
+}
+
+size_t gsr_sort_temp_bytes(long long n) { return sort_temp_bytes(n, SORT_MAX_PASSES); }
+
+int gsr_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out, uint64_t* keys_tmp,
+                   uint32_t* vals_tmp, long long n, int end_bit, char* temp, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || end_bit < 1 || end_bit > 64) return fail(GSR_ERR_INVALID_ARGUMENT, "bad n/end_bit");
+  if (n == 0) return GSR_OK;
+  if (n >= (1ll << 30)) return fail(GSR_ERR_INVALID_ARGUMENT, "n must be < 2^30");
+  const int passes = sort_passes(end_bit);
+  SortTemp st;
+  carve_sort_temp(temp, n, passes, st);
+  sort_temp_reset(temp, n, passes, stream);
+  launch_sort_histogram(keys_in, n, end_bit, st.hist, stream);
+  // arrange the ping-pong so that the last pass lands in keys_out: odd passes in->out directly
+  uint64_t* kb[2];
+  uint32_t* vb[2];
+  if (passes & 1) {
+    // pass 0 must read keys_in: copy-free only if we may treat keys_in as buffer 0; it is const, so stage through tmp
+    GSR_CUDA(cudaMemcpyAsync(keys_tmp, keys_in, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+    GSR_CUDA(cudaMemcpyAsync(vals_tmp, vals_in, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+    kb[0] = keys_tmp, kb[1] = keys_out, vb[0] = vals_tmp, vb[1] = vals_out;
+  } else {
+    GSR_CUDA(cudaMemcpyAsync(keys_out, keys_in, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+    GSR_CUDA(cudaMemcpyAsync(vals_out, vals_in, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+    kb[0] = keys_out, kb[1] = keys_tmp, vb[0] = vals_out, vb[1] = vals_tmp;
+  }
+  launch_onesweep(kb, vb, n, end_bit, st, stream);
+  GSR_STAGE("sort_pairs", 0, stream);
+  return GSR_OK;
+}
+
+}  // extern "C"

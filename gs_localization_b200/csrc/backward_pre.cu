@@ -1,0 +1,363 @@
+// Backward of the per-Gaussian preprocessing, one fused kernel.
+//
+// Replaces, from the reference (gaussian_splatting/submodules/diff-gaussian-rasterization):
+//   computeCov2DCUDA (backward)      cuda_rasterizer/backward.cu:144-274
+//   preprocessCUDA (backward)        cuda_rasterizer/backward.cu:346-396
+//   computeColorFromSH (backward)    cuda_rasterizer/backward.cu:20-139  (+ dnormvdv auxiliary.h:107-117)
+//   computeCov3D (backward)          cuda_rasterizer/backward.cu:278-341
+//   the nine torch::zeros fills      rasterize_points.cu:158-166
+//
+// B200 design: one thread per Gaussian, 128 per CTA; the two reference kernels are fused so
+// dL_dcov3D / dL_dmean3D never round-trip through HBM between them; every gradient row is
+// written exactly once for ALL P Gaussians (zeros for culled ones), so no zero-fill pass is
+// needed; the wide SH-gradient rows (12*M bytes each) are staged through shared memory and
+// leave the CTA as fully coalesced stores.  With dL_dtau != nullptr the SE(3) chain rule is
+// fused in: each thread forms its 6-vector contribution to dL/d(rho, theta) for the left
+// perturbation T_w2c <- exp(tau) T_w2c (gs_localization/pipelines/tools/pose_utils.py:90-122),
+// the CTA reduces it with shuffles and issues 6 atomics.
+#include "gsr_kernels.cuh"
+
+namespace gsr {
+
+constexpr int BW_THREADS = 128;
+constexpr int SH_MAX_FLOATS = 48;   // (3+1)^2 * 3
+
+// reference auxiliary.h:107-117
+__device__ __forceinline__ float3 dnormvdv(float3 v, float3 dv) {
+  const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
+  const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+  float3 o;
+  o.x = ((+sum2 - v.x * v.x) * dv.x - v.y * v.x * dv.y - v.z * v.x * dv.z) * invsum32;
+  o.y = (-v.x * v.y * dv.x + (sum2 - v.y * v.y) * dv.y - v.z * v.y * dv.z) * invsum32;
+  o.z = (-v.x * v.z * dv.x - v.y * v.z * dv.y + (sum2 - v.z * v.z) * dv.z) * invsum32;
+  return o;
+}
+
+// SH backward (reference backward.cu:20-139).  Writes this Gaussian's dL_dsh row into `out`
+// (shared memory, stride 1) and returns dL_dmean through the view direction.
+__device__ __forceinline__ float3 sh_backward(int deg, float3 pos, float3 campos, const float* __restrict__ sh,
+                                              float3 dL_dRGB, float* out) {
+  const float3 dir_orig = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
+  const float inv_len = 1.0f / sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+  const float x = dir_orig.x * inv_len, y = dir_orig.y * inv_len, z = dir_orig.z * inv_len;
+  float3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
+  auto S = [&](int k) { return make_float3(__ldg(sh + 3 * k), __ldg(sh + 3 * k + 1), __ldg(sh + 3 * k + 2)); };
+  auto put = [&](int k, float w) {
+    out[3 * k] = w * dL_dRGB.x;
+    out[3 * k + 1] = w * dL_dRGB.y;
+    out[3 * k + 2] = w * dL_dRGB.z;
+  };
+  auto axpy = [](float3& a, float w, float3 s) { a.x += w * s.x; a.y += w * s.y; a.z += w * s.z; };
+  put(0, SH_C0);
+  if (deg > 0) {
+    put(1, -SH_C1 * y);
+    put(2, SH_C1 * z);
+    put(3, -SH_C1 * x);
+    axpy(dRGBdx, -SH_C1, S(3));
+    axpy(dRGBdy, -SH_C1, S(1));
+    axpy(dRGBdz, SH_C1, S(2));
+    if (deg > 1) {
+      const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+      put(4, SH_C2[0] * xy);
+      put(5, SH_C2[1] * yz);
+      put(6, SH_C2[2] * (2.f * zz - xx - yy));
+      put(7, SH_C2[3] * xz);
+      put(8, SH_C2[4] * (xx - yy));
+      const float3 s4 = S(4), s5 = S(5), s6 = S(6), s7 = S(7), s8 = S(8);
+      axpy(dRGBdx, SH_C2[0] * y, s4); axpy(dRGBdx, SH_C2[2] * 2.f * -x, s6); axpy(dRGBdx, SH_C2[3] * z, s7); axpy(dRGBdx, SH_C2[4] * 2.f * x, s8);
+      axpy(dRGBdy, SH_C2[0] * x, s4); axpy(dRGBdy, SH_C2[1] * z, s5); axpy(dRGBdy, SH_C2[2] * 2.f * -y, s6); axpy(dRGBdy, SH_C2[4] * 2.f * -y, s8);
+      axpy(dRGBdz, SH_C2[1] * y, s5); axpy(dRGBdz, SH_C2[2] * 2.f * 2.f * z, s6); axpy(dRGBdz, SH_C2[3] * x, s7);
+      if (deg > 2) {
+        put(9, SH_C3[0] * y * (3.f * xx - yy));
+        put(10, SH_C3[1] * xy * z);
+        put(11, SH_C3[2] * y * (4.f * zz - xx - yy));
+        put(12, SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
+        put(13, SH_C3[4] * x * (4.f * zz - xx - yy));
+        put(14, SH_C3[5] * z * (xx - yy));
+        put(15, SH_C3[6] * x * (xx - 3.f * yy));
+        const float3 s9 = S(9), s10 = S(10), s11 = S(11), s12 = S(12), s13 = S(13), s14 = S(14), s15 = S(15);
+        axpy(dRGBdx, SH_C3[0] * 3.f * 2.f * xy, s9); axpy(dRGBdx, SH_C3[1] * yz, s10); axpy(dRGBdx, SH_C3[2] * -2.f * xy, s11);
+        axpy(dRGBdx, SH_C3[3] * -3.f * 2.f * xz, s12); axpy(dRGBdx, SH_C3[4] * (-3.f * xx + 4.f * zz - yy), s13);
+        axpy(dRGBdx, SH_C3[5] * 2.f * xz, s14); axpy(dRGBdx, SH_C3[6] * 3.f * (xx - yy), s15);
+        axpy(dRGBdy, SH_C3[0] * 3.f * (xx - yy), s9); axpy(dRGBdy, SH_C3[1] * xz, s10);
+        axpy(dRGBdy, SH_C3[2] * (-3.f * yy + 4.f * zz - xx), s11); axpy(dRGBdy, SH_C3[3] * -3.f * 2.f * yz, s12);
+        axpy(dRGBdy, SH_C3[4] * -2.f * xy, s13); axpy(dRGBdy, SH_C3[5] * -2.f * yz, s14); axpy(dRGBdy, SH_C3[6] * -3.f * 2.f * xy, s15);
+        axpy(dRGBdz, SH_C3[1] * xy, s10); axpy(dRGBdz, SH_C3[2] * 4.f * 2.f * yz, s11);
+        axpy(dRGBdz, SH_C3[3] * 3.f * (2.f * zz - xx - yy), s12); axpy(dRGBdz, SH_C3[4] * 4.f * 2.f * xz, s13);
+        axpy(dRGBdz, SH_C3[5] * (xx - yy), s14);
+      }
+    }
+  }
+  const float3 dL_ddir = {dRGBdx.x * dL_dRGB.x + dRGBdx.y * dL_dRGB.y + dRGBdx.z * dL_dRGB.z,
+                          dRGBdy.x * dL_dRGB.x + dRGBdy.y * dL_dRGB.y + dRGBdy.z * dL_dRGB.z,
+                          dRGBdz.x * dL_dRGB.x + dRGBdz.y * dL_dRGB.y + dRGBdz.z * dL_dRGB.z};
+  return dnormvdv(dir_orig, dL_ddir);
+}
+
+__global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwdParams p) {
+  __shared__ float s_sh[BW_THREADS * (SH_MAX_FLOATS + 1)];   // padded rows: conflict-free
+  __shared__ float s_tau[BW_THREADS / 32][6];
+  __shared__ int s_any_visible[BW_THREADS / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int idx = blockIdx.x * BW_THREADS + tid;
+  const int P = p.P, M = p.M;
+  const int row = 3 * M;                 // floats per SH row
+  const bool valid = idx < P;
+  const bool visible = valid && __ldg(p.radii + idx) > 0;
+  const float* vm = p.viewmatrix;
+  const float* proj = p.projmatrix;
+
+  float3 g_mean2D = {0, 0, 0};
+  float4 g_conic = {0, 0, 0, 0};
+  float g_opacity = 0.f;
+  float3 g_color = {0, 0, 0};
+  float3 g_mean = {0, 0, 0};
+  float g_cov[6] = {0, 0, 0, 0, 0, 0};
+  float3 g_scale = {0, 0, 0};
+  float4 g_rot = {0, 0, 0, 0};
+  float tau[6] = {0, 0, 0, 0, 0, 0};
+  float* my_sh = s_sh + tid * (SH_MAX_FLOATS + 1);
+  const bool want_sh = p.dL_dsh != nullptr && p.shs != nullptr;
+  if (want_sh) {
+    for (int k = 0; k < row; k++) my_sh[k] = 0.f;
+  }
+
+  if (visible) {
+    const float* acc = p.geom.grad_acc + 12 * (size_t)idx;
+    const float4 a0 = *reinterpret_cast<const float4*>(acc);
+    const float4 a1 = *reinterpret_cast<const float4*>(acc + 4);
+    const float4 a2 = *reinterpret_cast<const float4*>(acc + 8);
+    g_mean2D = make_float3(a0.x, a0.y, 0.f);
+    g_conic = make_float4(a0.z, a0.w, 0.f, a1.x);
+    g_opacity = a1.y;
+    g_color = make_float3(a1.z, a1.w, a2.x);
+    const float g_depth = a2.y;
+
+    const float3 mean = {__ldg(p.means3D + 3 * (size_t)idx), __ldg(p.means3D + 3 * (size_t)idx + 1),
+                         __ldg(p.means3D + 3 * (size_t)idx + 2)};
+    const float* c3 = p.cov3D_precomp ? p.cov3D_precomp + 6 * (size_t)idx : p.geom.cov3D + 6 * (size_t)idx;
+    float cov3D[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) cov3D[k] = __ldg(c3 + k);
+
+    // ---------------- computeCov2DCUDA backward (backward.cu:144-274)
+    float3 t = {vm[0] * mean.x + vm[4] * mean.y + vm[8] * mean.z + vm[12],
+                vm[1] * mean.x + vm[5] * mean.y + vm[9] * mean.z + vm[13],
+                vm[2] * mean.x + vm[6] * mean.y + vm[10] * mean.z + vm[14]};
+    const float3 t_orig = t;
+    const float limx = 1.3f * p.tan_fovx, limy = 1.3f * p.tan_fovy;
+    const float txtz = t.x / t.z, tytz = t.y / t.z;
+    t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
+    t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+    const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+    const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+    const float h_x = p.focal_x, h_y = p.focal_y;
+    const float J00 = h_x / t.z, J02 = -(h_x * t.x) / (t.z * t.z), J11 = h_y / t.z, J12 = -(h_y * t.y) / (t.z * t.z);
+    // Rw[k][i] = W2C rotation entry (row k, col i) = vm[4*i + k]
+    float T0[3], T1[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      T0[i] = vm[4 * i + 0] * J00 + vm[4 * i + 2] * J02;
+      T1[i] = vm[4 * i + 1] * J11 + vm[4 * i + 2] * J12;
+    }
+    const float V[3][3] = {{cov3D[0], cov3D[1], cov3D[2]}, {cov3D[1], cov3D[3], cov3D[4]}, {cov3D[2], cov3D[4], cov3D[5]}};
+    float TV0[3], TV1[3];   // T0 . V[:,j], T1 . V[:,j]
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      TV0[j] = T0[0] * V[0][j] + T0[1] * V[1][j] + T0[2] * V[2][j];
+      TV1[j] = T1[0] * V[0][j] + T1[1] * V[1][j] + T1[2] * V[2][j];
+    }
+    const float a = TV0[0] * T0[0] + TV0[1] * T0[1] + TV0[2] * T0[2] + 0.3f;
+    const float b = TV1[0] * T0[0] + TV1[1] * T0[1] + TV1[2] * T0[2];
+    const float c = TV1[0] * T1[0] + TV1[1] * T1[1] + TV1[2] * T1[2] + 0.3f;
+    const float denom = a * c - b * b;
+    float dL_da = 0, dL_db = 0, dL_dc = 0;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+    const float3 dL_dconic = {g_conic.x, g_conic.y, g_conic.w};
+    if (denom2inv != 0) {
+      dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - a * c) * dL_dconic.z);
+      dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
+      dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + a * b * dL_dconic.z);
+      g_cov[0] = (T0[0] * T0[0] * dL_da + T0[0] * T1[0] * dL_db + T1[0] * T1[0] * dL_dc);
+      g_cov[3] = (T0[1] * T0[1] * dL_da + T0[1] * T1[1] * dL_db + T1[1] * T1[1] * dL_dc);
+      g_cov[5] = (T0[2] * T0[2] * dL_da + T0[2] * T1[2] * dL_db + T1[2] * T1[2] * dL_dc);
+      g_cov[1] = 2 * T0[0] * T0[1] * dL_da + (T0[0] * T1[1] + T0[1] * T1[0]) * dL_db + 2 * T1[0] * T1[1] * dL_dc;
+      g_cov[2] = 2 * T0[0] * T0[2] * dL_da + (T0[0] * T1[2] + T0[2] * T1[0]) * dL_db + 2 * T1[0] * T1[2] * dL_dc;
+      g_cov[4] = 2 * T0[2] * T0[1] * dL_da + (T0[1] * T1[2] + T0[2] * T1[1]) * dL_db + 2 * T1[1] * T1[2] * dL_dc;
+    }
+    float dL_dT0[3], dL_dT1[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      dL_dT0[j] = 2 * TV0[j] * dL_da + TV1[j] * dL_db;
+      dL_dT1[j] = 2 * TV1[j] * dL_dc + TV0[j] * dL_db;
+    }
+    const float dL_dJ00 = vm[0] * dL_dT0[0] + vm[4] * dL_dT0[1] + vm[8] * dL_dT0[2];
+    const float dL_dJ02 = vm[2] * dL_dT0[0] + vm[6] * dL_dT0[1] + vm[10] * dL_dT0[2];
+    const float dL_dJ11 = vm[1] * dL_dT1[0] + vm[5] * dL_dT1[1] + vm[9] * dL_dT1[2];
+    const float dL_dJ12 = vm[2] * dL_dT1[0] + vm[6] * dL_dT1[1] + vm[10] * dL_dT1[2];
+    const float tz = 1.f / t.z, tz2 = tz * tz, tz3 = tz2 * tz;
+    const float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+    const float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+    const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 + (2 * h_y * t.y) * tz3 * dL_dJ12;
+    // transformVec4x3Transpose (auxiliary.h:89-97)
+    g_mean.x = vm[0] * dL_dtx + vm[1] * dL_dty + vm[2] * dL_dtz;
+    g_mean.y = vm[4] * dL_dtx + vm[5] * dL_dty + vm[6] * dL_dtz;
+    g_mean.z = vm[8] * dL_dtx + vm[9] * dL_dty + vm[10] * dL_dtz;
+
+    // ---------------- mean2D -> mean3D through projmatrix (backward.cu:370-387)
+    const float hw = proj[3] * mean.x + proj[7] * mean.y + proj[11] * mean.z + proj[15];
+    const float m_w = 1.0f / (hw + 0.0000001f);
+    const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
+    const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
+    g_mean.x += (proj[0] * m_w - proj[3] * mul1) * g_mean2D.x + (proj[1] * m_w - proj[3] * mul2) * g_mean2D.y;
+    g_mean.y += (proj[4] * m_w - proj[7] * mul1) * g_mean2D.x + (proj[5] * m_w - proj[7] * mul2) * g_mean2D.y;
+    g_mean.z += (proj[8] * m_w - proj[11] * mul1) * g_mean2D.x + (proj[9] * m_w - proj[11] * mul2) * g_mean2D.y;
+
+    // ---------------- SH (backward.cu:389-391)
+    float3 g_sh_mean = {0, 0, 0};
+    if (p.shs) {
+      const uint8_t cm = __ldg(p.geom.clamped + idx);
+      const float3 dL_dRGB = {(cm & 1) ? 0.f : g_color.x, (cm & 2) ? 0.f : g_color.y, (cm & 4) ? 0.f : g_color.z};
+      const float3 cp = {__ldg(p.campos), __ldg(p.campos + 1), __ldg(p.campos + 2)};
+      float dummy[SH_MAX_FLOATS];
+      float* out = want_sh ? my_sh : dummy;
+      g_sh_mean = sh_backward(p.D, mean, cp, p.shs + (size_t)idx * row, dL_dRGB, out);
+      g_mean.x += g_sh_mean.x; g_mean.y += g_sh_mean.y; g_mean.z += g_sh_mean.z;
+    }
+
+    // ---------------- computeCov3D backward (backward.cu:278-341)
+    if (p.scales) {
+      const float3 sc = {__ldg(p.scales + 3 * (size_t)idx), __ldg(p.scales + 3 * (size_t)idx + 1), __ldg(p.scales + 3 * (size_t)idx + 2)};
+      const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+      const float r = q.x, x = q.y, y = q.z, z = q.w;
+      // glm columns of R
+      const float Rm[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+                              {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+                              {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+      const float s[3] = {p.scale_modifier * sc.x, p.scale_modifier * sc.y, p.scale_modifier * sc.z};
+      const float dS[3][3] = {{g_cov[0], 0.5f * g_cov[1], 0.5f * g_cov[2]},
+                              {0.5f * g_cov[1], g_cov[3], 0.5f * g_cov[4]},
+                              {0.5f * g_cov[2], 0.5f * g_cov[4], g_cov[5]}};
+      // dL_dM[j][i] = 2 * sum_k M[k][i] dS[j][k], M[k][i] = s_i Rm[k][i];  dMt[j][i] = dM[i][j]
+      float dMt[3][3];
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+          dMt[i][j] = 2.f * s[i] * (Rm[0][i] * dS[j][0] + Rm[1][i] * dS[j][1] + Rm[2][i] * dS[j][2]);
+      g_scale.x = Rm[0][0] * dMt[0][0] + Rm[1][0] * dMt[0][1] + Rm[2][0] * dMt[0][2];
+      g_scale.y = Rm[0][1] * dMt[1][0] + Rm[1][1] * dMt[1][1] + Rm[2][1] * dMt[1][2];
+      g_scale.z = Rm[0][2] * dMt[2][0] + Rm[1][2] * dMt[2][1] + Rm[2][2] * dMt[2][2];
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) dMt[j][i] *= s[j];
+      g_rot.x = 2 * z * (dMt[0][1] - dMt[1][0]) + 2 * y * (dMt[2][0] - dMt[0][2]) + 2 * x * (dMt[1][2] - dMt[2][1]);
+      g_rot.y = 2 * y * (dMt[1][0] + dMt[0][1]) + 2 * z * (dMt[2][0] + dMt[0][2]) + 2 * r * (dMt[1][2] - dMt[2][1]) - 4 * x * (dMt[2][2] + dMt[1][1]);
+      g_rot.z = 2 * x * (dMt[1][0] + dMt[0][1]) + 2 * r * (dMt[2][0] - dMt[0][2]) + 2 * z * (dMt[1][2] + dMt[2][1]) - 4 * y * (dMt[2][2] + dMt[0][0]);
+      g_rot.w = 2 * r * (dMt[0][1] - dMt[1][0]) + 2 * x * (dMt[2][0] + dMt[0][2]) + 2 * y * (dMt[1][2] + dMt[2][1]) - 4 * z * (dMt[1][1] + dMt[0][0]);
+    }
+
+    // ---------------- SE(3) chain rule (pose extension), camera-space derivation
+    if (p.dL_dtau) {
+      const float* raw = p.projmatrix_raw;
+      // (1) screen-space mean through projmatrix_raw applied to the camera-space point
+      const float pcx = t_orig.x, pcy = t_orig.y, pcz = t_orig.z;
+      const float rw = raw[3] * pcx + raw[7] * pcy + raw[11] * pcz + raw[15];
+      const float r_w = 1.0f / (rw + 0.0000001f);
+      const float rmul1 = (raw[0] * pcx + raw[4] * pcy + raw[8] * pcz + raw[12]) * r_w * r_w;
+      const float rmul2 = (raw[1] * pcx + raw[5] * pcy + raw[9] * pcz + raw[13]) * r_w * r_w;
+      float gx = (raw[0] * r_w - raw[3] * rmul1) * g_mean2D.x + (raw[1] * r_w - raw[3] * rmul2) * g_mean2D.y;
+      float gy = (raw[4] * r_w - raw[7] * rmul1) * g_mean2D.x + (raw[5] * r_w - raw[7] * rmul2) * g_mean2D.y;
+      float gz = (raw[8] * r_w - raw[11] * rmul1) * g_mean2D.x + (raw[9] * r_w - raw[11] * rmul2) * g_mean2D.y;
+      // (2) covariance path through t, (3) rendered depth through p_c.z
+      gx += dL_dtx; gy += dL_dty; gz += dL_dtz + g_depth;
+      tau[0] = gx; tau[1] = gy; tau[2] = gz;
+      tau[3] = pcy * gz - pcz * gy;
+      tau[4] = pcz * gx - pcx * gz;
+      tau[5] = pcx * gy - pcy * gx;
+      // (4) covariance path through the rotation W: G[m][i] = dL/dR[m][i], Q = R G^T, dtheta = axial(Q - Q^T)
+      float G[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        G[0][i] = J00 * dL_dT0[i];
+        G[1][i] = J11 * dL_dT1[i];
+        G[2][i] = J02 * dL_dT0[i] + J12 * dL_dT1[i];
+      }
+      auto Q = [&](int i, int j) {   // sum_m R[i][m] G[j][m], R[i][m] = vm[4*m + i]
+        return vm[i] * G[j][0] + vm[4 + i] * G[j][1] + vm[8 + i] * G[j][2];
+      };
+      tau[3] += Q(1, 2) - Q(2, 1);
+      tau[4] += Q(2, 0) - Q(0, 2);
+      tau[5] += Q(0, 1) - Q(1, 0);
+      // (5) SH view direction: the camera centre moves by -R^T rho
+      tau[0] += vm[0] * g_sh_mean.x + vm[4] * g_sh_mean.y + vm[8] * g_sh_mean.z;
+      tau[1] += vm[1] * g_sh_mean.x + vm[5] * g_sh_mean.y + vm[9] * g_sh_mean.z;
+      tau[2] += vm[2] * g_sh_mean.x + vm[6] * g_sh_mean.y + vm[10] * g_sh_mean.z;
+    }
+  }
+
+  // ---------------- dense row writes (zeros for culled Gaussians)
+  if (valid) {
+    if (p.dL_dmean2D) { float* o = p.dL_dmean2D + 3 * (size_t)idx; o[0] = g_mean2D.x; o[1] = g_mean2D.y; o[2] = 0.f; }
+    if (p.dL_dconic) reinterpret_cast<float4*>(p.dL_dconic)[idx] = g_conic;
+    if (p.dL_dopacity) p.dL_dopacity[idx] = g_opacity;
+    if (p.dL_dcolor) { float* o = p.dL_dcolor + 3 * (size_t)idx; o[0] = g_color.x; o[1] = g_color.y; o[2] = g_color.z; }
+    if (p.dL_dmean3D) { float* o = p.dL_dmean3D + 3 * (size_t)idx; o[0] = g_mean.x; o[1] = g_mean.y; o[2] = g_mean.z; }
+    if (p.dL_dcov3D) {
+      float* o = p.dL_dcov3D + 6 * (size_t)idx;
+#pragma unroll
+      for (int k = 0; k < 6; k++) o[k] = g_cov[k];
+    }
+    if (p.dL_dscale) { float* o = p.dL_dscale + 3 * (size_t)idx; o[0] = g_scale.x; o[1] = g_scale.y; o[2] = g_scale.z; }
+    if (p.dL_drot) reinterpret_cast<float4*>(p.dL_drot)[idx] = g_rot;
+  }
+
+  // ---------------- SH gradient rows: the warp's 32 rows are contiguous in memory
+  if (p.dL_dsh != nullptr && M > 0) {
+    const int warp_first = blockIdx.x * BW_THREADS + warp * 32;
+    const int nrows = min(32, P - warp_first);
+    if (nrows > 0) {
+      const bool any_vis = __any_sync(0xffffffffu, visible) && want_sh;
+      float* dst = p.dL_dsh + (size_t)warp_first * row;
+      const int total = nrows * row;
+      __syncwarp();
+      if (any_vis) {
+        const float* src = s_sh + (warp * 32) * (SH_MAX_FLOATS + 1);
+        for (int e = lane; e < total; e += 32) {
+          const int rr = e / row, cc = e - rr * row;
+          dst[e] = src[rr * (SH_MAX_FLOATS + 1) + cc];
+        }
+      } else {
+        for (int e = lane; e < total; e += 32) dst[e] = 0.f;
+      }
+    }
+  }
+  (void)s_any_visible;
+
+  // ---------------- pose gradient: CTA reduction, 6 atomics
+  if (p.dL_dtau) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      float v = tau[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_tau[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid < 6) {
+      float v = 0.f;
+      for (int w = 0; w < BW_THREADS / 32; w++) v += s_tau[w][tid];
+      if (v != 0.f) atomicAdd(p.dL_dtau + tid, v);
+    }
+  }
+}
+
+void launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream) {
+  if (p.P <= 0) return;
+  preprocess_bwd_kernel<<<(p.P + BW_THREADS - 1) / BW_THREADS, BW_THREADS, 0, stream>>>(p);
+  count_launch();
+}
+
+}  // namespace gsr

@@ -1,0 +1,117 @@
+// Shared definitions of the B200 rasterizer kernels: scratch layout, rounding-pinned math
+// helpers and launch bookkeeping.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace gsr {
+
+constexpr int TILE_X = 16, TILE_Y = 16;     // reference config.h:15-17 (BLOCK_X/BLOCK_Y)
+constexpr int TILE_PIX = TILE_X * TILE_Y;
+constexpr int PRE_THREADS = 256;            // Gaussians per preprocess CTA
+
+// SH constants, reference auxiliary.h:22-39
+__device__ constexpr float SH_C0 = 0.28209479177387814f;
+__device__ constexpr float SH_C1 = 0.4886025119029199f;
+__device__ constexpr float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                       -1.0925484305920792f, 0.5462742152960396f};
+__device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                       0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                       -0.5900435899266435f};
+
+// ---------------------------------------------------------------------------------------
+// Scratch layout (private contract between this library's forward and backward).
+// All slabs 128-byte aligned.  SoA, sized for P Gaussians / R instances / N pixels.
+// ---------------------------------------------------------------------------------------
+struct GeometryView {           // replaces GeometryState (reference rasterizer_impl.h:29-44)
+  float* depths;                // [P]   view-space z (sort key low bits)
+  float2* means2D;              // [P]   pixel-space centre
+  float4* conic_opacity;        // [P]   (conic.x, conic.y, conic.z, opacity)
+  float4* rgbd;                 // [P]   (r, g, b, depth): one 16-byte gather for the blend kernels
+  float* cov3D;                 // [6P]
+  uint2* rect;                  // [P]   tile rectangle: x = minx | maxx<<16, y = miny | maxy<<16
+  uint8_t* clamped;             // [P]   bit c set <=> channel c was clamped at 0
+  uint32_t* tiles_touched;      // [P]
+  uint32_t* point_offsets;      // [P]   inclusive prefix sum of tiles_touched (Gaussian order)
+  unsigned long long* scan_status;  // [ceil(P/256)] decoupled look-back words (flag<<32 | value)
+  uint32_t* counters;           // [8]  0: CTA ticket, 1: num_rendered, 2: max depth bits
+  float* grad_acc;              // [12P] backward accumulators (see render_bwd)
+};
+
+struct ImageView {              // replaces ImageState (reference rasterizer_impl.h:46-52)
+  uint2* ranges;                // [T]
+  uint32_t* n_contrib;          // [N]
+};
+
+struct BinningView {            // replaces BinningState (reference rasterizer_impl.h:54-64)
+  uint64_t* keys[2];            // ping-pong; [0] holds the unsorted keys before the sort
+  uint32_t* vals[2];
+  char* sort_temp;
+  int final_buf;                // which of the two holds the sorted list (passes even -> 0)
+};
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename T> inline void carve(char*& p, T*& out, size_t count) {
+  p = (char*)align_up((size_t)p, 128);
+  out = (T*)p;
+  p += count * sizeof(T);
+}
+
+inline int num_pre_blocks(int P) { return (P + PRE_THREADS - 1) / PRE_THREADS; }
+
+inline char* carve_geometry(char* base, int P, GeometryView& g) {
+  char* p = base;
+  carve(p, g.depths, (size_t)P);
+  carve(p, g.means2D, (size_t)P);
+  carve(p, g.conic_opacity, (size_t)P);
+  carve(p, g.rgbd, (size_t)P);
+  carve(p, g.cov3D, 6 * (size_t)P);
+  carve(p, g.rect, (size_t)P);
+  carve(p, g.clamped, (size_t)P);
+  carve(p, g.tiles_touched, (size_t)P);
+  carve(p, g.point_offsets, (size_t)P);
+  carve(p, g.scan_status, (size_t)num_pre_blocks(P) + 1);
+  carve(p, g.counters, (size_t)32);
+  carve(p, g.grad_acc, 12 * (size_t)P);
+  return p;
+}
+
+inline char* carve_image(char* base, int W, int H, ImageView& im) {
+  char* p = base;
+  const size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+  carve(p, im.ranges, T);
+  carve(p, im.n_contrib, (size_t)W * H);
+  return p;
+}
+
+// reference rasterizer_impl.cu:35-50
+inline uint32_t get_higher_msb(uint32_t n) {
+  uint32_t msb = sizeof(n) * 4, step = msb;
+  while (step > 1) {
+    step /= 2;
+    if (n >> msb) msb += step; else msb -= step;
+  }
+  if (n >> msb) msb++;
+  return msb;
+}
+
+// ---------------------------------------------------------------------------------------
+// Rounding-pinned arithmetic.  The binning decisions (radius, tile rectangle, depth key)
+// and n_contrib must be bit-identical to the reference build, so the expressions that feed
+// them use explicit IEEE intrinsics in exactly the order nvcc contracted the reference's
+// source into FMAs on sm_100a (oracle/_ref/forward.sass).  These do
+// not depend on -fmad / -use_fast_math.
+// ---------------------------------------------------------------------------------------
+// a0*b0 + a1*b1 + a2*b2 as the reference compiles it: second product rounded, others fused.
+__device__ __forceinline__ float dot3c(float a0, float b0, float a1, float b1, float a2, float b2) {
+  float t = __fmul_rn(a1, b1);
+  t = __fmaf_rn(a0, b0, t);
+  t = __fmaf_rn(a2, b2, t);
+  return t;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+}  // namespace gsr

@@ -1,0 +1,131 @@
+// Kernel-launcher interface between api.cu and the stage files.
+#pragma once
+#include <atomic>
+#include <cstdio>
+#include "gsr_common.cuh"
+
+namespace gsr {
+
+extern std::atomic<unsigned long long> g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+struct PreprocessParams {
+  int P, D, M, W, H;
+  uint32_t grid_x, grid_y;
+  const float* means3D;
+  const float* scales;
+  const float* rotations;
+  const float* opacities;
+  const float* shs;
+  const float* cov3D_precomp;
+  const float* colors_precomp;
+  const float* viewmatrix;
+  const float* projmatrix;
+  const float* campos;
+  float scale_modifier, tan_fovx, tan_fovy, focal_x, focal_y;
+  int prefiltered;
+  int sh_vec4;          // SH rows are 16-byte aligned and a multiple of 4 floats long
+  int* radii;
+  int* n_touched;       // may be null
+  GeometryView geom;
+};
+
+void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream);
+void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
+
+// ---- binning (binning.cu)
+constexpr int SORT_RADIX_BITS = 8;
+constexpr int SORT_RADIX = 1 << SORT_RADIX_BITS;
+constexpr int SORT_MAX_PASSES = 8;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+
+struct SortTemp {
+  uint32_t* hist;     // [SORT_MAX_PASSES][256]  digit counts -> exclusive bases
+  uint32_t* tickets;  // [SORT_MAX_PASSES]       dynamic tile ids
+  uint32_t* status;   // [passes][ntiles][256]   decoupled look-back words
+};
+inline int sort_passes(int end_bit) { return (end_bit + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS; }
+inline size_t sort_num_tiles(long long n) { return (size_t)((n + SORT_TILE - 1) / SORT_TILE); }
+size_t sort_temp_bytes(long long n, int passes);
+void carve_sort_temp(char* base, long long n, int passes, SortTemp& t);
+// zero hist/tickets/status (one memset)
+void sort_temp_reset(char* base, long long n, int passes, cudaStream_t stream);
+
+// keys generated + per-digit histograms accumulated in one kernel
+void launch_duplicate_with_keys(int P, const GeometryView& g, uint64_t* keys, uint32_t* vals, uint32_t grid_x,
+                                int end_bit, uint32_t* hist /* may be null: keys only */, cudaStream_t stream);
+// histogram of existing keys (stand-alone sort entry)
+void launch_sort_histogram(const uint64_t* keys, long long n, int end_bit, uint32_t* hist, cudaStream_t stream);
+// exclusive scan of the histograms + all onesweep passes; returns index (0/1) of the buffer holding the result
+int launch_onesweep(uint64_t* keys[2], uint32_t* vals[2], long long n, int end_bit, const SortTemp& t, cudaStream_t stream);
+void launch_identify_tile_ranges(long long n, const uint64_t* keys, uint2* ranges, int num_tiles, cudaStream_t stream);
+
+// ---- blending (render.cu)
+struct RenderParams {
+  int W, H;
+  uint32_t grid_x, grid_y;
+  const uint2* ranges;
+  const uint32_t* point_list;
+  const float2* means2D;
+  const float4* conic_opacity;
+  const float4* rgbd;        // geometry rgb + depth, or depth-only w when colours are precomputed
+  const float* colors_precomp;  // null unless the caller supplied colours
+  const float* bg;
+  float* out_color;
+  float* out_depth;
+  float* out_alpha;
+  uint32_t* n_contrib;
+  int* n_touched;            // may be null
+};
+void launch_render_fwd(const RenderParams& p, cudaStream_t stream);
+
+struct RenderBwdParams {
+  int W, H;
+  uint32_t grid_x, grid_y;
+  const uint2* ranges;
+  const uint32_t* point_list;
+  const float2* means2D;
+  const float4* conic_opacity;
+  const float4* rgbd;
+  const float* colors_precomp;
+  const float* bg;
+  const float* out_alpha;
+  const uint32_t* n_contrib;
+  const float* dL_dpix;
+  const float* dL_ddepth;
+  const float* dL_dalpha;
+  float* grad_acc;           // [P][12]: mean2D.xy, conic.xyw, opacity, rgb, depth, pad, pad
+};
+void launch_render_bwd(const RenderBwdParams& p, cudaStream_t stream);
+
+// ---- preprocess backward (backward_pre.cu)
+struct PreBwdParams {
+  int P, D, M, W, H;
+  const float* means3D;
+  const int* radii;
+  const float* shs;
+  const float* scales;
+  const float* rotations;
+  const float* cov3D_precomp;
+  const float* viewmatrix;
+  const float* projmatrix;
+  const float* projmatrix_raw;  // pose mode only
+  const float* campos;
+  float scale_modifier, tan_fovx, tan_fovy, focal_x, focal_y;
+  GeometryView geom;
+  float* dL_dmean2D;   // [P,3]
+  float* dL_dconic;    // [P,4]
+  float* dL_dopacity;  // [P]
+  float* dL_dcolor;    // [P,3]
+  float* dL_dmean3D;   // [P,3]
+  float* dL_dcov3D;    // [P,6]
+  float* dL_dsh;       // [P,M,3]
+  float* dL_dscale;    // [P,3]
+  float* dL_drot;      // [P,4]
+  float* dL_dtau;      // [6] or null
+};
+void launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream);
+
+}  // namespace gsr

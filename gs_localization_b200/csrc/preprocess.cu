@@ -1,0 +1,331 @@
+// Forward preprocess fused with the tile-count prefix sum (one kernel, one pass over the map).
+//
+// Replaces, from the reference (gaussian_splatting/submodules/diff-gaussian-rasterization):
+//   preprocessCUDA            cuda_rasterizer/forward.cu:155-256
+//   in_frustum                cuda_rasterizer/auxiliary.h:139-164
+//   computeCov3D / Cov2D      cuda_rasterizer/forward.cu:118-152, 74-113
+//   computeColorFromSH        cuda_rasterizer/forward.cu:20-71
+//   cub::DeviceScan::InclusiveSum + its temp storage   cuda_rasterizer/rasterizer_impl.cu:278
+//   checkFrustum              cuda_rasterizer/rasterizer_impl.cu:54-66
+//
+// B200 design: 256 Gaussians per CTA; means are staged through shared memory with 128-bit
+// coalesced loads (the reference issues stride-3 scalar loads); the per-CTA tile-count sum
+// is chained across CTAs with a decoupled look-back (single pass, Merrill & Garland) so the
+// separate scan kernel, its 4P+4P bytes of traffic and its temp buffer disappear; CTA order
+// is taken from an atomic ticket so look-back never waits on an unscheduled CTA.
+// Arithmetic that decides binning is pinned with IEEE intrinsics to the reference's sm_100a
+// rounding sequence (gsr_common.cuh).
+#include "gsr_kernels.cuh"
+
+namespace gsr {
+
+__device__ __forceinline__ void compute_cov3D(const float3 scale, float mod, const float4 rot, float* cov3D) {
+  // reference forward.cu:118-152; rounding per oracle/_ref/forward.sass 0x0a50-0x0ef0
+  const float sx = __fmul_rn(scale.x, mod), sy = __fmul_rn(scale.y, mod), sz = __fmul_rn(scale.z, mod);
+  const float r = rot.x, x = rot.y, y = rot.z, z = rot.w;  // unnormalised (forward.cu:127)
+  const float xz = __fmul_rn(x, z), rx = __fmul_rn(r, x), rz = __fmul_rn(r, z);
+  const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+  const float xz_p_ry = __fmaf_rn(r, y, xz), xz_m_ry = __fmaf_rn(-r, y, xz);
+  const float yz_m_rx = __fmaf_rn(y, z, -rx), yz_p_rx = __fmaf_rn(y, z, rx);
+  const float xy_m_rz = __fmaf_rn(x, y, -rz), xy_p_rz = __fmaf_rn(x, y, rz);
+  const float xx_p_yy = __fmaf_rn(x, x, yy), yy_p_zz = __fadd_rn(yy, zz), xx_p_zz = __fmaf_rn(x, x, zz);
+  const float R00 = __fadd_rn(1.f, -__fadd_rn(yy_p_zz, yy_p_zz));
+  const float R11 = __fadd_rn(1.f, -__fadd_rn(xx_p_zz, xx_p_zz));
+  const float R22 = __fadd_rn(1.f, -__fadd_rn(xx_p_yy, xx_p_yy));
+  // M = S*R (glm, column-major): entry (col j, row i) = s_i * R[j][i].  The reference also adds
+  // 0*x terms of the diagonal S; for finite inputs they only affect the sign of zero.
+  const float m00 = __fmul_rn(sx, R00), m01 = __fmul_rn(sx, __fadd_rn(xy_p_rz, xy_p_rz)),
+              m02 = __fmul_rn(sx, __fadd_rn(xz_m_ry, xz_m_ry));
+  const float m10 = __fmul_rn(sy, __fadd_rn(xy_m_rz, xy_m_rz)), m11 = __fmul_rn(sy, R11),
+              m12 = __fmul_rn(sy, __fadd_rn(yz_p_rx, yz_p_rx));
+  const float m20 = __fmul_rn(sz, __fadd_rn(xz_p_ry, xz_p_ry)), m21 = __fmul_rn(sz, __fadd_rn(yz_m_rx, yz_m_rx)),
+              m22 = __fmul_rn(sz, R22);
+  cov3D[0] = dot3c(m00, m00, m10, m10, m20, m20);
+  cov3D[1] = dot3c(m00, m01, m10, m11, m20, m21);
+  cov3D[2] = dot3c(m00, m02, m10, m12, m20, m22);
+  cov3D[3] = dot3c(m01, m01, m11, m11, m21, m21);
+  cov3D[4] = dot3c(m01, m02, m11, m12, m21, m22);
+  cov3D[5] = dot3c(m02, m02, m12, m12, m22, m22);
+}
+
+// reference forward.cu:74-113; rounding per oracle/_ref/forward.sass 0x1040-0x1a90
+__device__ __forceinline__ float3 compute_cov2D(float tx, float ty, float tz, float focal_x, float focal_y,
+                                                float tan_fovx, float tan_fovy, const float* c, const float* vm) {
+  const float limx = __fmul_rn(1.3f, tan_fovx), limy = __fmul_rn(1.3f, tan_fovy);
+  const float txtz = __fdiv_rn(tx, tz), tytz = __fdiv_rn(ty, tz);
+  const float cxv = fminf(fmaxf(txtz, -limx), limx), cyv = fminf(fmaxf(tytz, -limy), limy);
+  tx = __fmul_rn(cxv, tz);
+  ty = __fmul_rn(cyv, tz);
+  const float tz2 = __fmul_rn(tz, tz);
+  const float J00 = __fdiv_rn(focal_x, tz), J02 = __fdiv_rn(__fmul_rn(-tx, focal_x), tz2);
+  const float J11 = __fdiv_rn(focal_y, tz), J12 = __fdiv_rn(__fmul_rn(-ty, focal_y), tz2);
+  float T0[3], T1[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float W0 = vm[4 * i + 0], W1 = vm[4 * i + 1], W2 = vm[4 * i + 2];
+    // reference: W0*J00 + W1*0 + W2*J02 and W0*0 + W1*J11 + W2*J12 (zero terms dropped: finite inputs)
+    T0[i] = __fmaf_rn(W2, J02, __fmul_rn(W0, J00));
+    T1[i] = __fmaf_rn(W2, J12, __fmul_rn(W1, J11));
+  }
+  const float V[3][3] = {{c[0], c[1], c[2]}, {c[1], c[3], c[4]}, {c[2], c[4], c[5]}};
+  float A0[3], A1[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    A0[j] = dot3c(T0[0], V[0][j], T0[1], V[1][j], T0[2], V[2][j]);
+    A1[j] = dot3c(T1[0], V[0][j], T1[1], V[1][j], T1[2], V[2][j]);
+  }
+  float3 cov;
+  cov.x = __fadd_rn(dot3c(A0[0], T0[0], A0[1], T0[1], A0[2], T0[2]), 0.3f);
+  cov.y = dot3c(A1[0], T0[0], A1[1], T0[1], A1[2], T0[2]);
+  cov.z = __fadd_rn(dot3c(A1[0], T1[0], A1[1], T1[1], A1[2], T1[2]), 0.3f);
+  return cov;
+}
+
+// reference forward.cu:20-71.  `sh` points at this Gaussian's M*3 coefficients.
+template <bool VEC4>
+__device__ __forceinline__ float3 color_from_sh(int deg, int M, float3 pos, float3 campos, const float* __restrict__ sh,
+                                                uint8_t& clamp_mask) {
+  float3 dir = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
+  const float len = sqrtf(__fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.x, dir.x, dir.y * dir.y)));
+  const float x = dir.x / len, y = dir.y / len, z = dir.z / len;
+  float c[48];
+  const int n = (deg == 0 ? 1 : deg == 1 ? 4 : deg == 2 ? 9 : 16) * 3;
+  if (VEC4) {
+    const float4* s4 = reinterpret_cast<const float4*>(sh);
+#pragma unroll
+    for (int q = 0; q < 12; q++) {
+      if (q * 4 < n) {
+        const float4 v = __ldg(s4 + q);
+        c[4 * q] = v.x, c[4 * q + 1] = v.y, c[4 * q + 2] = v.z, c[4 * q + 3] = v.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 48; q++)
+      if (q < n) c[q] = __ldg(sh + q);
+  }
+  (void)M;
+  float res[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    float r = SH_C0 * c[ch];
+    if (deg > 0) {
+      r = r - SH_C1 * y * c[3 + ch] + SH_C1 * z * c[6 + ch] - SH_C1 * x * c[9 + ch];
+      if (deg > 1) {
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        r = r + SH_C2[0] * xy * c[12 + ch] + SH_C2[1] * yz * c[15 + ch] + SH_C2[2] * (2.0f * zz - xx - yy) * c[18 + ch] +
+            SH_C2[3] * xz * c[21 + ch] + SH_C2[4] * (xx - yy) * c[24 + ch];
+        if (deg > 2) {
+          r = r + SH_C3[0] * y * (3.0f * xx - yy) * c[27 + ch] + SH_C3[1] * xy * z * c[30 + ch] +
+              SH_C3[2] * y * (4.0f * zz - xx - yy) * c[33 + ch] +
+              SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * c[36 + ch] +
+              SH_C3[4] * x * (4.0f * zz - xx - yy) * c[39 + ch] + SH_C3[5] * z * (xx - yy) * c[42 + ch] +
+              SH_C3[6] * x * (xx - 3.0f * yy) * c[45 + ch];
+        }
+      }
+    }
+    r += 0.5f;
+    res[ch] = r;
+  }
+  clamp_mask = (res[0] < 0 ? 1 : 0) | (res[1] < 0 ? 2 : 0) | (res[2] < 0 ? 4 : 0);
+  return make_float3(fmaxf(res[0], 0.f), fmaxf(res[1], 0.f), fmaxf(res[2], 0.f));
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreprocessParams p) {
+  __shared__ uint32_t s_block;
+  __shared__ uint32_t s_warp_sum[PRE_THREADS / 32];
+  __shared__ uint32_t s_prefix;
+  __shared__ __align__(16) float s_means[PRE_THREADS * 3];
+  __shared__ float s_cam[16 + 16 + 4];
+
+  const int tid = threadIdx.x;
+  if (tid == 0) s_block = atomicAdd(&p.geom.counters[0], 1u);  // ticket = processing order
+  if (tid < 16) s_cam[tid] = p.viewmatrix[tid];
+  else if (tid < 32) s_cam[tid] = p.projmatrix[tid - 16];
+  else if (tid < 35) s_cam[tid] = p.campos[tid - 32];
+  __syncthreads();
+  const uint32_t block = s_block;
+  const int base = (int)block * PRE_THREADS;
+  const int idx = base + tid;
+  const int P = p.P;
+
+  // ---- stage the CTA's means with coalesced 128-bit loads
+  {
+    const int nflt = min(PRE_THREADS, P - base) * 3;
+    const float* src = p.means3D + (size_t)base * 3;
+    if (ALIGNED) {
+      const int nv = nflt >> 2;
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      for (int i = tid; i < nv; i += PRE_THREADS) reinterpret_cast<float4*>(s_means)[i] = __ldg(s4 + i);
+      for (int i = (nv << 2) + tid; i < nflt; i += PRE_THREADS) s_means[i] = __ldg(src + i);
+    } else {
+      for (int i = tid; i < nflt; i += PRE_THREADS) s_means[i] = __ldg(src + i);
+    }
+  }
+  __syncthreads();
+
+  uint32_t tiles = 0;
+  int radius = 0;
+  if (idx < P) {
+    const float* vm = s_cam;
+    const float* pm = s_cam + 16;
+    const float px = s_means[3 * tid], py = s_means[3 * tid + 1], pz = s_means[3 * tid + 2];
+    // in_frustum: p_view.z <= 0.2 culls (NaN culls too)
+    const float vz = __fadd_rn(dot3c(px, vm[2], py, vm[6], pz, vm[10]), vm[14]);
+    if (vz > 0.2f) {
+      const float vx = __fadd_rn(dot3c(px, vm[0], py, vm[4], pz, vm[8]), vm[12]);
+      const float vy = __fadd_rn(dot3c(px, vm[1], py, vm[5], pz, vm[9]), vm[13]);
+      const float hx = __fadd_rn(dot3c(px, pm[0], py, pm[4], pz, pm[8]), pm[12]);
+      const float hy = __fadd_rn(dot3c(px, pm[1], py, pm[5], pz, pm[9]), pm[13]);
+      const float hw = __fadd_rn(dot3c(px, pm[3], py, pm[7], pz, pm[11]), pm[15]);
+      const float p_w = __frcp_rn(__fadd_rn(hw, 0.0000001f));
+      const float projx = __fmul_rn(hx, p_w), projy = __fmul_rn(hy, p_w);
+
+      float cov3D[6];
+      if (p.cov3D_precomp) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) cov3D[k] = __ldg(p.cov3D_precomp + 6 * (size_t)idx + k);
+      } else {
+        const float3 sc = {__ldg(p.scales + 3 * (size_t)idx), __ldg(p.scales + 3 * (size_t)idx + 1),
+                           __ldg(p.scales + 3 * (size_t)idx + 2)};
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+        compute_cov3D(sc, p.scale_modifier, q, cov3D);
+      }
+      const float3 cov = compute_cov2D(vx, vy, vz, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy, cov3D, vm);
+      const float det = __fmaf_rn(cov.x, cov.z, -__fmul_rn(cov.y, cov.y));
+      if (det != 0.0f) {
+        const float det_inv = __frcp_rn(det);
+        const float3 conic = {__fmul_rn(cov.z, det_inv), __fmul_rn(cov.y, -det_inv), __fmul_rn(cov.x, det_inv)};
+        const float mid = __fmul_rn(__fadd_rn(cov.x, cov.z), 0.5f);
+        const float s = __fsqrt_rn(fmaxf(__fmaf_rn(mid, mid, -det), 0.1f));
+        const float lambda1 = __fadd_rn(mid, s), lambda2 = __fadd_rn(mid, -s);
+        const int my_radius = __float2int_ru(__fmul_rn(__fsqrt_rn(fmaxf(lambda1, lambda2)), 3.0f));
+        // ndc2Pix in double with one DFMA (auxiliary.h:41-44)
+        const float pix_x = (float)(__dmul_rn(__fma_rn(__dadd_rn((double)projx, 1.0), (double)p.W, -1.0), 0.5));
+        const float pix_y = (float)(__dmul_rn(__fma_rn(__dadd_rn((double)projy, 1.0), (double)p.H, -1.0), 0.5));
+        // getRect (auxiliary.h:46-56)
+        const float rf = (float)my_radius;
+        const uint32_t gx = p.grid_x, gy = p.grid_y;
+        const uint32_t minx = min(gx, (uint32_t)max(0, __float2int_rz(__fmul_rn(__fadd_rn(pix_x, -rf), 0.0625f))));
+        const uint32_t miny = min(gy, (uint32_t)max(0, __float2int_rz(__fmul_rn(__fadd_rn(pix_y, -rf), 0.0625f))));
+        const uint32_t maxx = min(gx, (uint32_t)max(0, __float2int_rz(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(pix_x, rf), 16.0f), -1.0f), 0.0625f))));
+        const uint32_t maxy = min(gy, (uint32_t)max(0, __float2int_rz(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(pix_y, rf), 16.0f), -1.0f), 0.0625f))));
+        const uint32_t cnt = (maxx - minx) * (maxy - miny);
+        if (cnt != 0) {
+          float3 rgb;
+          uint8_t cm = 0;
+          if (p.colors_precomp) {
+            rgb = make_float3(__ldg(p.colors_precomp + 3 * (size_t)idx), __ldg(p.colors_precomp + 3 * (size_t)idx + 1),
+                              __ldg(p.colors_precomp + 3 * (size_t)idx + 2));
+          } else {
+            const float3 cp = {s_cam[32], s_cam[33], s_cam[34]};
+            const float* sh = p.shs + (size_t)idx * p.M * 3;
+            if (p.sh_vec4) rgb = color_from_sh<true>(p.D, p.M, make_float3(px, py, pz), cp, sh, cm);
+            else rgb = color_from_sh<false>(p.D, p.M, make_float3(px, py, pz), cp, sh, cm);
+          }
+          if (!p.cov3D_precomp) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) p.geom.cov3D[6 * (size_t)idx + k] = cov3D[k];
+          }
+          p.geom.depths[idx] = vz;
+          p.geom.means2D[idx] = make_float2(pix_x, pix_y);
+          p.geom.conic_opacity[idx] = make_float4(conic.x, conic.y, conic.z, __ldg(p.opacities + idx));
+          p.geom.rgbd[idx] = make_float4(rgb.x, rgb.y, rgb.z, vz);
+          p.geom.rect[idx] = make_uint2(minx | (maxx << 16), miny | (maxy << 16));
+          p.geom.clamped[idx] = cm;
+          tiles = cnt;
+          radius = my_radius;
+        }
+      }
+    } else if (p.prefiltered) {
+      // reference auxiliary.h:156-160
+      printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+      __trap();
+    }
+    p.radii[idx] = radius;
+    p.geom.tiles_touched[idx] = tiles;
+    if (p.n_touched) p.n_touched[idx] = 0;
+  }
+
+  // ---- CTA inclusive scan of `tiles`
+  const uint32_t lane = tid & 31, warp = tid >> 5;
+  uint32_t incl = tiles;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) s_warp_sum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t ws = lane < PRE_THREADS / 32 ? s_warp_sum[lane] : 0;
+    uint32_t wincl = ws;
+#pragma unroll
+    for (int o = 1; o < PRE_THREADS / 32; o <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, wincl, o);
+      if (lane >= o) wincl += n;
+    }
+    if (lane < PRE_THREADS / 32) s_warp_sum[lane] = wincl - ws;  // exclusive warp offsets
+    const uint32_t block_total = __shfl_sync(0xffffffffu, wincl, PRE_THREADS / 32 - 1);
+
+    // ---- decoupled look-back across CTAs (status word = flag<<32 | value; 1 aggregate, 2 inclusive)
+    volatile unsigned long long* status = p.geom.scan_status;
+    uint32_t exclusive = 0;
+    if (block == 0) {
+      if (lane == 0) status[0] = (2ull << 32) | block_total;
+    } else {
+      if (lane == 0) status[block] = (1ull << 32) | block_total;
+      int look = (int)block - 1;
+      while (true) {
+        const int j = look - (int)lane;
+        unsigned long long w = j >= 0 ? status[j] : (2ull << 32);
+        // wait until every word in the window is published
+        while (__any_sync(0xffffffffu, (w >> 32) == 0)) {
+          if ((w >> 32) == 0) w = status[j];
+        }
+        const uint32_t incl_mask = __ballot_sync(0xffffffffu, (w >> 32) == 2);
+        const uint32_t upto = incl_mask ? (uint32_t)(__ffs(incl_mask) - 1) : 31u;  // first inclusive lane
+        uint32_t v = lane <= upto ? (uint32_t)w : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        exclusive += v;
+        if (incl_mask) break;
+        look -= 32;
+      }
+      if (lane == 0) status[block] = (2ull << 32) | (unsigned long long)(exclusive + block_total);
+    }
+    if (lane == 0) {
+      s_prefix = exclusive;
+      if (block == gridDim.x - 1) p.geom.counters[1] = exclusive + block_total;  // num_rendered
+    }
+  }
+  __syncthreads();
+  if (idx < P) p.geom.point_offsets[idx] = s_prefix + s_warp_sum[warp] + incl;
+}
+
+void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream) {
+  const int blocks = num_pre_blocks(p.P);
+  const bool aligned = ((uintptr_t)p.means3D % 16) == 0;
+  if (aligned) preprocess_fwd_kernel<true><<<blocks, PRE_THREADS, 0, stream>>>(p);
+  else preprocess_fwd_kernel<false><<<blocks, PRE_THREADS, 0, stream>>>(p);
+  count_launch();
+}
+
+// reference rasterizer_impl.cu:54-66 (checkFrustum): present[i] = p_view.z > 0.2
+__global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D,
+                                                           const float* __restrict__ vm, uint8_t* __restrict__ present) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const float px = __ldg(means3D + 3 * (size_t)idx), py = __ldg(means3D + 3 * (size_t)idx + 1),
+              pz = __ldg(means3D + 3 * (size_t)idx + 2);
+  const float vz = __fadd_rn(dot3c(px, __ldg(vm + 2), py, __ldg(vm + 6), pz, __ldg(vm + 10)), __ldg(vm + 14));
+  present[idx] = vz > 0.2f ? 1 : 0;
+}
+
+void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream) {
+  mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, present);
+  count_launch();
+}
+
+}  // namespace gsr

@@ -1,0 +1,151 @@
+/*
+ * gsr_b200.h — C ABI of the B200-native differentiable 3D-Gaussian-splatting rasterizer.
+ *
+ * Drop-in boundary for the hot path of RPL-CS-UCL/gs_localization (LoGS): the depth+alpha
+ * fork of diff-gaussian-rasterization.  Every entry point replaces one host entry of the
+ * reference's native library; citations are relative to
+ *   gaussian_splatting/submodules/diff-gaussian-rasterization/
+ *
+ * Conventions (same as the reference, rasterize_points.cu:96-115):
+ *   - all pointers are DEVICE pointers to contiguous float32 / int32 data unless stated;
+ *   - absent optional inputs are NULL (the reference passes the data pointer of an empty tensor);
+ *   - matrices are 4x4 in the transposed storage the reference uses (scene/cameras.py:56-59);
+ *   - the caller owns all memory.  Scratch is three opaque byte buffers ("geometry",
+ *     "binning", "image") that the forward sizes through caller-supplied allocation
+ *     callbacks and the backward re-reads, exactly like the reference's
+ *     std::function<char*(size_t)> resize callbacks (cuda_rasterizer/rasterizer.h:24-27,
+ *     rasterize_points.cu:27-33).  Their layout is private to this library;
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream, which is what the
+ *     reference always uses).
+ *
+ * There is no CPU fallback: every function launches sm_100a kernels or fails.
+ */
+#ifndef GSR_B200_H_
+#define GSR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define GSR_API __attribute__((visibility("default")))
+#else
+#define GSR_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_ABI_VERSION 1
+
+/* error codes (negative return values) */
+#define GSR_OK 0
+#define GSR_ERR_INVALID_ARGUMENT (-1) /* reference: AT_ERROR in rasterize_points.cu:57-59 */
+#define GSR_ERR_CUDA (-2)             /* reference: CHECK_CUDA throw, auxiliary.h:166-173 */
+#define GSR_ERR_ALLOC (-3)            /* an allocation callback returned NULL */
+#define GSR_ERR_UNSUPPORTED (-4)      /* reference: "For non-RGB, provide precomputed Gaussian colors!" rasterizer_impl.cu:243-246 */
+
+/* Scratch allocation callback: must return a device pointer to at least `bytes` bytes,
+ * 128-byte aligned, that stays valid until the matching backward has run.
+ * Mirrors std::function<char*(size_t N)> (rasterizer.h:24-27). */
+typedef char* (*gsr_alloc_fn)(size_t bytes, void* user);
+
+GSR_API int gsr_abi_version(void);
+/* Human-readable description of the last error on the calling thread. */
+GSR_API const char* gsr_last_error(void);
+/* Number of kernels this library has launched since load (all threads). bench.py's gpu_launches. */
+GSR_API unsigned long long gsr_launch_count(void);
+
+/* Scratch sizes.  Replace CudaRasterizer::required<GeometryState|ImageState|BinningState>
+ * (rasterizer_impl.h:66-72).  The forward calls the callbacks with exactly these values. */
+GSR_API size_t gsr_geometry_bytes(int P);
+GSR_API size_t gsr_image_bytes(int width, int height);
+GSR_API size_t gsr_binning_bytes(long long num_rendered, int width, int height);
+
+/*
+ * Forward.  Replaces CudaRasterizer::Rasterizer::forward (rasterizer_impl.cu:197-339,
+ * declared rasterizer.h:35-60) as called from RasterizeGaussiansCUDA (rasterize_points.cu:86-116).
+ *
+ *   P, D, M            number of Gaussians, active SH degree, SH coefficients stored per Gaussian
+ *   background[3], means3D[P,3], shs[P,M,3] | colors_precomp[P,3], opacities[P],
+ *   scales[P,3] + rotations[P,4] | cov3D_precomp[P,6], viewmatrix[16], projmatrix[16], cam_pos[3]
+ *   out_color[3,H,W], out_depth[1,H,W], out_alpha[1,H,W], radii[P] (int32)
+ *   n_touched[P] (int32, may be NULL): pose-variant extra output
+ *
+ * Returns num_rendered (>= 0) — the number of (Gaussian, tile) instances — or a negative
+ * error code.  Like the reference it synchronises `stream` once to learn num_rendered
+ * (rasterizer_impl.cu:282) before sizing the binning buffer.
+ */
+GSR_API long long gsr_rasterize_forward(
+    gsr_alloc_fn geometry_alloc, gsr_alloc_fn binning_alloc, gsr_alloc_fn image_alloc, void* user,
+    int P, int D, int M,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+    const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+    float tan_fovx, float tan_fovy, int prefiltered,
+    float* out_color, float* out_depth, float* out_alpha, int* radii, int* n_touched,
+    int debug, void* stream);
+
+/*
+ * Backward.  Replaces CudaRasterizer::Rasterizer::backward (rasterizer_impl.cu:343-444,
+ * declared rasterizer.h:62-88) as called from RasterizeGaussiansBackwardCUDA
+ * (rasterize_points.cu:170-203).
+ *
+ * Gradient outputs are written densely for ALL P Gaussians (invisible ones get zeros), so
+ * the caller does NOT need to zero-fill them first (the reference needs nine torch::zeros,
+ * rasterize_points.cu:158-166).  Any output pointer may be NULL to skip that gradient.
+ *   dL_dmean2D[P,3], dL_dconic[P,4] (x,y,_,w as the reference's float4), dL_dopacity[P],
+ *   dL_dcolor[P,3], dL_dmean3D[P,3], dL_dcov3D[P,6], dL_dsh[P,M,3], dL_dscale[P,3], dL_drot[P,4]
+ *
+ * Pose extension (diff_gaussian_rasterization_pose surface used by
+ * gs_localization/pipelines/tools/__init__.py:58-141): when dL_dtau is non-NULL, six floats
+ * [d/drho(3), d/dtheta(3)] of the loss w.r.t. the left perturbation T_w2c <- exp(tau) T_w2c
+ * (tools/pose_utils.py:90-122) are written there; projmatrix_raw (transposed storage) is then
+ * required.
+ */
+GSR_API int gsr_rasterize_backward(
+    int P, int D, int M, long long num_rendered,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp, const float* out_alpha,
+    const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* projmatrix_raw, const float* cam_pos,
+    float tan_fovx, float tan_fovy, const int* radii,
+    char* geometry_buffer, char* binning_buffer, char* image_buffer,
+    const float* dL_dpix, const float* dL_ddepth, const float* dL_dalpha,
+    float* dL_dmean2D, float* dL_dconic, float* dL_dopacity, float* dL_dcolor,
+    float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot,
+    float* dL_dtau,
+    int debug, void* stream);
+
+/* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer_impl.cu:141-153): present[i] = z_view > 0.2. */
+GSR_API int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     unsigned char* present, void* stream);
+
+/*
+ * Introspection for parity tests (not on the hot path): copy the library's private
+ * intermediates out of the scratch buffers in the REFERENCE's formats
+ * (GeometryState / BinningState / ImageState, rasterizer_impl.h:29-64).  Any pointer may be NULL.
+ *   depths[P] means2D[P,2] cov3D[P,6] conic_opacity[P,4] rgb[P,3] clamped[P,3](u8)
+ *   tiles_touched[P] point_offsets[P]; keys_unsorted[R] list_unsorted[R] keys[R] list[R];
+ *   ranges[T,2] n_contrib[H*W]
+ */
+GSR_API int gsr_export_state(
+    int P, long long num_rendered, int width, int height,
+    const char* geometry_buffer, const char* binning_buffer, const char* image_buffer,
+    float* depths, float* means2D, float* cov3D, float* conic_opacity, float* rgb, unsigned char* clamped,
+    uint32_t* tiles_touched, uint32_t* point_offsets,
+    uint64_t* keys_unsorted, uint32_t* list_unsorted, uint64_t* keys, uint32_t* list,
+    uint32_t* ranges, uint32_t* n_contrib, void* stream);
+
+/* Stand-alone stable LSD radix sort of (u64 key, u32 value) pairs on bits [0, end_bit) —
+ * the hand-written onesweep that replaces cub::DeviceRadixSort::SortPairs
+ * (rasterizer_impl.cu:304-309).  temp must hold gsr_sort_temp_bytes(n) bytes. */
+GSR_API size_t gsr_sort_temp_bytes(long long n);
+GSR_API int gsr_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out,
+                   uint64_t* keys_tmp, uint32_t* vals_tmp, long long n, int end_bit, char* temp, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSR_B200_H_ */
