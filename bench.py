@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py — fwd+bwd rasterize iterations/s of the LoGS rasterizer hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload headline]
+
+Metric (BASELINE.json): forward+backward rasterize iterations per second at 1M Gaussians,
+640x480, SH degree 3 (the "headline" workload; other BASELINE configs are parity-test cases).
+One *step* = one pose-refinement style iteration: rasterize forward -> L1 loss gradient ->
+rasterize backward (all per-Gaussian gradients, like the reference computes them).
+
+  value   whole-job iterations/s with the map, cameras and target images already resident in
+          HBM, called through the `_C` C-ABI layer, timed with CUDA events on the launching stream.
+  e2e     the same metric through the public API (GaussianRasterizer + autograd) with HOST inputs:
+          every step copies that step's camera matrices and target image from pinned host memory
+          and reads the loss back; wall clock, synchronised on both sides.
+  N > 1   one process per GPU (torchrun), the map replicated, independent query poses per rank,
+          no collective on the data path: weak scaling, value = sum over ranks.
+
+`--impl reference` runs the UNMODIFIED reference CUDA rasterizer built by oracle/build_ref.sh
+(oracle/_ref) through its own Python API on the same GPU, same workload.  If that build is
+absent it times the CPU oracle port instead.  Both arms attach `cpu_baseline`: the CPU oracle
+(oracle/gsr_oracle.cpp, a port of the same math) timed on the host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from gs_localization_b200 import synthetic as syn  # noqa: E402
+
+N_POSES = 8  # distinct query cameras cycled through per rank
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="headline", choices=list(syn.CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stage-split", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- clocks sampling
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- workload
+def build_workload(name, rank, device):
+    cfg = syn.CONFIGS[name]
+    gmap = syn.make_map(cfg["P"], cfg["deg"], cfg["sigma0"], cfg["box"], seed=0)
+    cams = [syn.make_camera(cfg, rank * N_POSES + q).perturbed(syn.initial_perturbation(rank * N_POSES + q))
+            for q in range(N_POSES)]
+    dmap = gmap.to(device) if device is not None else gmap
+    return cfg, gmap, dmap, cams
+
+
+def l1_grad(color, target):
+    # d/dcolor of mean |color - target|
+    return torch.sign(color - target) / color.numel()
+
+
+class Arm:
+    """One implementation (ours / reference) behind the same two call shapes."""
+
+    def __init__(self, impl, device):
+        self.impl = impl
+        self.device = device
+        if impl == "ours":
+            import gs_localization_b200.diff_gaussian_rasterization as pkg
+            from gs_localization_b200 import _lib
+            _lib.load()
+            self.lib = _lib
+        else:
+            sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+            import diff_gaussian_rasterization as pkg  # the unmodified reference package
+            sys.path.pop(0)
+            self.lib = None
+        self.pkg = pkg
+        self.C = pkg._C
+
+    def c_forward(self, m, bg, view, proj, campos, cam):
+        e = torch.Tensor([])
+        return self.C.rasterize_gaussians(bg, m.means3D, e, m.opacities, m.scales, m.rotations, 1.0, e, view, proj,
+                                          cam.tanfovx, cam.tanfovy, cam.H, cam.W, m.shs, m.sh_degree, campos, False, False)
+
+    def c_backward(self, m, bg, view, proj, campos, cam, fwd, gC, gD, gA):
+        R, color, depth, alpha, radii, geom, binning, img = fwd
+        e = torch.Tensor([])
+        return self.C.rasterize_gaussians_backward(bg, m.means3D, radii, e, m.scales, m.rotations, 1.0, e, view, proj,
+                                                   cam.tanfovx, cam.tanfovy, gC, gD, gA, m.shs, m.sh_degree, campos, geom, R,
+                                                   binning, img, alpha, False)
+
+
+def run_gpu_arm(args, rank, world, local_rank):
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    arm = Arm(args.impl, device)
+    cfg, gmap, m, cams = build_workload(args.workload, rank, device)
+    H, W = cfg["H"], cfg["W"]
+    bg = torch.zeros(3, device=device)
+    mats = [c.matrices(device) for c in cams]
+    zerosD = torch.zeros(1, H, W, device=device)
+
+    # targets: render at the unperturbed (ground-truth) poses
+    targets = []
+    with torch.no_grad():
+        for q in range(N_POSES):
+            gt = syn.make_camera(cfg, rank * N_POSES + q)
+            v, p, _, c = gt.matrices(device)
+            targets.append(arm.c_forward(m, bg, v, p, c, gt)[1].clone())
+
+    stats = {}
+
+    def step_device(i):
+        q = i % N_POSES
+        view, proj, _, campos = mats[q]
+        fwd = arm.c_forward(m, bg, view, proj, campos, cams[q])
+        gC = l1_grad(fwd[1], targets[q])
+        arm.c_backward(m, bg, view, proj, campos, cams[q], fwd, gC, zerosD, zerosD)
+        return fwd[0]
+
+    # ---- value: device-resident, CUDA events
+    for i in range(args.warmup):
+        step_device(i)
+    torch.cuda.synchronize()
+    launches0 = arm.lib.launch_count() if arm.lib else 0
+    if world > 1:
+        torch.distributed.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    Rs = []
+    for i in range(args.steps):
+        Rs.append(step_device(i))
+    ev1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = (arm.lib.launch_count() - launches0) if arm.lib else 0
+
+    # ---- e2e: public API, host inputs, wall clock
+    settings_cls, raster_cls = arm.pkg.GaussianRasterizationSettings, arm.pkg.GaussianRasterizer
+    host_mats = [[t.cpu().pin_memory() for t in (mt[0], mt[1], mt[3])] for mt in mats]
+    host_targets = [t.cpu().pin_memory() for t in targets]
+    means = m.means3D.clone().requires_grad_(True)
+    shs = m.shs.clone().requires_grad_(True)
+    opac = m.opacities.clone().requires_grad_(True)
+    scales = m.scales.clone().requires_grad_(True)
+    rots = m.rotations.clone().requires_grad_(True)
+    params = [means, shs, opac, scales, rots]
+
+    def step_e2e(i):
+        q = i % N_POSES
+        view = host_mats[q][0].to(device, non_blocking=True)
+        proj = host_mats[q][1].to(device, non_blocking=True)
+        campos = host_mats[q][2].to(device, non_blocking=True)
+        target = host_targets[q].to(device, non_blocking=True)
+        cam = cams[q]
+        rs = settings_cls(image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=bg, scale_modifier=1.0,
+                          viewmatrix=view, projmatrix=proj, sh_degree=m.sh_degree, campos=campos, prefiltered=False, debug=False)
+        means2D = torch.zeros_like(means, requires_grad=True)
+        color, radii, depth, alpha = raster_cls(rs)(means3D=means, means2D=means2D, opacities=opac, shs=shs, scales=scales,
+                                                    rotations=rots)
+        loss = (color - target).abs().mean()
+        loss.backward()
+        for p_ in params:
+            p_.grad = None
+        return float(loss.item())   # device -> host read of the step's result
+
+    for i in range(max(3, args.warmup // 2)):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        torch.distributed.barrier()
+    h2d = (16 + 16 + 3 + 3 * H * W) * 4
+    d2h = 4
+
+    # ---- stage split + roofline of the dominant kernel (ours, rank 0 only; untimed extra passes)
+    roofline, split, workload_stats = None, None, None
+    if args.impl == "ours" and rank == 0 and not args.no_stage_split:
+        arm.lib.stage_timing(True)
+        for i in range(N_POSES * 2):
+            step_device(i)
+        torch.cuda.synchronize()
+        split = arm.lib.stage_times()
+        arm.lib.stage_timing(False)
+        # measured workload statistics for the bytes model
+        q = 0
+        view, proj, _, campos = mats[q]
+        fwd = arm.c_forward(m, bg, view, proj, campos, cams[q])
+        Rq, radii = fwd[0], fwd[4]
+        Pv = int((radii > 0).sum().item())
+        st = arm.C.export_state(cfg["P"], Rq, W, H, fwd[5], fwd[6], fwd[7])
+        n_contrib_sum = int(st["n_contrib"].to(torch.int64).sum().item())
+        rng = st["ranges"].to(torch.int64)
+        workload_stats = dict(P=cfg["P"], Pv=Pv, R=int(Rq), N=W * H, T=int(rng.shape[0]), n_contrib_sum=n_contrib_sum,
+                              mean_n_contrib=n_contrib_sum / (W * H))
+        roofline = make_roofline(split, workload_stats, cfg)
+    stats.update(ms_total=ms_total, clocks=clocks, launches=launches, e2e_s=e2e_s, h2d=h2d, d2h=d2h, split=split,
+                 roofline=roofline, workload_stats=workload_stats, mean_R=sum(Rs) / max(1, len(Rs)))
+    return stats
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def make_roofline(split, ws, cfg):
+    """Roofline of the dominant kernel.  Algorithmic bytes per launch from DESIGN.md §4
+    (SURVEY.md §8d terms restricted to that kernel)."""
+    if not split:
+        return None
+    M = (cfg["deg"] + 1) ** 2
+    P, Pv, R, N, T = ws["P"], ws["Pv"], ws["R"], ws["N"], ws["T"]
+    passes = -(-(32 + max(1, (T - 1).bit_length())) // 8)
+    bytes_per_stage = {
+        "preprocess": 44 * P + 12 * M * Pv + 8 * P + 4 * P + 75 * Pv,        # reads + radii/tiles/offsets + per-visible records
+        "duplicate_with_keys": 8 * P + 16 * Pv + 12 * R,
+        "radix_sort": 24 * passes * R,
+        "tile_ranges": 8 * R + 8 * T,
+        "render": 44 * R + 24 * N,
+        "render_backward": 44 * R + 28 * N + 36 * Pv,
+        "preprocess_backward": 4 * P + (107 + 12 * M) * Pv + (64 + 12 * M) * P,  # dense gradient rows are written for all P
+    }
+    dom = max(split, key=lambda k: split[k])
+    peak, how = measured_peaks()
+    achieved = bytes_per_stage[dom] / (split[dom] * 1e-3) / 1e9 if split[dom] > 0 else 0.0
+    return {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 5), "traffic": None, "peak_source": how,
+            "algorithmic_bytes_per_launch": int(bytes_per_stage[dom]), "ms_per_launch": round(split[dom], 4),
+            "note": "blend kernels re-use each staged splat 256x from shared memory; they are issue/latency bound, "
+                    "so a low HBM fraction is expected (DESIGN.md §4)"}
+
+
+# --------------------------------------------------------------------------- CPU oracle timing
+def cpu_oracle_timing(workload, budget_s=20.0):
+    """The CPU oracle (a port of the reference math) on the host cores: bounded sample."""
+    from oracle.oracle import Oracle, num_threads
+    cfg, gmap, _, cams = build_workload(workload, 0, None)
+    H, W = cfg["H"], cfg["W"]
+    bg = torch.zeros(3)
+    o = Oracle("f32")
+    times = []
+    t_start = time.perf_counter()
+    q = 0
+    while True:
+        cam = cams[q % N_POSES]
+        view, proj, _, campos = cam.matrices()
+        t0 = time.perf_counter()
+        o.forward(bg, gmap.means3D, None, gmap.opacities, gmap.scales, gmap.rotations, 1.0, None, view, proj, cam.tanfovx,
+                  cam.tanfovy, H, W, gmap.shs, gmap.sh_degree, campos)
+        color, _, _ = o.images()
+        g = (torch.sign(torch.from_numpy(color)) / color.size).numpy()
+        o.backward(g, None, None)
+        times.append(time.perf_counter() - t0)
+        q += 1
+        if q >= 2 and (time.perf_counter() - t_start > budget_s or q >= 8):
+            break
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": round(1.0 / med, 4), "unit": "iterations/s", "cores": num_threads(), "kind": "port",
+            "sample": f"{len(times)} full fwd+bwd iterations of the {workload} workload (median), OpenMP oracle/gsr_oracle.cpp"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = syn.CONFIGS[args.workload]
+    config = {"workload": f"{args.workload}: {cfg['P']} Gaussians, {cfg['W']}x{cfg['H']}, SH degree {cfg['deg']}, "
+                          f"{N_POSES} query poses/rank cycled, all per-Gaussian gradients",
+              "l2_policy": "inputs larger than L2 (map = 236 B/Gaussian > 126 MB) and a different camera every step",
+              "parallelism": f"queries sharded over {world} GPU(s), map replicated, no collective"}
+    base = {"metric": "fwd+bwd rasterize iterations/s @1M Gaussians 640x480", "unit": "iterations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config}
+
+    ref_built = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "diff_gaussian_rasterization", "_C.so"))
+    if args.impl == "reference" and not (ref_built and torch.cuda.is_available()):
+        # CPU oracle port as the reference arm (rank 0 only)
+        if rank != 0:
+            return
+        cb = cpu_oracle_timing(args.workload, budget_s=60.0)
+        line = dict(base, impl="reference", value=cb["value"], ms_per_step=round(1e3 / cb["value"], 3), n_gpus=1,
+                    cpu_baseline=cb, gpu_launches=0,
+                    e2e={"value": cb["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: gs_localization_b200 has no CPU fallback")
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    st = run_gpu_arm(args, rank, world, local_rank)
+
+    ms_total, e2e_s = st["ms_total"], st["e2e_s"]
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_total, e2e_s = float(t[0]), float(t[1])
+    if rank == 0:
+        value = world * args.steps / (ms_total * 1e-3)
+        line = dict(base, value=round(value, 3), ms_per_step=round(ms_total / args.steps, 4), clocks=st["clocks"],
+                    e2e={"value": round(world * args.steps / e2e_s, 3), "unit": "iterations/s",
+                         "h2d_bytes_per_step": st["h2d"], "d2h_bytes_per_step": st["d2h"]},
+                    gpu_launches=int(st["launches"]))
+        if args.impl == "reference":
+            line["impl"] = "reference"
+            line["config"]["reference"] = "unmodified reference CUDA rasterizer built for sm_100a (oracle/_ref) on this GPU"
+        if st["roofline"]:
+            line["roofline"] = st["roofline"]
+        if st["split"]:
+            line["stage_ms"] = {k: round(v, 4) for k, v in st["split"].items()}
+        if st["workload_stats"]:
+            line["workload_stats"] = st["workload_stats"]
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_oracle_timing(args.workload)
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

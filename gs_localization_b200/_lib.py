@@ -45,6 +45,8 @@ SIGNATURES = {
         C.c_int, _P]),
     "gsr_mark_visible": (C.c_int, [C.c_int, _P, _P, _P, _P, _P]),
     "gsr_export_state": (C.c_int, [C.c_int, C.c_longlong, C.c_int, C.c_int] + [_P] * 3 + [_P] * 14 + [_P]),
+    "gsr_stage_timing": (None, [C.c_int]),
+    "gsr_stage_times": (C.c_int, [_P, _P, C.c_int]),
     "gsr_sort_temp_bytes": (C.c_size_t, [C.c_longlong]),
     "gsr_sort_pairs": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_longlong, C.c_int, _P, _P]),
 }
@@ -80,6 +82,23 @@ def check(code: int, what: str):
         msg = load().gsr_last_error().decode("utf-8", "replace")
         raise GsrError(f"{what} failed ({code}): {msg}")
     return code
+
+
+STAGES = ("preprocess", "duplicate_with_keys", "radix_sort", "tile_ranges", "render", "render_backward",
+          "preprocess_backward")
+
+
+def stage_timing(enable: bool) -> None:
+    load().gsr_stage_timing(int(bool(enable)))
+
+
+def stage_times() -> dict:
+    """{stage: mean ms per call} accumulated since stage_timing(True)."""
+    n = len(STAGES)
+    ms = (C.c_double * n)()
+    calls = (C.c_ulonglong * n)()
+    load().gsr_stage_times(ms, calls, n)
+    return {STAGES[i]: (ms[i] / calls[i] if calls[i] else 0.0) for i in range(n)}
 
 
 def launch_count() -> int:

@@ -67,6 +67,51 @@ char* carve_binning(char* base, long long R, int W, int H, BinningLayout& b) {
   return p;
 }
 
+// ---- optional per-stage device timing (bench.py's stage split; off on the hot path)
+enum Stage { ST_PREPROCESS, ST_DUPLICATE, ST_SORT, ST_RANGES, ST_RENDER, ST_BWD_RENDER, ST_BWD_PREPROCESS, ST_COUNT };
+struct StageTimer {
+  bool enabled = false;
+  cudaEvent_t ev[ST_COUNT][2] = {};
+  bool used[ST_COUNT] = {};
+  double total_ms[ST_COUNT] = {};
+  unsigned long long calls[ST_COUNT] = {};
+  std::mutex mu;
+};
+StageTimer g_timer;
+
+struct StageScope {
+  int st;
+  cudaStream_t stream;
+  bool on;
+  StageScope(int st_, cudaStream_t s) : st(st_), stream(s), on(g_timer.enabled) {
+    if (!on) return;
+    if (!g_timer.ev[st][0]) {
+      cudaEventCreate(&g_timer.ev[st][0]);
+      cudaEventCreate(&g_timer.ev[st][1]);
+    }
+    cudaEventRecord(g_timer.ev[st][0], stream);
+  }
+  ~StageScope() {
+    if (!on) return;
+    cudaEventRecord(g_timer.ev[st][1], stream);
+    g_timer.used[st] = true;
+  }
+};
+void stage_collect(cudaStream_t stream) {
+  if (!g_timer.enabled) return;
+  cudaStreamSynchronize(stream);
+  std::lock_guard<std::mutex> lk(g_timer.mu);
+  for (int i = 0; i < ST_COUNT; i++) {
+    if (!g_timer.used[i]) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_timer.ev[i][0], g_timer.ev[i][1]) == cudaSuccess) {
+      g_timer.total_ms[i] += ms;
+      g_timer.calls[i]++;
+    }
+    g_timer.used[i] = false;
+  }
+}
+
 // pinned 4-byte mailbox for num_rendered, one per host thread
 uint32_t* pinned_mailbox() {
   thread_local uint32_t* box = nullptr;
@@ -149,7 +194,10 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     pp.prefiltered = prefiltered;
     pp.sh_vec4 = shs && (M % 4 == 0) && ((uintptr_t)shs % 16 == 0);
     pp.radii = radii, pp.n_touched = n_touched, pp.geom = g;
-    launch_preprocess_fwd(pp, stream);
+    {
+      StageScope ts(ST_PREPROCESS, stream);
+      launch_preprocess_fwd(pp, stream);
+    }
     GSR_STAGE("preprocess", debug, stream);
 
     // num_rendered -> host (the one sync the reference also has, rasterizer_impl.cu:282)
@@ -168,10 +216,16 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     const int passes = sort_passes(end_bit);
     SortTemp st;
     carve_sort_temp(bl.sort_temp, R, passes, st);
-    sort_temp_reset(bl.sort_temp, R, passes, stream);
-    launch_duplicate_with_keys(P, g, bl.keys[0], bl.vals[0], gx, end_bit, st.hist, stream);
+    {
+      StageScope ts(ST_DUPLICATE, stream);
+      sort_temp_reset(bl.sort_temp, R, passes, stream);
+      launch_duplicate_with_keys(P, g, bl.keys[0], bl.vals[0], gx, end_bit, st.hist, stream);
+    }
     GSR_STAGE("duplicate_with_keys", debug, stream);
-    final_buf = launch_onesweep(bl.keys, bl.vals, R, end_bit, st, stream);
+    {
+      StageScope ts(ST_SORT, stream);
+      final_buf = launch_onesweep(bl.keys, bl.vals, R, end_bit, st, stream);
+    }
     GSR_STAGE("radix_sort", debug, stream);
   } else {
     // keep the callback contract: the binning buffer exists (possibly tiny) even when nothing is visible
@@ -179,7 +233,10 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     if (!bin_base) return fail(GSR_ERR_ALLOC, "binning_alloc returned NULL");
     carve_binning(bin_base, 0, width, height, bl);
   }
-  launch_identify_tile_ranges(R, bl.keys[final_buf], im.ranges, T, stream);
+  {
+    StageScope ts(ST_RANGES, stream);
+    launch_identify_tile_ranges(R, bl.keys[final_buf], im.ranges, T, stream);
+  }
   GSR_STAGE("identify_tile_ranges", debug, stream);
 
   RenderParams rp{};
@@ -188,8 +245,12 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
   rp.means2D = g.means2D, rp.conic_opacity = g.conic_opacity, rp.rgbd = g.rgbd;
   rp.bg = background, rp.out_color = out_color, rp.out_depth = out_depth, rp.out_alpha = out_alpha;
   rp.n_contrib = im.n_contrib, rp.n_touched = (P > 0) ? n_touched : nullptr;
-  launch_render_fwd(rp, stream);
+  {
+    StageScope ts(ST_RENDER, stream);
+    launch_render_fwd(rp, stream);
+  }
   GSR_STAGE("render", debug, stream);
+  stage_collect(stream);
   return R;
 }
 
@@ -221,7 +282,9 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
   carve_binning(binning_buffer, R, width, height, bl);
   const int final_buf = R > 0 ? (sort_passes(sort_end_bit(width, height)) & 1) : 0;
 
-  GSR_CUDA(cudaMemsetAsync(g.grad_acc, 0, sizeof(float) * 12 * (size_t)P, stream));
+  StageScope* ts_r = new StageScope(ST_BWD_RENDER, stream);
+  cudaError_t me = cudaMemsetAsync(g.grad_acc, 0, sizeof(float) * 12 * (size_t)P, stream);
+  if (me != cudaSuccess) { delete ts_r; return fail(GSR_ERR_CUDA, "memset grad_acc: %s", cudaGetErrorString(me)); }
   if (R > 0) {
     RenderBwdParams rb{};
     rb.W = width, rb.H = height, rb.grid_x = gx, rb.grid_y = gy;
@@ -230,8 +293,9 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
     rb.bg = background, rb.out_alpha = out_alpha, rb.n_contrib = im.n_contrib;
     rb.dL_dpix = dL_dpix, rb.dL_ddepth = dL_ddepth, rb.dL_dalpha = dL_dalpha, rb.grad_acc = g.grad_acc;
     launch_render_bwd(rb, stream);
-    GSR_STAGE("render_backward", debug, stream);
   }
+  delete ts_r;
+  GSR_STAGE("render_backward", debug, stream);
 
   PreBwdParams pb{};
   pb.P = P, pb.D = D, pb.M = M, pb.W = width, pb.H = height;
@@ -244,8 +308,12 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
   pb.dL_dmean2D = dL_dmean2D, pb.dL_dconic = dL_dconic, pb.dL_dopacity = dL_dopacity, pb.dL_dcolor = dL_dcolor;
   pb.dL_dmean3D = dL_dmean3D, pb.dL_dcov3D = dL_dcov3D, pb.dL_dsh = dL_dsh, pb.dL_dscale = dL_dscale, pb.dL_drot = dL_drot;
   pb.dL_dtau = dL_dtau;
-  launch_preprocess_bwd(pb, stream);
+  {
+    StageScope ts(ST_BWD_PREPROCESS, stream);
+    launch_preprocess_bwd(pb, stream);
+  }
   GSR_STAGE("preprocess_backward", debug, stream);
+  stage_collect(stream);
   return GSR_OK;
 }
 
@@ -326,6 +394,20 @@ int gsr_export_state(int P, long long R, int width, int height, const char* geom
   }
   GSR_STAGE("export_state", 1, stream);
   return GSR_OK;
+}
+
+void gsr_stage_timing(int enable) {
+  std::lock_guard<std::mutex> lk(g_timer.mu);
+  g_timer.enabled = enable != 0;
+  for (int i = 0; i < ST_COUNT; i++) g_timer.total_ms[i] = 0.0, g_timer.calls[i] = 0, g_timer.used[i] = false;
+}
+int gsr_stage_times(double* total_ms, unsigned long long* calls, int n) {
+  std::lock_guard<std::mutex> lk(g_timer.mu);
+  for (int i = 0; i < n && i < ST_COUNT; i++) {
+    if (total_ms) total_ms[i] = g_timer.total_ms[i];
+    if (calls) calls[i] = g_timer.calls[i];
+  }
+  return ST_COUNT;
 }
 
 size_t gsr_sort_temp_bytes(long long n) { return sort_temp_bytes(n, SORT_MAX_PASSES); }

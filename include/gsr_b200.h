@@ -138,6 +138,16 @@ GSR_API int gsr_export_state(
     uint64_t* keys_unsorted, uint32_t* list_unsorted, uint64_t* keys, uint32_t* list,
     uint32_t* ranges, uint32_t* n_contrib, void* stream);
 
+/*
+ * Per-stage device timing for bench.py's stage split.  While enabled, every
+ * forward/backward brackets its stages with CUDA events on the launching stream and
+ * synchronises at the end to accumulate them — measurement only, never on in a timed run.
+ * Stage order: preprocess(+scan), duplicate_with_keys, radix_sort, tile_ranges, render,
+ * render_backward, preprocess_backward.  gsr_stage_times returns the number of stages.
+ */
+GSR_API void gsr_stage_timing(int enable);
+GSR_API int gsr_stage_times(double* total_ms, unsigned long long* calls, int n);
+
 /* Stand-alone stable LSD radix sort of (u64 key, u32 value) pairs on bits [0, end_bit) —
  * the hand-written onesweep that replaces cub::DeviceRadixSort::SortPairs
  * (rasterizer_impl.cu:304-309).  temp must hold gsr_sort_temp_bytes(n) bytes. */
