@@ -173,6 +173,7 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
   carve_image(img_base, width, height, im);
 
   long long R = 0;
+  int Pv = 0;
   GeometryView g{};
   BinningLayout bl{};
   int final_buf = 0;
@@ -200,12 +201,13 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     }
     GSR_STAGE("preprocess", debug, stream);
 
-    // num_rendered -> host (the one sync the reference also has, rasterizer_impl.cu:282)
+    // num_rendered (and the visible count) -> host: the one sync the reference also has (rasterizer_impl.cu:282)
     uint32_t* box = pinned_mailbox();
     if (!box) return fail(GSR_ERR_CUDA, "cudaHostAlloc failed");
-    GSR_CUDA(cudaMemcpyAsync(box, g.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    GSR_CUDA(cudaMemcpyAsync(box, g.counters + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     GSR_CUDA(cudaStreamSynchronize(stream));
-    R = (long long)*box;
+    R = (long long)box[0];
+    Pv = (int)box[1];
   }
 
   if (R > 0) {
@@ -219,12 +221,13 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     {
       StageScope ts(ST_DUPLICATE, stream);
       sort_temp_reset(bl.sort_temp, R, passes, stream);
-      launch_duplicate_with_keys(P, g, bl.keys[0], bl.vals[0], gx, end_bit, st.hist, stream);
+      launch_emit_keys(Pv, g, bl.keys[0], bl.vals[0], gx, (uint32_t)R, stream);
     }
-    GSR_STAGE("duplicate_with_keys", debug, stream);
+    GSR_STAGE("emit_keys", debug, stream);
     {
       StageScope ts(ST_SORT, stream);
-      final_buf = launch_onesweep(bl.keys, bl.vals, R, end_bit, st, stream);
+      launch_sort_histogram(bl.keys[0], nullptr, R, end_bit, st.hist, stream);
+      final_buf = launch_onesweep(bl.keys, bl.vals, nullptr, R, end_bit, st, stream);
     }
     GSR_STAGE("radix_sort", debug, stream);
   } else {
@@ -235,14 +238,14 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
   }
   {
     StageScope ts(ST_RANGES, stream);
-    launch_identify_tile_ranges(R, bl.keys[final_buf], im.ranges, T, stream);
+    launch_identify_tile_ranges(nullptr, R, bl.keys[final_buf], im.ranges, T, stream);
   }
   GSR_STAGE("identify_tile_ranges", debug, stream);
 
   RenderParams rp{};
   rp.W = width, rp.H = height, rp.grid_x = gx, rp.grid_y = gy;
   rp.ranges = im.ranges, rp.point_list = bl.vals[final_buf];
-  rp.means2D = g.means2D, rp.conic_opacity = g.conic_opacity, rp.rgbd = g.rgbd;
+  rp.means2D = g.means2D, rp.conic_opacity = g.conic_opacity, rp.rgbd = g.rgbd, rp.gid = g.gid;
   rp.bg = background, rp.out_color = out_color, rp.out_depth = out_depth, rp.out_alpha = out_alpha;
   rp.n_contrib = im.n_contrib, rp.n_touched = (P > 0) ? n_touched : nullptr;
   {
@@ -283,7 +286,9 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
   const int final_buf = R > 0 ? (sort_passes(sort_end_bit(width, height)) & 1) : 0;
 
   StageScope* ts_r = new StageScope(ST_BWD_RENDER, stream);
-  cudaError_t me = cudaMemsetAsync(g.grad_acc, 0, sizeof(float) * 12 * (size_t)P, stream);
+  // accumulator rows exist only for visible Gaussians, and every visible Gaussian owns >= 1 instance
+  const size_t acc_rows = (size_t)std::min<long long>(P, R);
+  cudaError_t me = acc_rows ? cudaMemsetAsync(g.grad_acc, 0, sizeof(float) * 12 * acc_rows, stream) : cudaSuccess;
   if (me != cudaSuccess) { delete ts_r; return fail(GSR_ERR_CUDA, "memset grad_acc: %s", cudaGetErrorString(me)); }
   if (R > 0) {
     RenderBwdParams rb{};
@@ -310,7 +315,15 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
   pb.dL_dtau = dL_dtau;
   {
     StageScope ts(ST_BWD_PREPROCESS, stream);
-    launch_preprocess_bwd(pb, stream);
+    // dense outputs: zero rows for culled Gaussians (the reference's torch::zeros, rasterize_points.cu:158-166),
+    // then one thread per visible Gaussian writes its rows
+    const size_t Pz = (size_t)P;
+    struct { float* p; size_t n; } fills[] = {{dL_dmean2D, 3 * Pz}, {dL_dconic, 4 * Pz}, {dL_dopacity, Pz}, {dL_dcolor, 3 * Pz},
+                                             {dL_dmean3D, 3 * Pz}, {dL_dcov3D, 6 * Pz}, {dL_dsh, 3 * (size_t)M * Pz},
+                                             {dL_dscale, 3 * Pz}, {dL_drot, 4 * Pz}};
+    for (auto& f : fills)
+      if (f.p && f.n) GSR_CUDA(cudaMemsetAsync(f.p, 0, sizeof(float) * f.n, stream));
+    if (R > 0) launch_preprocess_bwd(pb, (int)acc_rows, stream);
   }
   GSR_STAGE("preprocess_backward", debug, stream);
   stage_collect(stream);
@@ -332,32 +345,34 @@ int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const
 
 // ----------------------------------------------------------------------------- state export (tests)
 namespace {
-__global__ void export_geometry_kernel(int P, GeometryView g, float* depths, float* means2D, float* cov3D, float* conic_opacity,
-                                       float* rgb, unsigned char* clamped, uint32_t* tiles_touched, uint32_t* point_offsets) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P) return;
-  const bool vis = g.tiles_touched[i] != 0;   // culled slots of the scratch are uninitialised: export zeros
-  if (depths) depths[i] = vis ? g.depths[i] : 0.f;
-  if (means2D) {
-    means2D[2 * i] = vis ? g.means2D[i].x : 0.f;
-    means2D[2 * i + 1] = vis ? g.means2D[i].y : 0.f;
-  }
+// scatter the compact per-visible records back to the reference's per-Gaussian arrays (outputs pre-zeroed)
+__global__ void export_geometry_kernel(GeometryView g, float* depths, float* means2D, float* cov3D, float* conic_opacity,
+                                       float* rgb, unsigned char* clamped, uint32_t* tiles_touched) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= g.counters[2]) return;
+  const size_t i = g.gid[k];
+  if (depths) depths[i] = g.depths[k];
+  if (means2D) means2D[2 * i] = g.means2D[k].x, means2D[2 * i + 1] = g.means2D[k].y;
   if (cov3D)
-    for (int k = 0; k < 6; k++) cov3D[6 * (size_t)i + k] = vis ? g.cov3D[6 * (size_t)i + k] : 0.f;
+    for (int q = 0; q < 6; q++) cov3D[6 * i + q] = g.cov3D[6 * (size_t)k + q];
   if (conic_opacity) {
-    const float4 c = vis ? g.conic_opacity[i] : make_float4(0, 0, 0, 0);
+    const float4 c = g.conic_opacity[k];
     conic_opacity[4 * i] = c.x, conic_opacity[4 * i + 1] = c.y, conic_opacity[4 * i + 2] = c.z, conic_opacity[4 * i + 3] = c.w;
   }
   if (rgb) {
-    const float4 c = vis ? g.rgbd[i] : make_float4(0, 0, 0, 0);
-    rgb[3 * (size_t)i] = c.x, rgb[3 * (size_t)i + 1] = c.y, rgb[3 * (size_t)i + 2] = c.z;
+    const float4 c = g.rgbd[k];
+    rgb[3 * i] = c.x, rgb[3 * i + 1] = c.y, rgb[3 * i + 2] = c.z;
   }
   if (clamped) {
-    const uint8_t m = vis ? g.clamped[i] : 0;
-    clamped[3 * (size_t)i] = m & 1, clamped[3 * (size_t)i + 1] = (m >> 1) & 1, clamped[3 * (size_t)i + 2] = (m >> 2) & 1;
+    const uint8_t m = g.clamped[k];
+    clamped[3 * i] = m & 1, clamped[3 * i + 1] = (m >> 1) & 1, clamped[3 * i + 2] = (m >> 2) & 1;
   }
-  if (tiles_touched) tiles_touched[i] = g.tiles_touched[i];
-  if (point_offsets) point_offsets[i] = g.point_offsets[i];
+  if (tiles_touched) tiles_touched[i] = g.tiles_touched[k];
+}
+// visible rank -> Gaussian id (the reference's point_list holds Gaussian ids)
+__global__ void translate_ranks_kernel(uint32_t* vals, const uint32_t* gid, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) vals[i] = gid[vals[i]];
 }
 }  // namespace
 
@@ -369,22 +384,29 @@ int gsr_export_state(int P, long long R, int width, int height, const char* geom
                      uint32_t* list_unsorted, uint64_t* keys, uint32_t* list, uint32_t* ranges, uint32_t* n_contrib,
                      void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  (void)point_offsets;   // per-Gaussian offsets are the prefix sum of tiles_touched; the caller derives them
   const uint32_t gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
   GeometryView g{};
   if (P > 0 && geometry_buffer) {
     carve_geometry(const_cast<char*>(geometry_buffer), P, g);
-    export_geometry_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g, depths, means2D, cov3D, conic_opacity, rgb, clamped,
-                                                              tiles_touched, point_offsets);
+    export_geometry_kernel<<<(P + 255) / 256, 256, 0, stream>>>(g, depths, means2D, cov3D, conic_opacity, rgb, clamped,
+                                                              tiles_touched);
   }
-  if (R > 0 && binning_buffer) {
+  if (R > 0 && binning_buffer && P > 0 && geometry_buffer) {
     BinningLayout bl;
     carve_binning(const_cast<char*>(binning_buffer), R, width, height, bl);
     const int end_bit = sort_end_bit(width, height);
     const int fb = sort_passes(end_bit) & 1;
+    const unsigned nb = (unsigned)((R + 255) / 256);
     if (keys) GSR_CUDA(cudaMemcpyAsync(keys, bl.keys[fb], sizeof(uint64_t) * (size_t)R, cudaMemcpyDeviceToDevice, stream));
-    if (list) GSR_CUDA(cudaMemcpyAsync(list, bl.vals[fb], sizeof(uint32_t) * (size_t)R, cudaMemcpyDeviceToDevice, stream));
-    if (keys_unsorted && list_unsorted && P > 0 && geometry_buffer)   // regenerated: the sort's ping-pong overwrote them
-      launch_duplicate_with_keys(P, g, keys_unsorted, list_unsorted, gx, end_bit, nullptr, stream);
+    if (list) {
+      GSR_CUDA(cudaMemcpyAsync(list, bl.vals[fb], sizeof(uint32_t) * (size_t)R, cudaMemcpyDeviceToDevice, stream));
+      translate_ranks_kernel<<<nb, 256, 0, stream>>>(list, g.gid, R);
+    }
+    if (keys_unsorted && list_unsorted) {   // regenerated: the sort's ping-pong overwrote them
+      launch_emit_keys(P, g, keys_unsorted, list_unsorted, gx, (uint32_t)R, stream);
+      translate_ranks_kernel<<<nb, 256, 0, stream>>>(list_unsorted, g.gid, R);
+    }
   }
   if (image_buffer) {
     ImageView im;
@@ -422,7 +444,7 @@ int gsr_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* 
   SortTemp st;
   carve_sort_temp(temp, n, passes, st);
   sort_temp_reset(temp, n, passes, stream);
-  launch_sort_histogram(keys_in, n, end_bit, st.hist, stream);
+  launch_sort_histogram(keys_in, nullptr, n, end_bit, st.hist, stream);
   // arrange the ping-pong so that the last pass lands in keys_out: odd passes in->out directly
   uint64_t* kb[2];
   uint32_t* vb[2];
@@ -436,7 +458,7 @@ int gsr_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* 
     GSR_CUDA(cudaMemcpyAsync(vals_out, vals_in, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, stream));
     kb[0] = keys_out, kb[1] = keys_tmp, vb[0] = vals_out, vb[1] = vals_tmp;
   }
-  launch_onesweep(kb, vb, n, end_bit, st, stream);
+  launch_onesweep(kb, vb, nullptr, n, end_bit, st, stream);
   GSR_STAGE("sort_pairs", 0, stream);
   return GSR_OK;
 }

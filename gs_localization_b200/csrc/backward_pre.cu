@@ -7,14 +7,15 @@
 //   computeCov3D (backward)          cuda_rasterizer/backward.cu:278-341
 //   the nine torch::zeros fills      rasterize_points.cu:158-166
 //
-// B200 design: one thread per Gaussian, 128 per CTA; the two reference kernels are fused so
-// dL_dcov3D / dL_dmean3D never round-trip through HBM between them; every gradient row is
-// written exactly once for ALL P Gaussians (zeros for culled ones), so no zero-fill pass is
-// needed; the wide SH-gradient rows (12*M bytes each) are staged through shared memory and
-// leave the CTA as fully coalesced stores.  With dL_dtau != nullptr the SE(3) chain rule is
-// fused in: each thread forms its 6-vector contribution to dL/d(rho, theta) for the left
-// perturbation T_w2c <- exp(tau) T_w2c (gs_localization/pipelines/tools/pose_utils.py:90-122),
-// the CTA reduces it with shuffles and issues 6 atomics.
+// B200 design: the forward left a compact list of the visible Gaussians, so this kernel runs
+// one thread per VISIBLE Gaussian on dense warps (the reference launches P threads of which
+// >90 % exit at once); the two reference kernels are fused, so dL_dcov3D / dL_dmean3D never
+// round-trip through HBM between them; the dense zero rows the API promises for culled
+// Gaussians are produced by plain memsets at copy-engine bandwidth, and each visible row is
+// then written exactly once.  With dL_dtau != nullptr the SE(3) chain rule is fused in: each
+// thread forms its 6-vector contribution to dL/d(rho, theta) for the left perturbation
+// T_w2c <- exp(tau) T_w2c (gs_localization/pipelines/tools/pose_utils.py:90-122), the CTA
+// reduces it with shuffles and issues 6 atomics.
 #include "gsr_kernels.cuh"
 
 namespace gsr {
@@ -33,8 +34,8 @@ __device__ __forceinline__ float3 dnormvdv(float3 v, float3 dv) {
   return o;
 }
 
-// SH backward (reference backward.cu:20-139).  Writes this Gaussian's dL_dsh row into `out`
-// (shared memory, stride 1) and returns dL_dmean through the view direction.
+// SH backward (reference backward.cu:20-139).  Writes this Gaussian's dL_dsh row to `out`
+// (may be null) and returns dL_dmean through the view direction.
 __device__ __forceinline__ float3 sh_backward(int deg, float3 pos, float3 campos, const float* __restrict__ sh,
                                               float3 dL_dRGB, float* out) {
   const float3 dir_orig = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
@@ -43,9 +44,11 @@ __device__ __forceinline__ float3 sh_backward(int deg, float3 pos, float3 campos
   float3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
   auto S = [&](int k) { return make_float3(__ldg(sh + 3 * k), __ldg(sh + 3 * k + 1), __ldg(sh + 3 * k + 2)); };
   auto put = [&](int k, float w) {
-    out[3 * k] = w * dL_dRGB.x;
-    out[3 * k + 1] = w * dL_dRGB.y;
-    out[3 * k + 2] = w * dL_dRGB.z;
+    if (out) {
+      out[3 * k] = w * dL_dRGB.x;
+      out[3 * k + 1] = w * dL_dRGB.y;
+      out[3 * k + 2] = w * dL_dRGB.z;
+    }
   };
   auto axpy = [](float3& a, float w, float3 s) { a.x += w * s.x; a.y += w * s.y; a.z += w * s.z; };
   put(0, SH_C0);
@@ -95,16 +98,15 @@ __device__ __forceinline__ float3 sh_backward(int deg, float3 pos, float3 campos
 }
 
 __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwdParams p) {
-  __shared__ float s_sh[BW_THREADS * (SH_MAX_FLOATS + 1)];   // padded rows: conflict-free
   __shared__ float s_tau[BW_THREADS / 32][6];
-  __shared__ int s_any_visible[BW_THREADS / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int idx = blockIdx.x * BW_THREADS + tid;
-  const int P = p.P, M = p.M;
+  const uint32_t Pv = p.geom.counters[2];
+  if ((uint32_t)blockIdx.x * BW_THREADS >= Pv) return;
+  const uint32_t k = blockIdx.x * BW_THREADS + tid;     // visible rank
+  const int M = p.M;
   const int row = 3 * M;                 // floats per SH row
-  const bool valid = idx < P;
-  const bool visible = valid && __ldg(p.radii + idx) > 0;
+  const bool visible = k < Pv;
   const float* vm = p.viewmatrix;
   const float* proj = p.projmatrix;
 
@@ -117,14 +119,11 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
   float3 g_scale = {0, 0, 0};
   float4 g_rot = {0, 0, 0, 0};
   float tau[6] = {0, 0, 0, 0, 0, 0};
-  float* my_sh = s_sh + tid * (SH_MAX_FLOATS + 1);
-  const bool want_sh = p.dL_dsh != nullptr && p.shs != nullptr;
-  if (want_sh) {
-    for (int k = 0; k < row; k++) my_sh[k] = 0.f;
-  }
+  size_t idx = 0;
 
   if (visible) {
-    const float* acc = p.geom.grad_acc + 12 * (size_t)idx;
+    idx = __ldg(p.geom.gid + k);
+    const float* acc = p.geom.grad_acc + 12 * (size_t)k;
     const float4 a0 = *reinterpret_cast<const float4*>(acc);
     const float4 a1 = *reinterpret_cast<const float4*>(acc + 4);
     const float4 a2 = *reinterpret_cast<const float4*>(acc + 8);
@@ -134,12 +133,11 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
     g_color = make_float3(a1.z, a1.w, a2.x);
     const float g_depth = a2.y;
 
-    const float3 mean = {__ldg(p.means3D + 3 * (size_t)idx), __ldg(p.means3D + 3 * (size_t)idx + 1),
-                         __ldg(p.means3D + 3 * (size_t)idx + 2)};
-    const float* c3 = p.cov3D_precomp ? p.cov3D_precomp + 6 * (size_t)idx : p.geom.cov3D + 6 * (size_t)idx;
+    const float3 mean = {__ldg(p.means3D + 3 * idx), __ldg(p.means3D + 3 * idx + 1), __ldg(p.means3D + 3 * idx + 2)};
+    const float* c3 = p.cov3D_precomp ? p.cov3D_precomp + 6 * idx : p.geom.cov3D + 6 * (size_t)k;
     float cov3D[6];
 #pragma unroll
-    for (int k = 0; k < 6; k++) cov3D[k] = __ldg(c3 + k);
+    for (int q = 0; q < 6; q++) cov3D[q] = __ldg(c3 + q);
 
     // ---------------- computeCov2DCUDA backward (backward.cu:144-274)
     float3 t = {vm[0] * mean.x + vm[4] * mean.y + vm[8] * mean.z + vm[12],
@@ -217,18 +215,17 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
     // ---------------- SH (backward.cu:389-391)
     float3 g_sh_mean = {0, 0, 0};
     if (p.shs) {
-      const uint8_t cm = __ldg(p.geom.clamped + idx);
+      const uint8_t cm = __ldg(p.geom.clamped + k);
       const float3 dL_dRGB = {(cm & 1) ? 0.f : g_color.x, (cm & 2) ? 0.f : g_color.y, (cm & 4) ? 0.f : g_color.z};
       const float3 cp = {__ldg(p.campos), __ldg(p.campos + 1), __ldg(p.campos + 2)};
-      float dummy[SH_MAX_FLOATS];
-      float* out = want_sh ? my_sh : dummy;
-      g_sh_mean = sh_backward(p.D, mean, cp, p.shs + (size_t)idx * row, dL_dRGB, out);
+      // rows of the SH gradient were zero-filled; coefficients above the active degree stay zero
+      g_sh_mean = sh_backward(p.D, mean, cp, p.shs + idx * row, dL_dRGB, p.dL_dsh ? p.dL_dsh + idx * row : nullptr);
       g_mean.x += g_sh_mean.x; g_mean.y += g_sh_mean.y; g_mean.z += g_sh_mean.z;
     }
 
     // ---------------- computeCov3D backward (backward.cu:278-341)
     if (p.scales) {
-      const float3 sc = {__ldg(p.scales + 3 * (size_t)idx), __ldg(p.scales + 3 * (size_t)idx + 1), __ldg(p.scales + 3 * (size_t)idx + 2)};
+      const float3 sc = {__ldg(p.scales + 3 * idx), __ldg(p.scales + 3 * idx + 1), __ldg(p.scales + 3 * idx + 2)};
       const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
       const float r = q.x, x = q.y, y = q.z, z = q.w;
       // glm columns of R
@@ -298,43 +295,21 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
     }
   }
 
-  // ---------------- dense row writes (zeros for culled Gaussians)
-  if (valid) {
-    if (p.dL_dmean2D) { float* o = p.dL_dmean2D + 3 * (size_t)idx; o[0] = g_mean2D.x; o[1] = g_mean2D.y; o[2] = 0.f; }
+  // ---------------- rows of the visible Gaussians (culled rows were zero-filled by memset)
+  if (visible) {
+    if (p.dL_dmean2D) { float* o = p.dL_dmean2D + 3 * idx; o[0] = g_mean2D.x; o[1] = g_mean2D.y; o[2] = 0.f; }
     if (p.dL_dconic) reinterpret_cast<float4*>(p.dL_dconic)[idx] = g_conic;
     if (p.dL_dopacity) p.dL_dopacity[idx] = g_opacity;
-    if (p.dL_dcolor) { float* o = p.dL_dcolor + 3 * (size_t)idx; o[0] = g_color.x; o[1] = g_color.y; o[2] = g_color.z; }
-    if (p.dL_dmean3D) { float* o = p.dL_dmean3D + 3 * (size_t)idx; o[0] = g_mean.x; o[1] = g_mean.y; o[2] = g_mean.z; }
+    if (p.dL_dcolor) { float* o = p.dL_dcolor + 3 * idx; o[0] = g_color.x; o[1] = g_color.y; o[2] = g_color.z; }
+    if (p.dL_dmean3D) { float* o = p.dL_dmean3D + 3 * idx; o[0] = g_mean.x; o[1] = g_mean.y; o[2] = g_mean.z; }
     if (p.dL_dcov3D) {
-      float* o = p.dL_dcov3D + 6 * (size_t)idx;
+      float* o = p.dL_dcov3D + 6 * idx;
 #pragma unroll
-      for (int k = 0; k < 6; k++) o[k] = g_cov[k];
+      for (int q = 0; q < 6; q++) o[q] = g_cov[q];
     }
-    if (p.dL_dscale) { float* o = p.dL_dscale + 3 * (size_t)idx; o[0] = g_scale.x; o[1] = g_scale.y; o[2] = g_scale.z; }
+    if (p.dL_dscale) { float* o = p.dL_dscale + 3 * idx; o[0] = g_scale.x; o[1] = g_scale.y; o[2] = g_scale.z; }
     if (p.dL_drot) reinterpret_cast<float4*>(p.dL_drot)[idx] = g_rot;
   }
-
-  // ---------------- SH gradient rows: the warp's 32 rows are contiguous in memory
-  if (p.dL_dsh != nullptr && M > 0) {
-    const int warp_first = blockIdx.x * BW_THREADS + warp * 32;
-    const int nrows = min(32, P - warp_first);
-    if (nrows > 0) {
-      const bool any_vis = __any_sync(0xffffffffu, visible) && want_sh;
-      float* dst = p.dL_dsh + (size_t)warp_first * row;
-      const int total = nrows * row;
-      __syncwarp();
-      if (any_vis) {
-        const float* src = s_sh + (warp * 32) * (SH_MAX_FLOATS + 1);
-        for (int e = lane; e < total; e += 32) {
-          const int rr = e / row, cc = e - rr * row;
-          dst[e] = src[rr * (SH_MAX_FLOATS + 1) + cc];
-        }
-      } else {
-        for (int e = lane; e < total; e += 32) dst[e] = 0.f;
-      }
-    }
-  }
-  (void)s_any_visible;
 
   // ---------------- pose gradient: CTA reduction, 6 atomics
   if (p.dL_dtau) {
@@ -354,9 +329,9 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
   }
 }
 
-void launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream) {
-  if (p.P <= 0) return;
-  preprocess_bwd_kernel<<<(p.P + BW_THREADS - 1) / BW_THREADS, BW_THREADS, 0, stream>>>(p);
+void launch_preprocess_bwd(const PreBwdParams& p, int max_visible, cudaStream_t stream) {
+  if (max_visible <= 0) return;
+  preprocess_bwd_kernel<<<(max_visible + BW_THREADS - 1) / BW_THREADS, BW_THREADS, 0, stream>>>(p);
   count_launch();
 }
 

@@ -47,84 +47,91 @@ __device__ __forceinline__ uint32_t digit_of(uint64_t key, int shift, uint32_t m
   return (uint32_t)(key >> shift) & mask;
 }
 
-// ------------------------------------------------------------------ key generation + histograms
-__global__ void __launch_bounds__(256) duplicate_with_keys_kernel(int P, const uint32_t* __restrict__ tiles_touched,
-                                                                  const uint32_t* __restrict__ point_offsets,
-                                                                  const uint2* __restrict__ rects,
-                                                                  const float* __restrict__ depths,
-                                                                  uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                                  uint32_t grid_x, int end_bit, uint32_t* __restrict__ hist) {
-  __shared__ uint32_t s_hist[SORT_MAX_PASSES * SORT_RADIX];
-  const int passes = (end_bit + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS;
-  if (hist) {
-    for (int i = threadIdx.x; i < passes * SORT_RADIX; i += blockDim.x) s_hist[i] = 0;
-    __syncthreads();
+// ------------------------------------------------------------------ key generation
+// One CTA expands 256 consecutive visible Gaussians.  The CTA's output range is contiguous
+// (prefix sums), so all 256 threads walk it together: output slot j finds its owner with a
+// binary search over the CTA-local prefix sums in shared memory, decodes its tile from the
+// owner's rectangle (rows then columns, like the reference's nested loop) and writes
+// key = tile << 32 | depth bits, value = visible rank.  Writes are fully coalesced and a
+// Gaussian covering thousands of tiles costs no more per key than one covering four.
+__global__ void __launch_bounds__(256) emit_keys_kernel(const uint32_t* __restrict__ counters,
+                                                        const uint32_t* __restrict__ tiles_touched,
+                                                        const uint32_t* __restrict__ point_offsets,
+                                                        const uint2* __restrict__ rects, const float* __restrict__ depths,
+                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                        uint32_t grid_x, uint32_t capacity) {
+  __shared__ uint32_t s_end[256];     // CTA-local inclusive prefix of tiles
+  __shared__ uint2 s_rect[256];
+  __shared__ uint32_t s_depth[256];
+  const uint32_t Pv = counters[2];
+  const uint32_t first = blockIdx.x * 256u;
+  if (first >= Pv) return;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t k = first + tid;
+  const uint32_t cnt = min(256u, Pv - first);
+  const uint32_t block_begin = first == 0 ? 0u : __ldg(point_offsets + first - 1);
+  if (tid < cnt) {
+    s_end[tid] = __ldg(point_offsets + k) - block_begin;
+    s_rect[tid] = __ldg(rects + k);
+    s_depth[tid] = __float_as_uint(__ldg(depths + k));
   }
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < P) {
-    const uint32_t tiles = __ldg(tiles_touched + idx);
-    if (tiles) {
-      uint32_t off = __ldg(point_offsets + idx) - tiles;
-      const uint2 rc = __ldg(rects + idx);
-      const uint32_t minx = rc.x & 0xffffu, maxx = rc.x >> 16, miny = rc.y & 0xffffu, maxy = rc.y >> 16;
-      const uint32_t dbits = __float_as_uint(__ldg(depths + idx));
-      if (hist) {
-#pragma unroll
-        for (int p = 0; p < 4; p++) {
-          const int shift = 8 * p;
-          if (shift < end_bit) {
-            const uint32_t mask = (1u << min(SORT_RADIX_BITS, end_bit - shift)) - 1u;
-            atomicAdd(&s_hist[p * SORT_RADIX + ((dbits >> shift) & mask)], tiles);
-          }
-        }
-      }
-      for (uint32_t y = miny; y < maxy; y++) {
-        for (uint32_t x = minx; x < maxx; x++) {
-          const uint32_t tile = y * grid_x + x;
-          keys[off] = ((uint64_t)tile << 32) | dbits;
-          vals[off] = (uint32_t)idx;
-          off++;
-          if (hist) {
-            for (int p = 4; p < passes; p++) {
-              const int shift = 8 * p;
-              const uint32_t mask = (1u << min(SORT_RADIX_BITS, end_bit - shift)) - 1u;
-              atomicAdd(&s_hist[p * SORT_RADIX + ((tile >> (shift - 32)) & mask)], 1u);
-            }
-          }
-        }
-      }
+  __syncthreads();
+  const uint32_t total = s_end[cnt - 1];
+  for (uint32_t j = tid; j < total; j += 256u) {
+    // smallest t with s_end[t] > j
+    uint32_t lo = 0, hi = cnt - 1;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s_end[mid] > j) hi = mid; else lo = mid + 1;
     }
-  }
-  if (hist) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < passes * SORT_RADIX; i += blockDim.x) {
-      const uint32_t c = s_hist[i];
-      if (c) atomicAdd(&hist[i], c);
+    const uint32_t begin = lo == 0 ? 0u : s_end[lo - 1];
+    const uint32_t within = j - begin;
+    const uint2 rc = s_rect[lo];
+    const uint32_t minx = rc.x & 0xffffu, w = (rc.x >> 16) - minx, miny = rc.y & 0xffffu;
+    const uint32_t row = within / w, col = within - row * w;
+    const uint32_t tile = (miny + row) * grid_x + (minx + col);
+    const uint32_t dst = block_begin + j;
+    if (dst < capacity) {
+      keys[dst] = ((uint64_t)tile << 32) | s_depth[lo];
+      vals[dst] = first + lo;
     }
   }
 }
 
-void launch_duplicate_with_keys(int P, const GeometryView& g, uint64_t* keys, uint32_t* vals, uint32_t grid_x,
-                                int end_bit, uint32_t* hist, cudaStream_t stream) {
-  if (P <= 0) return;
-  duplicate_with_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, g.tiles_touched, g.point_offsets, g.rect, g.depths,
-                                                                 keys, vals, grid_x, end_bit, hist);
+void launch_emit_keys(int max_visible, const GeometryView& g, uint64_t* keys, uint32_t* vals, uint32_t grid_x,
+                      uint32_t capacity, cudaStream_t stream) {
+  if (max_visible <= 0) return;
+  emit_keys_kernel<<<(max_visible + 255) / 256, 256, 0, stream>>>(g.counters, g.tiles_touched, g.point_offsets, g.rect,
+                                                               g.depths, keys, vals, grid_x, capacity);
   count_launch();
 }
 
-// stand-alone histogram (generic sort entry point)
-__global__ void __launch_bounds__(256) sort_histogram_kernel(const uint64_t* __restrict__ keys, long long n, int end_bit,
-                                                             uint32_t* __restrict__ hist) {
+// ------------------------------------------------------------------ digit histograms of all passes
+// Keys of one Gaussian are adjacent and share every depth digit, so equal digits are first
+// aggregated inside the warp (match_any) and cost one shared-memory atomic per group.
+__global__ void __launch_bounds__(256) sort_histogram_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ n_ptr,
+                                                             uint32_t n_host, int end_bit, uint32_t* __restrict__ hist) {
   __shared__ uint32_t s_hist[SORT_MAX_PASSES * SORT_RADIX];
+  const uint32_t n = n_ptr ? min(*n_ptr, n_host) : n_host;
   const int passes = (end_bit + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS;
   for (int i = threadIdx.x; i < passes * SORT_RADIX; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const uint64_t k = __ldg(keys + i);
-    for (int p = 0; p < passes; p++) {
-      const int shift = 8 * p;
-      const uint32_t mask = (1u << min(SORT_RADIX_BITS, end_bit - shift)) - 1u;
-      atomicAdd(&s_hist[p * SORT_RADIX + digit_of(k, shift, mask)], 1u);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  // warp-uniform trip count so that match_any sees full warps
+  for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+    const uint32_t i = base + lane;
+    const bool valid = i < n;
+    const uint64_t k = valid ? __ldg(keys + i) : 0ull;
+    const uint32_t act = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      for (int p = 0; p < passes; p++) {
+        const int shift = SORT_RADIX_BITS * p;
+        const uint32_t mask = (1u << min(SORT_RADIX_BITS, end_bit - shift)) - 1u;
+        const uint32_t d = digit_of(k, shift, mask);
+        const uint32_t peers = __match_any_sync(act, d);
+        if (lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_hist[p * SORT_RADIX + d], (uint32_t)__popc(peers));
+      }
     }
   }
   __syncthreads();
@@ -133,10 +140,11 @@ __global__ void __launch_bounds__(256) sort_histogram_kernel(const uint64_t* __r
     if (c) atomicAdd(&hist[i], c);
   }
 }
-void launch_sort_histogram(const uint64_t* keys, long long n, int end_bit, uint32_t* hist, cudaStream_t stream) {
-  if (n <= 0) return;
-  const int blocks = (int)std::min<long long>((n + 256 * 16 - 1) / (256 * 16), 148 * 8);
-  sort_histogram_kernel<<<blocks, 256, 0, stream>>>(keys, n, end_bit, hist);
+void launch_sort_histogram(const uint64_t* keys, const uint32_t* n_ptr, long long n_host, int end_bit, uint32_t* hist,
+                           cudaStream_t stream) {
+  if (n_host <= 0) return;
+  const int blocks = (int)std::min<long long>((n_host + 256 * 8 - 1) / (256 * 8), 148 * 4);
+  sort_histogram_kernel<<<blocks, 256, 0, stream>>>(keys, n_ptr, (uint32_t)n_host, end_bit, hist);
   count_launch();
 }
 
@@ -174,19 +182,21 @@ struct __align__(16) SortSmem {
 
 __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout,
                                                                     const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
-                                                                    uint32_t n, int shift, uint32_t mask,
-                                                                    const uint32_t* __restrict__ bases, uint32_t* ticket,
+                                                                    const uint32_t* __restrict__ n_ptr, uint32_t n_host, int shift,
+                                                                    uint32_t mask, const uint32_t* __restrict__ bases,
                                                                     volatile uint32_t* status) {
   extern __shared__ __align__(16) char smem_raw[];
   SortSmem& s = *reinterpret_cast<SortSmem*>(smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = SORT_THREADS / 32;
 
-  if (tid == 0) s.tile = atomicAdd(ticket, 1u);
+  // CTAs are dispatched in blockIdx order: every predecessor the look-back waits on is resident.
+  const uint32_t n = n_ptr ? min(*n_ptr, n_host) : n_host;
+  const uint32_t tile = blockIdx.x;
+  const uint32_t tile_base = tile * SORT_TILE;
+  if (tile_base >= n) return;
   for (int i = tid; i < NW * SORT_RADIX; i += SORT_THREADS) (&s.warp_hist[0][0])[i] = 0;
   __syncthreads();
-  const uint32_t tile = s.tile;
-  const uint32_t tile_base = tile * SORT_TILE;
   const uint32_t count = min((uint32_t)SORT_TILE, n - tile_base);
 
   // ---- load (warp-striped: item i of lane l sits at warp_base + 32 i + l, so index order = (i, lane))
@@ -286,7 +296,8 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(const uint6
   }
 }
 
-int launch_onesweep(uint64_t* keys[2], uint32_t* vals[2], long long n, int end_bit, const SortTemp& t, cudaStream_t stream) {
+int launch_onesweep(uint64_t* keys[2], uint32_t* vals[2], const uint32_t* n_ptr, long long n, int end_bit, const SortTemp& t,
+                    cudaStream_t stream) {
   const int passes = sort_passes(end_bit);
   if (n <= 0 || passes == 0) return 0;
   static bool attr_set = false;
@@ -302,7 +313,7 @@ int launch_onesweep(uint64_t* keys[2], uint32_t* vals[2], long long n, int end_b
     const int shift = SORT_RADIX_BITS * p;
     const uint32_t mask = (1u << std::min(SORT_RADIX_BITS, end_bit - shift)) - 1u;
     onesweep_pass_kernel<<<(unsigned)ntiles, SORT_THREADS, sizeof(SortSmem), stream>>>(
-        keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], (uint32_t)n, shift, mask, t.hist + p * SORT_RADIX, t.tickets + p,
+        keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n_ptr, (uint32_t)n, shift, mask, t.hist + p * SORT_RADIX,
         t.status + (size_t)p * ntiles * SORT_RADIX);
     count_launch();
     cur ^= 1;
@@ -311,8 +322,10 @@ int launch_onesweep(uint64_t* keys[2], uint32_t* vals[2], long long n, int end_b
 }
 
 // ------------------------------------------------------------------ tile ranges
-__global__ void __launch_bounds__(256) identify_tile_ranges_kernel(uint32_t L, const uint64_t* __restrict__ keys,
+__global__ void __launch_bounds__(256) identify_tile_ranges_kernel(const uint32_t* __restrict__ n_ptr, uint32_t n_host,
+                                                                   const uint64_t* __restrict__ keys,
                                                                    uint2* __restrict__ ranges) {
+  const uint32_t L = n_ptr ? min(*n_ptr, n_host) : n_host;
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= L) return;
   const uint32_t cur = (uint32_t)(__ldg(keys + idx) >> 32);
@@ -328,10 +341,11 @@ __global__ void __launch_bounds__(256) identify_tile_ranges_kernel(uint32_t L, c
   if (idx == L - 1) ranges[cur].y = L;
 }
 
-void launch_identify_tile_ranges(long long n, const uint64_t* keys, uint2* ranges, int num_tiles, cudaStream_t stream) {
+void launch_identify_tile_ranges(const uint32_t* n_ptr, long long n, const uint64_t* keys, uint2* ranges, int num_tiles,
+                                 cudaStream_t stream) {
   cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, stream);
   if (n > 0) {
-    identify_tile_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((uint32_t)n, keys, ranges);
+    identify_tile_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n_ptr, (uint32_t)n, keys, ranges);
     count_launch();
   }
 }

@@ -24,19 +24,24 @@ __device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f,
 // Scratch layout (private contract between this library's forward and backward).
 // All slabs 128-byte aligned.  SoA, sized for P Gaussians / R instances / N pixels.
 // ---------------------------------------------------------------------------------------
+// The forward compacts the visible Gaussians: everything downstream of preprocess (key
+// emission, sort payload, blending gathers, backward accumulators) is indexed by the visible
+// rank k in [0, Pv) — Gaussian order is preserved, so sort stability / tie order is unchanged —
+// and only `radii` stays indexed by Gaussian id.  All arrays are sized for the worst case Pv = P.
 struct GeometryView {           // replaces GeometryState (reference rasterizer_impl.h:29-44)
-  float* depths;                // [P]   view-space z (sort key low bits)
-  float2* means2D;              // [P]   pixel-space centre
-  float4* conic_opacity;        // [P]   (conic.x, conic.y, conic.z, opacity)
-  float4* rgbd;                 // [P]   (r, g, b, depth): one 16-byte gather for the blend kernels
-  float* cov3D;                 // [6P]
-  uint2* rect;                  // [P]   tile rectangle: x = minx | maxx<<16, y = miny | maxy<<16
-  uint8_t* clamped;             // [P]   bit c set <=> channel c was clamped at 0
-  uint32_t* tiles_touched;      // [P]
-  uint32_t* point_offsets;      // [P]   inclusive prefix sum of tiles_touched (Gaussian order)
-  unsigned long long* scan_status;  // [ceil(P/256)] decoupled look-back words (flag<<32 | value)
-  uint32_t* counters;           // [8]  0: CTA ticket, 1: num_rendered, 2: max depth bits
-  float* grad_acc;              // [12P] backward accumulators (see render_bwd)
+  float* depths;                // [Pv]  view-space z (sort key low bits)
+  float2* means2D;              // [Pv]  pixel-space centre
+  float4* conic_opacity;        // [Pv]  (conic.x, conic.y, conic.z, opacity)
+  float4* rgbd;                 // [Pv]  (r, g, b, depth): one 16-byte gather for the blend kernels
+  float* cov3D;                 // [6Pv]
+  uint2* rect;                  // [Pv]  tile rectangle: x = minx | maxx<<16, y = miny | maxy<<16
+  uint8_t* clamped;             // [Pv]  bit c set <=> channel c was clamped at 0
+  uint32_t* gid;                // [Pv]  Gaussian id of visible rank k (ascending)
+  uint32_t* tiles_touched;      // [Pv]
+  uint32_t* point_offsets;      // [Pv]  inclusive prefix sum of tiles_touched
+  unsigned long long* scan_status;  // [ceil(P/256)] decoupled look-back words (flag<<62 | visible<<32 | tiles)
+  uint32_t* counters;           // [32] 0: unused, 1: num_rendered, 2: num_visible, 3: overflow flag
+  float* grad_acc;              // [12Pv] backward accumulators (see render_bwd)
 };
 
 struct ImageView {              // replaces ImageState (reference rasterizer_impl.h:46-52)
@@ -70,6 +75,7 @@ inline char* carve_geometry(char* base, int P, GeometryView& g) {
   carve(p, g.cov3D, 6 * (size_t)P);
   carve(p, g.rect, (size_t)P);
   carve(p, g.clamped, (size_t)P);
+  carve(p, g.gid, (size_t)P);
   carve(p, g.tiles_touched, (size_t)P);
   carve(p, g.point_offsets, (size_t)P);
   carve(p, g.scan_status, (size_t)num_pre_blocks(P) + 1);

@@ -53,25 +53,29 @@ void carve_sort_temp(char* base, long long n, int passes, SortTemp& t);
 // zero hist/tickets/status (one memset)
 void sort_temp_reset(char* base, long long n, int passes, cudaStream_t stream);
 
-// keys generated + per-digit histograms accumulated in one kernel
-void launch_duplicate_with_keys(int P, const GeometryView& g, uint64_t* keys, uint32_t* vals, uint32_t grid_x,
-                                int end_bit, uint32_t* hist /* may be null: keys only */, cudaStream_t stream);
-// histogram of existing keys (stand-alone sort entry)
-void launch_sort_histogram(const uint64_t* keys, long long n, int end_bit, uint32_t* hist, cudaStream_t stream);
+// All binning kernels take the element count both as a host upper bound (grid sizing) and, optionally,
+// as a device pointer (the exact value written by preprocess), so the chain can run without a host sync.
+// key = tile<<32 | depth bits, value = visible rank; block-cooperative expansion over the compact visible set
+void launch_emit_keys(int max_visible, const GeometryView& g, uint64_t* keys, uint32_t* vals, uint32_t grid_x,
+                      uint32_t capacity, cudaStream_t stream);
+void launch_sort_histogram(const uint64_t* keys, const uint32_t* n_ptr, long long n_host, int end_bit, uint32_t* hist,
+                           cudaStream_t stream);
 // exclusive scan of the histograms + all onesweep passes; returns index (0/1) of the buffer holding the result
-int launch_onesweep(uint64_t* keys[2], uint32_t* vals[2], long long n, int end_bit, const SortTemp& t, cudaStream_t stream);
-void launch_identify_tile_ranges(long long n, const uint64_t* keys, uint2* ranges, int num_tiles, cudaStream_t stream);
+int launch_onesweep(uint64_t* keys[2], uint32_t* vals[2], const uint32_t* n_ptr, long long n_host, int end_bit,
+                    const SortTemp& t, cudaStream_t stream);
+void launch_identify_tile_ranges(const uint32_t* n_ptr, long long n_host, const uint64_t* keys, uint2* ranges, int num_tiles,
+                                 cudaStream_t stream);
 
 // ---- blending (render.cu)
 struct RenderParams {
   int W, H;
   uint32_t grid_x, grid_y;
   const uint2* ranges;
-  const uint32_t* point_list;
+  const uint32_t* point_list;   // sorted visible ranks
   const float2* means2D;
   const float4* conic_opacity;
-  const float4* rgbd;        // geometry rgb + depth, or depth-only w when colours are precomputed
-  const float* colors_precomp;  // null unless the caller supplied colours
+  const float4* rgbd;        // (r, g, b, depth) per visible rank
+  const uint32_t* gid;       // visible rank -> Gaussian id (n_touched only)
   const float* bg;
   float* out_color;
   float* out_depth;
@@ -85,18 +89,17 @@ struct RenderBwdParams {
   int W, H;
   uint32_t grid_x, grid_y;
   const uint2* ranges;
-  const uint32_t* point_list;
+  const uint32_t* point_list;   // sorted visible ranks
   const float2* means2D;
   const float4* conic_opacity;
   const float4* rgbd;
-  const float* colors_precomp;
   const float* bg;
   const float* out_alpha;
   const uint32_t* n_contrib;
   const float* dL_dpix;
   const float* dL_ddepth;
   const float* dL_dalpha;
-  float* grad_acc;           // [P][12]: mean2D.xy, conic.xyw, opacity, rgb, depth, pad, pad
+  float* grad_acc;           // [Pv][12]: mean2D.xy, conic.xyw, opacity, rgb, depth, pad, pad
 };
 void launch_render_bwd(const RenderBwdParams& p, cudaStream_t stream);
 
@@ -126,6 +129,7 @@ struct PreBwdParams {
   float* dL_drot;      // [P,4]
   float* dL_dtau;      // [6] or null
 };
-void launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream);
+// one thread per visible Gaussian; max_visible is a host upper bound (P), the exact count is read on the device
+void launch_preprocess_bwd(const PreBwdParams& p, int max_visible, cudaStream_t stream);
 
 }  // namespace gsr

@@ -81,71 +81,77 @@ __device__ __forceinline__ float3 compute_cov2D(float tx, float ty, float tz, fl
   return cov;
 }
 
-// reference forward.cu:20-71.  `sh` points at this Gaussian's M*3 coefficients.
+// reference forward.cu:20-71.  `sh` points at this Gaussian's M*3 coefficients.  Evaluated in
+// groups of four coefficients (= three 16-byte loads) to keep register pressure low.
 template <bool VEC4>
-__device__ __forceinline__ float3 color_from_sh(int deg, int M, float3 pos, float3 campos, const float* __restrict__ sh,
+__device__ __forceinline__ float3 color_from_sh(int deg, float3 pos, float3 campos, const float* __restrict__ sh,
                                                 uint8_t& clamp_mask) {
   float3 dir = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
   const float len = sqrtf(__fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.x, dir.x, dir.y * dir.y)));
   const float x = dir.x / len, y = dir.y / len, z = dir.z / len;
-  float c[48];
-  const int n = (deg == 0 ? 1 : deg == 1 ? 4 : deg == 2 ? 9 : 16) * 3;
-  if (VEC4) {
-    const float4* s4 = reinterpret_cast<const float4*>(sh);
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+  float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+  const int ngroups = deg == 0 ? 1 : deg == 1 ? 1 : deg == 2 ? 3 : 4;   // groups of 4 coefficients
 #pragma unroll
-    for (int q = 0; q < 12; q++) {
-      if (q * 4 < n) {
-        const float4 v = __ldg(s4 + q);
-        c[4 * q] = v.x, c[4 * q + 1] = v.y, c[4 * q + 2] = v.z, c[4 * q + 3] = v.w;
+  for (int g = 0; g < 4; g++) {
+    if (g < ngroups) {
+      float w[4];
+      if (g == 0) { w[0] = SH_C0; w[1] = -SH_C1 * y; w[2] = SH_C1 * z; w[3] = -SH_C1 * x; }
+      else if (g == 1) { w[0] = SH_C2[0] * xy; w[1] = SH_C2[1] * yz; w[2] = SH_C2[2] * (2.0f * zz - xx - yy); w[3] = SH_C2[3] * xz; }
+      else if (g == 2) { w[0] = SH_C2[4] * (xx - yy); w[1] = SH_C3[0] * y * (3.0f * xx - yy); w[2] = SH_C3[1] * xy * z;
+                         w[3] = SH_C3[2] * y * (4.0f * zz - xx - yy); }
+      else { w[0] = SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy); w[1] = SH_C3[4] * x * (4.0f * zz - xx - yy);
+             w[2] = SH_C3[5] * z * (xx - yy); w[3] = SH_C3[6] * x * (xx - 3.0f * yy); }
+      // number of valid coefficients in this group for the active degree
+      const int ncoef = (deg + 1) * (deg + 1);
+      float c[12];
+      if (VEC4) {
+        const float4* s4 = reinterpret_cast<const float4*>(sh + 12 * g);
+        const float4 v0 = __ldg(s4), v1 = __ldg(s4 + 1), v2 = __ldg(s4 + 2);
+        c[0] = v0.x, c[1] = v0.y, c[2] = v0.z, c[3] = v0.w, c[4] = v1.x, c[5] = v1.y, c[6] = v1.z, c[7] = v1.w;
+        c[8] = v2.x, c[9] = v2.y, c[10] = v2.z, c[11] = v2.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 12; q++) c[q] = (4 * g + q / 3 < ncoef) ? __ldg(sh + 12 * g + q) : 0.f;
       }
-    }
-  } else {
 #pragma unroll
-    for (int q = 0; q < 48; q++)
-      if (q < n) c[q] = __ldg(sh + q);
-  }
-  (void)M;
-  float res[3];
-#pragma unroll
-  for (int ch = 0; ch < 3; ch++) {
-    float r = SH_C0 * c[ch];
-    if (deg > 0) {
-      r = r - SH_C1 * y * c[3 + ch] + SH_C1 * z * c[6 + ch] - SH_C1 * x * c[9 + ch];
-      if (deg > 1) {
-        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-        r = r + SH_C2[0] * xy * c[12 + ch] + SH_C2[1] * yz * c[15 + ch] + SH_C2[2] * (2.0f * zz - xx - yy) * c[18 + ch] +
-            SH_C2[3] * xz * c[21 + ch] + SH_C2[4] * (xx - yy) * c[24 + ch];
-        if (deg > 2) {
-          r = r + SH_C3[0] * y * (3.0f * xx - yy) * c[27 + ch] + SH_C3[1] * xy * z * c[30 + ch] +
-              SH_C3[2] * y * (4.0f * zz - xx - yy) * c[33 + ch] +
-              SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * c[36 + ch] +
-              SH_C3[4] * x * (4.0f * zz - xx - yy) * c[39 + ch] + SH_C3[5] * z * (xx - yy) * c[42 + ch] +
-              SH_C3[6] * x * (xx - 3.0f * yy) * c[45 + ch];
+      for (int k = 0; k < 4; k++) {
+        if (4 * g + k < ncoef) {
+          r0 += w[k] * c[3 * k];
+          r1 += w[k] * c[3 * k + 1];
+          r2 += w[k] * c[3 * k + 2];
         }
       }
     }
-    r += 0.5f;
-    res[ch] = r;
   }
-  clamp_mask = (res[0] < 0 ? 1 : 0) | (res[1] < 0 ? 2 : 0) | (res[2] < 0 ? 4 : 0);
-  return make_float3(fmaxf(res[0], 0.f), fmaxf(res[1], 0.f), fmaxf(res[2], 0.f));
+  r0 += 0.5f, r1 += 0.5f, r2 += 0.5f;
+  clamp_mask = (r0 < 0 ? 1 : 0) | (r1 < 0 ? 2 : 0) | (r2 < 0 ? 4 : 0);
+  return make_float3(fmaxf(r0, 0.f), fmaxf(r1, 0.f), fmaxf(r2, 0.f));
+}
+
+// status word of the decoupled look-back: flag (2 bits) | visible count (30 bits) | tile count (32 bits)
+__device__ __forceinline__ unsigned long long pack_status(uint32_t flag, uint32_t vis, uint32_t tiles) {
+  return ((unsigned long long)flag << 62) | ((unsigned long long)vis << 32) | tiles;
 }
 
 template <bool ALIGNED>
-__global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreprocessParams p) {
-  __shared__ uint32_t s_block;
-  __shared__ uint32_t s_warp_sum[PRE_THREADS / 32];
-  __shared__ uint32_t s_prefix;
+__global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_fwd_kernel(const PreprocessParams p) {
+  __shared__ uint32_t s_warp_tiles[PRE_THREADS / 32];
+  __shared__ uint32_t s_warp_vis[PRE_THREADS / 32];
+  __shared__ uint32_t s_prefix_tiles, s_prefix_vis, s_block_vis;
   __shared__ __align__(16) float s_means[PRE_THREADS * 3];
   __shared__ float s_cam[16 + 16 + 4];
+  __shared__ uint16_t s_vis_tid[PRE_THREADS];
+  __shared__ float s_vis_depth[PRE_THREADS];
 
   const int tid = threadIdx.x;
-  if (tid == 0) s_block = atomicAdd(&p.geom.counters[0], 1u);  // ticket = processing order
+  const uint32_t lane = tid & 31, warp = tid >> 5;
   if (tid < 16) s_cam[tid] = p.viewmatrix[tid];
   else if (tid < 32) s_cam[tid] = p.projmatrix[tid - 16];
   else if (tid < 35) s_cam[tid] = p.campos[tid - 32];
-  __syncthreads();
-  const uint32_t block = s_block;
+  // CTAs are dispatched in blockIdx order, so every predecessor the look-back waits on is
+  // already resident or finished (same assumption as CUB's single-pass scan).
+  const uint32_t block = blockIdx.x;
   const int base = (int)block * PRE_THREADS;
   const int idx = base + tid;
   const int P = p.P;
@@ -167,12 +173,16 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const Prepr
 
   uint32_t tiles = 0;
   int radius = 0;
+  float vz = 0.f, pix_x = 0.f, pix_y = 0.f;
+  float3 conic = {0, 0, 0};
+  float cov3D[6];
+  uint2 rect = {0, 0};
   if (idx < P) {
     const float* vm = s_cam;
     const float* pm = s_cam + 16;
     const float px = s_means[3 * tid], py = s_means[3 * tid + 1], pz = s_means[3 * tid + 2];
     // in_frustum: p_view.z <= 0.2 culls (NaN culls too)
-    const float vz = __fadd_rn(dot3c(px, vm[2], py, vm[6], pz, vm[10]), vm[14]);
+    vz = __fadd_rn(dot3c(px, vm[2], py, vm[6], pz, vm[10]), vm[14]);
     if (vz > 0.2f) {
       const float vx = __fadd_rn(dot3c(px, vm[0], py, vm[4], pz, vm[8]), vm[12]);
       const float vy = __fadd_rn(dot3c(px, vm[1], py, vm[5], pz, vm[9]), vm[13]);
@@ -181,8 +191,6 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const Prepr
       const float hw = __fadd_rn(dot3c(px, pm[3], py, pm[7], pz, pm[11]), pm[15]);
       const float p_w = __frcp_rn(__fadd_rn(hw, 0.0000001f));
       const float projx = __fmul_rn(hx, p_w), projy = __fmul_rn(hy, p_w);
-
-      float cov3D[6];
       if (p.cov3D_precomp) {
 #pragma unroll
         for (int k = 0; k < 6; k++) cov3D[k] = __ldg(p.cov3D_precomp + 6 * (size_t)idx + k);
@@ -196,14 +204,14 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const Prepr
       const float det = __fmaf_rn(cov.x, cov.z, -__fmul_rn(cov.y, cov.y));
       if (det != 0.0f) {
         const float det_inv = __frcp_rn(det);
-        const float3 conic = {__fmul_rn(cov.z, det_inv), __fmul_rn(cov.y, -det_inv), __fmul_rn(cov.x, det_inv)};
+        conic = make_float3(__fmul_rn(cov.z, det_inv), __fmul_rn(cov.y, -det_inv), __fmul_rn(cov.x, det_inv));
         const float mid = __fmul_rn(__fadd_rn(cov.x, cov.z), 0.5f);
         const float s = __fsqrt_rn(fmaxf(__fmaf_rn(mid, mid, -det), 0.1f));
         const float lambda1 = __fadd_rn(mid, s), lambda2 = __fadd_rn(mid, -s);
         const int my_radius = __float2int_ru(__fmul_rn(__fsqrt_rn(fmaxf(lambda1, lambda2)), 3.0f));
         // ndc2Pix in double with one DFMA (auxiliary.h:41-44)
-        const float pix_x = (float)(__dmul_rn(__fma_rn(__dadd_rn((double)projx, 1.0), (double)p.W, -1.0), 0.5));
-        const float pix_y = (float)(__dmul_rn(__fma_rn(__dadd_rn((double)projy, 1.0), (double)p.H, -1.0), 0.5));
+        pix_x = (float)(__dmul_rn(__fma_rn(__dadd_rn((double)projx, 1.0), (double)p.W, -1.0), 0.5));
+        pix_y = (float)(__dmul_rn(__fma_rn(__dadd_rn((double)projy, 1.0), (double)p.H, -1.0), 0.5));
         // getRect (auxiliary.h:46-56)
         const float rf = (float)my_radius;
         const uint32_t gx = p.grid_x, gy = p.grid_y;
@@ -213,29 +221,9 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const Prepr
         const uint32_t maxy = min(gy, (uint32_t)max(0, __float2int_rz(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(pix_y, rf), 16.0f), -1.0f), 0.0625f))));
         const uint32_t cnt = (maxx - minx) * (maxy - miny);
         if (cnt != 0) {
-          float3 rgb;
-          uint8_t cm = 0;
-          if (p.colors_precomp) {
-            rgb = make_float3(__ldg(p.colors_precomp + 3 * (size_t)idx), __ldg(p.colors_precomp + 3 * (size_t)idx + 1),
-                              __ldg(p.colors_precomp + 3 * (size_t)idx + 2));
-          } else {
-            const float3 cp = {s_cam[32], s_cam[33], s_cam[34]};
-            const float* sh = p.shs + (size_t)idx * p.M * 3;
-            if (p.sh_vec4) rgb = color_from_sh<true>(p.D, p.M, make_float3(px, py, pz), cp, sh, cm);
-            else rgb = color_from_sh<false>(p.D, p.M, make_float3(px, py, pz), cp, sh, cm);
-          }
-          if (!p.cov3D_precomp) {
-#pragma unroll
-            for (int k = 0; k < 6; k++) p.geom.cov3D[6 * (size_t)idx + k] = cov3D[k];
-          }
-          p.geom.depths[idx] = vz;
-          p.geom.means2D[idx] = make_float2(pix_x, pix_y);
-          p.geom.conic_opacity[idx] = make_float4(conic.x, conic.y, conic.z, __ldg(p.opacities + idx));
-          p.geom.rgbd[idx] = make_float4(rgb.x, rgb.y, rgb.z, vz);
-          p.geom.rect[idx] = make_uint2(minx | (maxx << 16), miny | (maxy << 16));
-          p.geom.clamped[idx] = cm;
           tiles = cnt;
           radius = my_radius;
+          rect = make_uint2(minx | (maxx << 16), miny | (maxy << 16));
         }
       }
     } else if (p.prefiltered) {
@@ -244,64 +232,118 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const Prepr
       __trap();
     }
     p.radii[idx] = radius;
-    p.geom.tiles_touched[idx] = tiles;
     if (p.n_touched) p.n_touched[idx] = 0;
   }
 
-  // ---- CTA inclusive scan of `tiles`
-  const uint32_t lane = tid & 31, warp = tid >> 5;
+  // ---- CTA scan: tiles by shuffle, visible rank by ballot
+  const bool vis = tiles != 0;
+  const uint32_t vis_mask = __ballot_sync(0xffffffffu, vis);
+  const uint32_t vis_rank_in_warp = __popc(vis_mask & ((1u << lane) - 1u));
   uint32_t incl = tiles;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += n;
   }
-  if (lane == 31) s_warp_sum[warp] = incl;
+  if (lane == 31) s_warp_tiles[warp] = incl;
+  if (lane == 0) s_warp_vis[warp] = __popc(vis_mask);
   __syncthreads();
   if (warp == 0) {
-    uint32_t ws = lane < PRE_THREADS / 32 ? s_warp_sum[lane] : 0;
-    uint32_t wincl = ws;
+    const uint32_t wt = lane < PRE_THREADS / 32 ? s_warp_tiles[lane] : 0;
+    const uint32_t wv = lane < PRE_THREADS / 32 ? s_warp_vis[lane] : 0;
+    uint32_t it = wt, iv = wv;
 #pragma unroll
     for (int o = 1; o < PRE_THREADS / 32; o <<= 1) {
-      const uint32_t n = __shfl_up_sync(0xffffffffu, wincl, o);
-      if (lane >= o) wincl += n;
+      const uint32_t nt = __shfl_up_sync(0xffffffffu, it, o);
+      const uint32_t nv = __shfl_up_sync(0xffffffffu, iv, o);
+      if (lane >= o) it += nt, iv += nv;
     }
-    if (lane < PRE_THREADS / 32) s_warp_sum[lane] = wincl - ws;  // exclusive warp offsets
-    const uint32_t block_total = __shfl_sync(0xffffffffu, wincl, PRE_THREADS / 32 - 1);
+    if (lane < PRE_THREADS / 32) s_warp_tiles[lane] = it - wt, s_warp_vis[lane] = iv - wv;  // exclusive warp offsets
+    const uint32_t block_tiles = __shfl_sync(0xffffffffu, it, PRE_THREADS / 32 - 1);
+    const uint32_t block_vis = __shfl_sync(0xffffffffu, iv, PRE_THREADS / 32 - 1);
 
-    // ---- decoupled look-back across CTAs (status word = flag<<32 | value; 1 aggregate, 2 inclusive)
+    // ---- decoupled look-back across CTAs (flag 1 = aggregate, 2 = inclusive prefix)
     volatile unsigned long long* status = p.geom.scan_status;
-    uint32_t exclusive = 0;
+    uint32_t ex_tiles = 0, ex_vis = 0;
     if (block == 0) {
-      if (lane == 0) status[0] = (2ull << 32) | block_total;
+      if (lane == 0) status[0] = pack_status(2, block_vis, block_tiles);
     } else {
-      if (lane == 0) status[block] = (1ull << 32) | block_total;
+      if (lane == 0) status[block] = pack_status(1, block_vis, block_tiles);
       int look = (int)block - 1;
       while (true) {
         const int j = look - (int)lane;
-        unsigned long long w = j >= 0 ? status[j] : (2ull << 32);
-        // wait until every word in the window is published
-        while (__any_sync(0xffffffffu, (w >> 32) == 0)) {
-          if ((w >> 32) == 0) w = status[j];
+        unsigned long long w = j >= 0 ? status[j] : pack_status(2, 0, 0);
+        while (__any_sync(0xffffffffu, (w >> 62) == 0)) {
+          if ((w >> 62) == 0) w = status[j];
         }
-        const uint32_t incl_mask = __ballot_sync(0xffffffffu, (w >> 32) == 2);
-        const uint32_t upto = incl_mask ? (uint32_t)(__ffs(incl_mask) - 1) : 31u;  // first inclusive lane
-        uint32_t v = lane <= upto ? (uint32_t)w : 0u;
+        const uint32_t incl_mask = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+        const uint32_t upto = incl_mask ? (uint32_t)(__ffs(incl_mask) - 1) : 31u;  // nearest inclusive word
+        uint32_t vt = lane <= upto ? (uint32_t)w : 0u;
+        uint32_t vv = lane <= upto ? (uint32_t)((w >> 32) & 0x3fffffffu) : 0u;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        exclusive += v;
+        for (int o = 16; o > 0; o >>= 1) {
+          vt += __shfl_xor_sync(0xffffffffu, vt, o);
+          vv += __shfl_xor_sync(0xffffffffu, vv, o);
+        }
+        ex_tiles += vt;
+        ex_vis += vv;
         if (incl_mask) break;
         look -= 32;
       }
-      if (lane == 0) status[block] = (2ull << 32) | (unsigned long long)(exclusive + block_total);
+      if (lane == 0) status[block] = pack_status(2, ex_vis + block_vis, ex_tiles + block_tiles);
     }
     if (lane == 0) {
-      s_prefix = exclusive;
-      if (block == gridDim.x - 1) p.geom.counters[1] = exclusive + block_total;  // num_rendered
+      s_prefix_tiles = ex_tiles;
+      s_prefix_vis = ex_vis;
+      s_block_vis = block_vis;
+      if (block == gridDim.x - 1) {
+        p.geom.counters[1] = ex_tiles + block_tiles;  // num_rendered
+        p.geom.counters[2] = ex_vis + block_vis;      // num_visible
+      }
     }
   }
   __syncthreads();
-  if (idx < P) p.geom.point_offsets[idx] = s_prefix + s_warp_sum[warp] + incl;
+
+  // ---- compact per-visible records (Gaussian order preserved)
+  const uint32_t vis_base = s_prefix_vis;
+  if (vis) {
+    const uint32_t lr = s_warp_vis[warp] + vis_rank_in_warp;   // rank inside the CTA
+    const uint32_t k = vis_base + lr;
+    s_vis_tid[lr] = (uint16_t)tid;
+    s_vis_depth[lr] = vz;
+    p.geom.depths[k] = vz;
+    p.geom.means2D[k] = make_float2(pix_x, pix_y);
+    p.geom.conic_opacity[k] = make_float4(conic.x, conic.y, conic.z, __ldg(p.opacities + idx));
+    p.geom.rect[k] = rect;
+    p.geom.gid[k] = (uint32_t)idx;
+    p.geom.tiles_touched[k] = tiles;
+    p.geom.point_offsets[k] = s_prefix_tiles + s_warp_tiles[warp] + incl;
+    if (!p.cov3D_precomp) {
+#pragma unroll
+      for (int q = 0; q < 6; q++) p.geom.cov3D[6 * (size_t)k + q] = cov3D[q];
+    }
+  }
+  __syncthreads();
+
+  // ---- colour for the CTA's visible Gaussians only, on dense lanes
+  const uint32_t nvis = s_block_vis;
+  for (uint32_t lr = tid; lr < nvis; lr += PRE_THREADS) {
+    const uint32_t t = s_vis_tid[lr];
+    const size_t g = (size_t)base + t;
+    float3 rgb;
+    uint8_t cm = 0;
+    if (p.colors_precomp) {
+      rgb = make_float3(__ldg(p.colors_precomp + 3 * g), __ldg(p.colors_precomp + 3 * g + 1), __ldg(p.colors_precomp + 3 * g + 2));
+    } else {
+      const float3 cp = {s_cam[32], s_cam[33], s_cam[34]};
+      const float3 pos = {s_means[3 * t], s_means[3 * t + 1], s_means[3 * t + 2]};
+      const float* sh = p.shs + g * p.M * 3;
+      if (p.sh_vec4) rgb = color_from_sh<true>(p.D, pos, cp, sh, cm);
+      else rgb = color_from_sh<false>(p.D, pos, cp, sh, cm);
+    }
+    p.geom.rgbd[vis_base + lr] = make_float4(rgb.x, rgb.y, rgb.z, s_vis_depth[lr]);
+    p.geom.clamped[vis_base + lr] = cm;
+  }
 }
 
 void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream) {

@@ -195,4 +195,6 @@ def export_state(P, R, W, H, geomBuffer, binningBuffer, imgBuffer):
                                   *[_ptr(out[k]) for k in order], _stream(dev))
     _lib.check(rc, "gsr_export_state")
     torch.cuda.synchronize(dev)
+    # the library keeps offsets per visible Gaussian only; the reference's per-Gaussian array is their prefix sum
+    out["point_offsets"] = torch.cumsum(out["tiles_touched"].to(torch.int64), 0).to(torch.int32)
     return out
