@@ -70,6 +70,9 @@ class ClockSampler:
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:   # nvidia-smi takes a moment to emit its first sample
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 

@@ -44,7 +44,7 @@ SIGNATURES = {
         _P,
         C.c_int, _P]),
     "gsr_mark_visible": (C.c_int, [C.c_int, _P, _P, _P, _P, _P]),
-    "gsr_export_state": (C.c_int, [C.c_int, C.c_longlong, C.c_int, C.c_int] + [_P] * 3 + [_P] * 14 + [_P]),
+    "gsr_export_state": (C.c_int, [C.c_int, C.c_longlong, C.c_int, C.c_int] + [_P] * 3 + [_P] * 11 + [_P]),
     "gsr_stage_timing": (None, [C.c_int]),
     "gsr_stage_times": (C.c_int, [_P, _P, C.c_int]),
     "gsr_sort_temp_bytes": (C.c_size_t, [C.c_longlong]),

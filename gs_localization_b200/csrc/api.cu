@@ -44,26 +44,10 @@ int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail(GSR_ERR_CUDA, "stage %s: %s", name, cudaGetErrorString(e__)); \
   } while (0)
 
-struct BinningLayout {
-  uint64_t* keys[2];
-  uint32_t* vals[2];
-  char* sort_temp;
-};
-
-int sort_end_bit(int W, int H) {
-  const uint32_t gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
-  return 32 + (int)get_higher_msb(gx * gy);   // reference rasterizer_impl.cu:301,309
-}
-
-char* carve_binning(char* base, long long R, int W, int H, BinningLayout& b) {
+char* carve_binning(char* base, long long R, BinningView& b) {
   char* p = base;
-  carve(p, b.keys[0], (size_t)R);
-  carve(p, b.keys[1], (size_t)R);
-  carve(p, b.vals[0], (size_t)R);
-  carve(p, b.vals[1], (size_t)R);
-  p = (char*)align_up((size_t)p, 128);
-  b.sort_temp = p;
-  p += sort_temp_bytes(R, sort_passes(sort_end_bit(W, H)));
+  carve(p, b.comp, (size_t)R);
+  carve(p, b.point_list, (size_t)R);
   return p;
 }
 
@@ -112,6 +96,28 @@ void stage_collect(cudaStream_t stream) {
   }
 }
 
+// Side stream for the dense zero-fills of the backward: they run at copy bandwidth concurrently with the
+// (compute-bound) blend backward and re-join before the per-Gaussian kernel.  Fork/join through events,
+// which is also legal while the caller's stream is being captured into a CUDA graph.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+  static std::mutex mu;
+  static SideStream per_device[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  SideStream& s = per_device[dev];
+  if (!s.stream) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &s;
+}
+
 // pinned 4-byte mailbox for num_rendered, one per host thread
 uint32_t* pinned_mailbox() {
   thread_local uint32_t* box = nullptr;
@@ -139,8 +145,9 @@ size_t gsr_image_bytes(int width, int height) {
   return (size_t)end + 128;
 }
 size_t gsr_binning_bytes(long long num_rendered, int width, int height) {
-  BinningLayout b;
-  char* end = carve_binning(nullptr, num_rendered, width, height, b);
+  (void)width, (void)height;
+  BinningView b;
+  char* end = carve_binning(nullptr, num_rendered, b);
   return (size_t)end + 128;
 }
 
@@ -173,16 +180,14 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
   carve_image(img_base, width, height, im);
 
   long long R = 0;
-  int Pv = 0;
   GeometryView g{};
-  BinningLayout bl{};
-  int final_buf = 0;
+  BinningView bl{};
   if (P > 0) {
     char* geom_base = geometry_alloc(gsr_geometry_bytes(P), user);
     if (!geom_base) return fail(GSR_ERR_ALLOC, "geometry_alloc returned NULL");
     carve_geometry(geom_base, P, g);
-    // scan status words + counters are contiguous: one small memset
-    GSR_CUDA(cudaMemsetAsync(g.scan_status, 0, (size_t)((char*)(g.counters + 32) - (char*)g.scan_status), stream));
+    GSR_CUDA(cudaMemsetAsync(g.counters, 0, 32 * sizeof(uint32_t), stream));
+    GSR_CUDA(cudaMemsetAsync(im.tile_diff, 0, sizeof(int) * (size_t)(gx + 1) * (gy + 1), stream));
 
     PreprocessParams pp{};
     pp.P = P, pp.D = D, pp.M = M, pp.W = width, pp.H = height, pp.grid_x = gx, pp.grid_y = gy;
@@ -194,57 +199,49 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     pp.focal_x = width / (2.0f * tan_fovx);
     pp.prefiltered = prefiltered;
     pp.sh_vec4 = shs && (M % 4 == 0) && ((uintptr_t)shs % 16 == 0);
-    pp.radii = radii, pp.n_touched = n_touched, pp.geom = g;
+    pp.radii = radii, pp.n_touched = n_touched, pp.tile_diff = im.tile_diff, pp.geom = g;
     {
       StageScope ts(ST_PREPROCESS, stream);
       launch_preprocess_fwd(pp, stream);
     }
     GSR_STAGE("preprocess", debug, stream);
+    {
+      StageScope ts(ST_RANGES, stream);
+      launch_scan_tiles(im.tile_diff, gx, gy, im.ranges, im.tile_cursor, im.tile_order, g.counters, stream);
+    }
+    GSR_STAGE("scan_tiles", debug, stream);
 
-    // num_rendered (and the visible count) -> host: the one sync the reference also has (rasterizer_impl.cu:282)
+    // num_rendered -> host: the one sync the reference also has (rasterizer_impl.cu:282)
     uint32_t* box = pinned_mailbox();
     if (!box) return fail(GSR_ERR_CUDA, "cudaHostAlloc failed");
-    GSR_CUDA(cudaMemcpyAsync(box, g.counters + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    GSR_CUDA(cudaMemcpyAsync(box, g.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     GSR_CUDA(cudaStreamSynchronize(stream));
     R = (long long)box[0];
-    Pv = (int)box[1];
+  } else {
+    GSR_CUDA(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)T, stream));
   }
 
-  if (R > 0) {
+  {
     char* bin_base = binning_alloc(gsr_binning_bytes(R, width, height), user);
     if (!bin_base) return fail(GSR_ERR_ALLOC, "binning_alloc returned NULL");
-    carve_binning(bin_base, R, width, height, bl);
-    const int end_bit = sort_end_bit(width, height);
-    const int passes = sort_passes(end_bit);
-    SortTemp st;
-    carve_sort_temp(bl.sort_temp, R, passes, st);
+    carve_binning(bin_base, R, bl);
+  }
+  if (R > 0) {
     {
       StageScope ts(ST_DUPLICATE, stream);
-      sort_temp_reset(bl.sort_temp, R, passes, stream);
-      launch_emit_keys(Pv, g, bl.keys[0], bl.vals[0], gx, (uint32_t)R, stream);
+      launch_scatter(P, g, im.tile_cursor, bl.comp, gx, (uint32_t)R, stream);
     }
-    GSR_STAGE("emit_keys", debug, stream);
+    GSR_STAGE("scatter", debug, stream);
     {
       StageScope ts(ST_SORT, stream);
-      launch_sort_histogram(bl.keys[0], nullptr, R, end_bit, st.hist, stream);
-      final_buf = launch_onesweep(bl.keys, bl.vals, nullptr, R, end_bit, st, stream);
+      launch_tile_sort(T, im.ranges, bl.comp, bl.point_list, (uint32_t)R, stream);
     }
-    GSR_STAGE("radix_sort", debug, stream);
-  } else {
-    // keep the callback contract: the binning buffer exists (possibly tiny) even when nothing is visible
-    char* bin_base = binning_alloc(gsr_binning_bytes(0, width, height), user);
-    if (!bin_base) return fail(GSR_ERR_ALLOC, "binning_alloc returned NULL");
-    carve_binning(bin_base, 0, width, height, bl);
+    GSR_STAGE("tile_sort", debug, stream);
   }
-  {
-    StageScope ts(ST_RANGES, stream);
-    launch_identify_tile_ranges(nullptr, R, bl.keys[final_buf], im.ranges, T, stream);
-  }
-  GSR_STAGE("identify_tile_ranges", debug, stream);
 
   RenderParams rp{};
   rp.W = width, rp.H = height, rp.grid_x = gx, rp.grid_y = gy;
-  rp.ranges = im.ranges, rp.point_list = bl.vals[final_buf];
+  rp.ranges = im.ranges, rp.point_list = bl.point_list, rp.tile_order = (P > 0) ? im.tile_order : nullptr;
   rp.means2D = g.means2D, rp.conic_opacity = g.conic_opacity, rp.rgbd = g.rgbd, rp.gid = g.gid;
   rp.bg = background, rp.out_color = out_color, rp.out_depth = out_depth, rp.out_alpha = out_alpha;
   rp.n_contrib = im.n_contrib, rp.n_touched = (P > 0) ? n_touched : nullptr;
@@ -281,19 +278,34 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
   carve_geometry(geometry_buffer, P, g);
   ImageView im;
   carve_image(image_buffer, width, height, im);
-  BinningLayout bl;
-  carve_binning(binning_buffer, R, width, height, bl);
-  const int final_buf = R > 0 ? (sort_passes(sort_end_bit(width, height)) & 1) : 0;
+  BinningView bl;
+  carve_binning(binning_buffer, R, bl);
 
+  // dense outputs: zero rows for culled Gaussians (the reference's nine torch::zeros, rasterize_points.cu:158-166)
+  // are filled on a side stream while the blend backward runs
+  {
+    SideStream* ss = side_stream();
+    cudaStream_t fill = ss ? ss->stream : stream;
+    if (ss) {
+      GSR_CUDA(cudaEventRecord(ss->fork, stream));
+      GSR_CUDA(cudaStreamWaitEvent(fill, ss->fork, 0));
+    }
+    const size_t Pz = (size_t)P;
+    struct { float* p; size_t n; } fills[] = {{dL_dmean2D, 3 * Pz}, {dL_dconic, 4 * Pz}, {dL_dopacity, Pz}, {dL_dcolor, 3 * Pz},
+                                             {dL_dmean3D, 3 * Pz}, {dL_dcov3D, 6 * Pz}, {dL_dsh, 3 * (size_t)M * Pz},
+                                             {dL_dscale, 3 * Pz}, {dL_drot, 4 * Pz}};
+    for (auto& f : fills)
+      if (f.p && f.n) GSR_CUDA(cudaMemsetAsync(f.p, 0, sizeof(float) * f.n, fill));
+    if (ss) GSR_CUDA(cudaEventRecord(ss->join, fill));
+  }
+
+  // the accumulator rows of all visible slots are zero here: the forward's scatter kernel zeroed
+  // them and every preprocess-backward leaves them zero again
   StageScope* ts_r = new StageScope(ST_BWD_RENDER, stream);
-  // accumulator rows exist only for visible Gaussians, and every visible Gaussian owns >= 1 instance
-  const size_t acc_rows = (size_t)std::min<long long>(P, R);
-  cudaError_t me = acc_rows ? cudaMemsetAsync(g.grad_acc, 0, sizeof(float) * 12 * acc_rows, stream) : cudaSuccess;
-  if (me != cudaSuccess) { delete ts_r; return fail(GSR_ERR_CUDA, "memset grad_acc: %s", cudaGetErrorString(me)); }
   if (R > 0) {
     RenderBwdParams rb{};
     rb.W = width, rb.H = height, rb.grid_x = gx, rb.grid_y = gy;
-    rb.ranges = im.ranges, rb.point_list = bl.vals[final_buf];
+    rb.ranges = im.ranges, rb.point_list = bl.point_list, rb.tile_order = im.tile_order;
     rb.means2D = g.means2D, rb.conic_opacity = g.conic_opacity, rb.rgbd = g.rgbd;
     rb.bg = background, rb.out_alpha = out_alpha, rb.n_contrib = im.n_contrib;
     rb.dL_dpix = dL_dpix, rb.dL_ddepth = dL_ddepth, rb.dL_dalpha = dL_dalpha, rb.grad_acc = g.grad_acc;
@@ -313,17 +325,10 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
   pb.dL_dmean2D = dL_dmean2D, pb.dL_dconic = dL_dconic, pb.dL_dopacity = dL_dopacity, pb.dL_dcolor = dL_dcolor;
   pb.dL_dmean3D = dL_dmean3D, pb.dL_dcov3D = dL_dcov3D, pb.dL_dsh = dL_dsh, pb.dL_dscale = dL_dscale, pb.dL_drot = dL_drot;
   pb.dL_dtau = dL_dtau;
+  if (SideStream* ss = side_stream()) GSR_CUDA(cudaStreamWaitEvent(stream, ss->join, 0));
   {
     StageScope ts(ST_BWD_PREPROCESS, stream);
-    // dense outputs: zero rows for culled Gaussians (the reference's torch::zeros, rasterize_points.cu:158-166),
-    // then one thread per visible Gaussian writes its rows
-    const size_t Pz = (size_t)P;
-    struct { float* p; size_t n; } fills[] = {{dL_dmean2D, 3 * Pz}, {dL_dconic, 4 * Pz}, {dL_dopacity, Pz}, {dL_dcolor, 3 * Pz},
-                                             {dL_dmean3D, 3 * Pz}, {dL_dcov3D, 6 * Pz}, {dL_dsh, 3 * (size_t)M * Pz},
-                                             {dL_dscale, 3 * Pz}, {dL_drot, 4 * Pz}};
-    for (auto& f : fills)
-      if (f.p && f.n) GSR_CUDA(cudaMemsetAsync(f.p, 0, sizeof(float) * f.n, stream));
-    if (R > 0) launch_preprocess_bwd(pb, (int)acc_rows, stream);
+    if (R > 0) launch_preprocess_bwd(pb, stream);
   }
   GSR_STAGE("preprocess_backward", debug, stream);
   stage_collect(stream);
@@ -345,11 +350,11 @@ int gsr_mark_visible(int P, const float* means3D, const float* viewmatrix, const
 
 // ----------------------------------------------------------------------------- state export (tests)
 namespace {
-// scatter the compact per-visible records back to the reference's per-Gaussian arrays (outputs pre-zeroed)
+// scatter the per-slot records back to the reference's per-Gaussian arrays (outputs pre-zeroed)
 __global__ void export_geometry_kernel(GeometryView g, float* depths, float* means2D, float* cov3D, float* conic_opacity,
                                        float* rgb, unsigned char* clamped, uint32_t* tiles_touched) {
+  if (threadIdx.x >= g.block_vis[blockIdx.x]) return;
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= g.counters[2]) return;
   const size_t i = g.gid[k];
   if (depths) depths[i] = g.depths[k];
   if (means2D) means2D[2 * i] = g.means2D[k].x, means2D[2 * i + 1] = g.means2D[k].y;
@@ -367,12 +372,20 @@ __global__ void export_geometry_kernel(GeometryView g, float* depths, float* mea
     const uint8_t m = g.clamped[k];
     clamped[3 * i] = m & 1, clamped[3 * i + 1] = (m >> 1) & 1, clamped[3 * i + 2] = (m >> 2) & 1;
   }
-  if (tiles_touched) tiles_touched[i] = g.tiles_touched[k];
+  if (tiles_touched) {
+    const uint2 rc = g.rect[k];
+    tiles_touched[i] = ((rc.x >> 16) - (rc.x & 0xffffu)) * ((rc.y >> 16) - (rc.y & 0xffffu));
+  }
 }
-// visible rank -> Gaussian id (the reference's point_list holds Gaussian ids)
-__global__ void translate_ranks_kernel(uint32_t* vals, const uint32_t* gid, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) vals[i] = gid[vals[i]];
+// the reference's sorted arrays: keys = tile << 32 | depth bits, point_list = Gaussian ids
+__global__ void export_sorted_kernel(const uint2* ranges, const uint64_t* comp, const uint32_t* gid, uint64_t* keys,
+                                     uint32_t* list) {
+  const uint2 rg = ranges[blockIdx.x];
+  for (uint32_t i = rg.x + threadIdx.x; i < rg.y; i += blockDim.x) {
+    const uint64_t c = comp[i];
+    if (keys) keys[i] = ((uint64_t)blockIdx.x << 32) | (c >> 32);
+    if (list) list[i] = gid[(uint32_t)c];
+  }
 }
 }  // namespace
 
@@ -380,37 +393,24 @@ extern "C" {
 
 int gsr_export_state(int P, long long R, int width, int height, const char* geometry_buffer, const char* binning_buffer,
                      const char* image_buffer, float* depths, float* means2D, float* cov3D, float* conic_opacity, float* rgb,
-                     unsigned char* clamped, uint32_t* tiles_touched, uint32_t* point_offsets, uint64_t* keys_unsorted,
-                     uint32_t* list_unsorted, uint64_t* keys, uint32_t* list, uint32_t* ranges, uint32_t* n_contrib,
-                     void* stream_) {
+                     unsigned char* clamped, uint32_t* tiles_touched, uint64_t* keys, uint32_t* list, uint32_t* ranges,
+                     uint32_t* n_contrib, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  (void)point_offsets;   // per-Gaussian offsets are the prefix sum of tiles_touched; the caller derives them
   const uint32_t gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
   GeometryView g{};
+  ImageView im{};
+  if (image_buffer) carve_image(const_cast<char*>(image_buffer), width, height, im);
   if (P > 0 && geometry_buffer) {
     carve_geometry(const_cast<char*>(geometry_buffer), P, g);
-    export_geometry_kernel<<<(P + 255) / 256, 256, 0, stream>>>(g, depths, means2D, cov3D, conic_opacity, rgb, clamped,
-                                                              tiles_touched);
+    export_geometry_kernel<<<num_pre_blocks(P), PRE_THREADS, 0, stream>>>(g, depths, means2D, cov3D, conic_opacity, rgb, clamped,
+                                                                       tiles_touched);
   }
-  if (R > 0 && binning_buffer && P > 0 && geometry_buffer) {
-    BinningLayout bl;
-    carve_binning(const_cast<char*>(binning_buffer), R, width, height, bl);
-    const int end_bit = sort_end_bit(width, height);
-    const int fb = sort_passes(end_bit) & 1;
-    const unsigned nb = (unsigned)((R + 255) / 256);
-    if (keys) GSR_CUDA(cudaMemcpyAsync(keys, bl.keys[fb], sizeof(uint64_t) * (size_t)R, cudaMemcpyDeviceToDevice, stream));
-    if (list) {
-      GSR_CUDA(cudaMemcpyAsync(list, bl.vals[fb], sizeof(uint32_t) * (size_t)R, cudaMemcpyDeviceToDevice, stream));
-      translate_ranks_kernel<<<nb, 256, 0, stream>>>(list, g.gid, R);
-    }
-    if (keys_unsorted && list_unsorted) {   // regenerated: the sort's ping-pong overwrote them
-      launch_emit_keys(P, g, keys_unsorted, list_unsorted, gx, (uint32_t)R, stream);
-      translate_ranks_kernel<<<nb, 256, 0, stream>>>(list_unsorted, g.gid, R);
-    }
+  if (R > 0 && binning_buffer && image_buffer && P > 0 && geometry_buffer && (keys || list)) {
+    BinningView bl;
+    carve_binning(const_cast<char*>(binning_buffer), R, bl);
+    export_sorted_kernel<<<gx * gy, 256, 0, stream>>>(im.ranges, bl.comp, g.gid, keys, list);
   }
   if (image_buffer) {
-    ImageView im;
-    carve_image(const_cast<char*>(image_buffer), width, height, im);
     if (ranges) GSR_CUDA(cudaMemcpyAsync(ranges, im.ranges, sizeof(uint2) * (size_t)gx * gy, cudaMemcpyDeviceToDevice, stream));
     if (n_contrib) GSR_CUDA(cudaMemcpyAsync(n_contrib, im.n_contrib, sizeof(uint32_t) * (size_t)width * height, cudaMemcpyDeviceToDevice, stream));
   }

@@ -7,9 +7,9 @@
 //   computeCov3D (backward)          cuda_rasterizer/backward.cu:278-341
 //   the nine torch::zeros fills      rasterize_points.cu:158-166
 //
-// B200 design: the forward left a compact list of the visible Gaussians, so this kernel runs
-// one thread per VISIBLE Gaussian on dense warps (the reference launches P threads of which
-// >90 % exit at once); the two reference kernels are fused, so dL_dcov3D / dL_dmean3D never
+// B200 design: the forward packed the visible Gaussians of every 256-Gaussian segment into the
+// segment's first slots, so each CTA here runs only ceil(visible/32) dense warps (the reference
+// launches P threads, most of which exit at once); the two reference kernels are fused, so dL_dcov3D / dL_dmean3D never
 // round-trip through HBM between them; the dense zero rows the API promises for culled
 // Gaussians are produced by plain memsets at copy-engine bandwidth, and each visible row is
 // then written exactly once.  With dL_dtau != nullptr the SE(3) chain rule is fused in: each
@@ -20,8 +20,7 @@
 
 namespace gsr {
 
-constexpr int BW_THREADS = 128;
-constexpr int SH_MAX_FLOATS = 48;   // (3+1)^2 * 3
+constexpr int BW_THREADS = PRE_THREADS;   // one CTA per preprocess slot segment
 
 // reference auxiliary.h:107-117
 __device__ __forceinline__ float3 dnormvdv(float3 v, float3 dv) {
@@ -101,12 +100,12 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
   __shared__ float s_tau[BW_THREADS / 32][6];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t Pv = p.geom.counters[2];
-  if ((uint32_t)blockIdx.x * BW_THREADS >= Pv) return;
-  const uint32_t k = blockIdx.x * BW_THREADS + tid;     // visible rank
+  const uint32_t nvis = p.geom.block_vis[blockIdx.x];
+  if (nvis == 0) return;
+  const uint32_t k = blockIdx.x * BW_THREADS + tid;     // slot
   const int M = p.M;
   const int row = 3 * M;                 // floats per SH row
-  const bool visible = k < Pv;
+  const bool visible = (uint32_t)tid < nvis;
   const float* vm = p.viewmatrix;
   const float* proj = p.projmatrix;
 
@@ -123,10 +122,9 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
 
   if (visible) {
     idx = __ldg(p.geom.gid + k);
-    const float* acc = p.geom.grad_acc + 12 * (size_t)k;
-    const float4 a0 = *reinterpret_cast<const float4*>(acc);
-    const float4 a1 = *reinterpret_cast<const float4*>(acc + 4);
-    const float4 a2 = *reinterpret_cast<const float4*>(acc + 8);
+    float4* acc = reinterpret_cast<float4*>(p.geom.grad_acc + 12 * (size_t)k);
+    const float4 a0 = acc[0], a1 = acc[1], a2 = acc[2];
+    acc[0] = acc[1] = acc[2] = make_float4(0.f, 0.f, 0.f, 0.f);   // leave the row zero for the next backward
     g_mean2D = make_float3(a0.x, a0.y, 0.f);
     g_conic = make_float4(a0.z, a0.w, 0.f, a1.x);
     g_opacity = a1.y;
@@ -314,11 +312,11 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
   // ---------------- pose gradient: CTA reduction, 6 atomics
   if (p.dL_dtau) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
-      float v = tau[k];
+    for (int c = 0; c < 6; c++) {
+      float v = tau[c];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) s_tau[warp][k] = v;
+      if (lane == 0) s_tau[warp][c] = v;
     }
     __syncthreads();
     if (tid < 6) {
@@ -329,9 +327,9 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
   }
 }
 
-void launch_preprocess_bwd(const PreBwdParams& p, int max_visible, cudaStream_t stream) {
-  if (max_visible <= 0) return;
-  preprocess_bwd_kernel<<<(max_visible + BW_THREADS - 1) / BW_THREADS, BW_THREADS, 0, stream>>>(p);
+void launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream) {
+  if (p.P <= 0) return;
+  preprocess_bwd_kernel<<<num_pre_blocks(p.P), BW_THREADS, 0, stream>>>(p);
   count_launch();
 }
 

@@ -1,23 +1,29 @@
-// Tile binning: key generation, a hand-written stable onesweep LSD radix sort of
-// (u64 tile|depth key, u32 Gaussian id) pairs, and tile-range extraction.
+// Tile binning: per-tile list lengths and ranges from the coverage grid, bucketing of the
+// (Gaussian, tile) instances, a tile-local sort — and the hand-written onesweep LSD radix sort.
 //
 // Replaces, from the reference (gaussian_splatting/submodules/diff-gaussian-rasterization):
+//   cub::DeviceScan::InclusiveSum             cuda_rasterizer/rasterizer_impl.cu:278
 //   duplicateWithKeys                         cuda_rasterizer/rasterizer_impl.cu:70-111
 //   cub::DeviceRadixSort::SortPairs           cuda_rasterizer/rasterizer_impl.cu:304-309 (size query :187-190)
 //   cudaMemset(ranges) + identifyTileRanges   cuda_rasterizer/rasterizer_impl.cu:311-318, 116-138
 //
-// B200 design
-//   * duplicate_with_keys also accumulates the per-digit histograms every sort pass needs
-//     (one shared-memory histogram per CTA, one atomic per Gaussian for the four depth
-//     digits because all of a Gaussian's instances share its depth), so the sort needs no
-//     histogram pass over the 8R bytes of keys.
-//   * onesweep (Adinets & Merrill): one kernel per 8-bit digit; each CTA ranks a 4096-key
-//     tile with warp match_any (stable), chains its per-digit counts to its predecessors
-//     with a decoupled look-back, stages the tile in shared memory in sorted order and
-//     writes runs of equal digits out contiguously.  Each pass reads and writes every
-//     pair exactly once (12R + 12R bytes).
-//   * Stability is required: instances with equal (tile, depth bits) must stay in Gaussian
-//     order as with the reference's CUB sort, otherwise point_list diverges.
+// B200 design.  The reference sorts all R instances globally on a 64-bit tile|depth key (six
+// 8-bit passes, each reading and writing 12R bytes) and then recovers the tile ranges from the
+// sorted keys.  The tile half of that key is known before sorting, so here:
+//   1. scan_tiles: a 2-D prefix sum over the tile-coverage difference grid (written by
+//      preprocess, four atomics per Gaussian) gives every tile's list length; their exclusive
+//      scan IS the tile ranges and num_rendered.  One small CTA.
+//   2. scatter: CTAs expand their slot segment cooperatively (output slot j finds its owner by
+//      binary search over CTA-local prefix sums, so a Gaussian covering thousands of tiles
+//      costs no more per instance than one covering four) and drop each instance into its
+//      tile's bucket through an atomic cursor, as the composite depth_bits << 32 | slot.
+//   3. tile_sort: one CTA per tile sorts its bucket in shared memory with a bitonic network on
+//      the composite key.  Slot order is Gaussian order, so ascending (depth bits, slot) is
+//      exactly the order the reference's stable LSD sort produces — ties included — while each
+//      instance crosses HBM once instead of 12 times.  Buckets larger than the shared-memory
+//      budget are sorted by the same network directly in global memory (L2).
+// The onesweep radix sort (Adinets & Merrill) that replaces cub::DeviceRadixSort as a library
+// primitive is kept below and exported as gsr_sort_pairs.
 #include "gsr_kernels.cuh"
 
 namespace gsr {
@@ -47,62 +53,209 @@ __device__ __forceinline__ uint32_t digit_of(uint64_t key, int shift, uint32_t m
   return (uint32_t)(key >> shift) & mask;
 }
 
-// ------------------------------------------------------------------ key generation
-// One CTA expands 256 consecutive visible Gaussians.  The CTA's output range is contiguous
-// (prefix sums), so all 256 threads walk it together: output slot j finds its owner with a
-// binary search over the CTA-local prefix sums in shared memory, decodes its tile from the
-// owner's rectangle (rows then columns, like the reference's nested loop) and writes
-// key = tile << 32 | depth bits, value = visible rank.  Writes are fully coalesced and a
-// Gaussian covering thousands of tiles costs no more per key than one covering four.
-__global__ void __launch_bounds__(256) emit_keys_kernel(const uint32_t* __restrict__ counters,
-                                                        const uint32_t* __restrict__ tiles_touched,
-                                                        const uint32_t* __restrict__ point_offsets,
-                                                        const uint2* __restrict__ rects, const float* __restrict__ depths,
-                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                        uint32_t grid_x, uint32_t capacity) {
-  __shared__ uint32_t s_end[256];     // CTA-local inclusive prefix of tiles
-  __shared__ uint2 s_rect[256];
-  __shared__ uint32_t s_depth[256];
-  const uint32_t Pv = counters[2];
-  const uint32_t first = blockIdx.x * 256u;
-  if (first >= Pv) return;
-  const uint32_t tid = threadIdx.x;
-  const uint32_t k = first + tid;
-  const uint32_t cnt = min(256u, Pv - first);
-  const uint32_t block_begin = first == 0 ? 0u : __ldg(point_offsets + first - 1);
-  if (tid < cnt) {
-    s_end[tid] = __ldg(point_offsets + k) - block_begin;
-    s_rect[tid] = __ldg(rects + k);
-    s_depth[tid] = __float_as_uint(__ldg(depths + k));
-  }
-  __syncthreads();
-  const uint32_t total = s_end[cnt - 1];
-  for (uint32_t j = tid; j < total; j += 256u) {
-    // smallest t with s_end[t] > j
-    uint32_t lo = 0, hi = cnt - 1;
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (s_end[mid] > j) hi = mid; else lo = mid + 1;
-    }
-    const uint32_t begin = lo == 0 ? 0u : s_end[lo - 1];
-    const uint32_t within = j - begin;
-    const uint2 rc = s_rect[lo];
-    const uint32_t minx = rc.x & 0xffffu, w = (rc.x >> 16) - minx, miny = rc.y & 0xffffu;
-    const uint32_t row = within / w, col = within - row * w;
-    const uint32_t tile = (miny + row) * grid_x + (minx + col);
-    const uint32_t dst = block_begin + j;
-    if (dst < capacity) {
-      keys[dst] = ((uint64_t)tile << 32) | s_depth[lo];
-      vals[dst] = first + lo;
+// ------------------------------------------------------------------ block-wide bitonic network
+// Ascending bitonic network in which every merge starts with a mirrored compare (i <-> i ^ (k-1))
+// followed by half-cleaners, so ALL compare-exchanges put the smaller key at the lower index and
+// virtual +inf padding beyond `n` never has to be stored or moved.
+template <typename T, typename Ptr>
+__device__ __forceinline__ void bitonic_sort_block(Ptr a, uint32_t n, uint32_t n2) {
+  const uint32_t half = n2 >> 1;
+  for (uint32_t k = 2; k <= n2; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      const bool mirror = j == (k >> 1);
+      for (uint32_t t = threadIdx.x; t < half; t += blockDim.x) {
+        const uint32_t i0 = ((t & ~(j - 1)) << 1) | (t & (j - 1));          // t with a zero inserted at bit j
+        const uint32_t i1 = mirror ? (i0 & ~(k - 1)) | ((k - 1) - (i0 & (k - 1))) : (i0 | j);
+        if (i1 < n) {                                                        // beyond n: virtual +inf, already in place
+          const T x = a[i0], y = a[i1];
+          if (x > y) { a[i0] = y; a[i1] = x; }
+        }
+      }
+      __syncthreads();
     }
   }
 }
 
-void launch_emit_keys(int max_visible, const GeometryView& g, uint64_t* keys, uint32_t* vals, uint32_t grid_x,
-                      uint32_t capacity, cudaStream_t stream) {
-  if (max_visible <= 0) return;
-  emit_keys_kernel<<<(max_visible + 255) / 256, 256, 0, stream>>>(g.counters, g.tiles_touched, g.point_offsets, g.rect,
-                                                               g.depths, keys, vals, grid_x, capacity);
+// ------------------------------------------------------------------ tile counts -> ranges
+// One CTA.  diff is the (gy+1) x (gx+1) difference grid; after the 2-D inclusive prefix sum
+// diff[y][x] is the number of Gaussians whose rectangle covers tile (x, y).
+constexpr uint32_t ST_SMEM_CELLS = 10240;   // difference grids up to this many cells are scanned in shared memory
+
+__global__ void __launch_bounds__(1024) scan_tiles_kernel(int* __restrict__ diff_g, uint32_t gx, uint32_t gy,
+                                                          uint2* __restrict__ ranges, uint32_t* __restrict__ cursor,
+                                                          uint32_t* __restrict__ tile_order, uint32_t* __restrict__ counters) {
+  __shared__ int s_grid[ST_SMEM_CELLS];
+  __shared__ uint32_t s_part[1024];
+  __shared__ uint32_t s_max[32];
+  const uint32_t tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t stride = gx + 1;
+  const uint32_t cells = stride * (gy + 1);
+  const bool in_smem = cells <= ST_SMEM_CELLS;
+  int* diff = in_smem ? s_grid : diff_g;
+  if (in_smem) {
+    for (uint32_t i = tid; i < cells; i += nt) s_grid[i] = diff_g[i];
+    __syncthreads();
+  }
+  for (uint32_t y = tid; y <= gy; y += nt) {      // along rows
+    int run = 0;
+    int* row = diff + y * stride;
+    for (uint32_t x = 0; x <= gx; x++) { run += row[x]; row[x] = run; }
+  }
+  __syncthreads();
+  for (uint32_t x = tid; x <= gx; x += nt) {      // along columns
+    int run = 0;
+    for (uint32_t y = 0; y <= gy; y++) { run += diff[y * stride + x]; diff[y * stride + x] = run; }
+  }
+  __syncthreads();
+  // exclusive scan of the T counts in tile order: each thread owns a contiguous chunk
+  const uint32_t T = gx * gy;
+  const uint32_t chunk = (T + nt - 1) / nt;
+  const uint32_t t0 = min(T, tid * chunk), t1 = min(T, t0 + chunk);
+  uint32_t sum = 0, mx = 0;
+  for (uint32_t t = t0; t < t1; t++) {
+    const uint32_t c = (uint32_t)diff[(t / gx) * stride + (t % gx)];
+    sum += c;
+    mx = max(mx, c);
+  }
+  s_part[tid] = sum;
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((tid & 31) == 0) s_max[tid >> 5] = mx;
+  __syncthreads();
+  if (tid < 32) {   // scan the 1024 partials: 32 per lane, then across lanes
+    uint32_t loc = 0;
+    for (uint32_t i = 0; i < nt / 32; i++) { const uint32_t v = s_part[tid * (nt / 32) + i]; s_part[tid * (nt / 32) + i] = loc; loc += v; }
+    uint32_t incl = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= (uint32_t)o) incl += v; }
+    const uint32_t excl = incl - loc;
+    for (uint32_t i = 0; i < nt / 32; i++) s_part[tid * (nt / 32) + i] += excl;
+    uint32_t m = tid < nt / 32 ? s_max[tid] : 0;
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (tid == 31) counters[1] = incl;   // num_rendered
+    if (tid == 0) counters[4] = m;       // longest tile list
+  }
+  __syncthreads();
+  uint32_t run = s_part[tid];
+  for (uint32_t t = t0; t < t1; t++) {
+    const uint32_t c = (uint32_t)diff[(t / gx) * stride + (t % gx)];
+    ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);   // untouched tiles stay (0,0) like the reference
+    cursor[t] = run;
+    run += c;
+  }
+  // launch order of the blend CTAs: longest lists first, so the short ones fill the tail of the grid
+  if (T <= 8192 && in_smem) {
+    __syncthreads();
+    uint32_t* keys = reinterpret_cast<uint32_t*>(s_grid);
+    uint32_t cnt_of[8];
+    for (uint32_t i = 0, t = tid; t < T; t += nt, i++) cnt_of[i] = (uint32_t)diff[(t / gx) * stride + (t % gx)];
+    __syncthreads();   // counts are in registers; the grid memory is reused for the sort keys
+    for (uint32_t i = 0, t = tid; t < T; t += nt, i++) keys[t] = ~((min(cnt_of[i], 0x7ffffu) << 13) | t);
+    __syncthreads();
+    uint32_t n2 = 1;
+    while (n2 < T) n2 <<= 1;
+    bitonic_sort_block<uint32_t>(keys, T, n2);
+    for (uint32_t t = tid; t < T; t += nt) tile_order[t] = (~keys[t]) & 0x1fffu;
+  } else {
+    for (uint32_t t = tid; t < T; t += nt) tile_order[t] = t;
+  }
+}
+
+void launch_scan_tiles(int* tile_diff, uint32_t gx, uint32_t gy, uint2* ranges, uint32_t* cursor, uint32_t* tile_order,
+                       uint32_t* counters, cudaStream_t stream) {
+  scan_tiles_kernel<<<1, 1024, 0, stream>>>(tile_diff, gx, gy, ranges, cursor, tile_order, counters);
+  count_launch();
+}
+
+// ------------------------------------------------------------------ instances -> tile buckets
+// One CTA per preprocess slot segment.  Also zeroes the backward accumulator rows of its slots.
+__global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict__ block_vis, const uint2* __restrict__ rects,
+                                                      const float* __restrict__ depths, uint32_t* __restrict__ cursor,
+                                                      uint64_t* __restrict__ comp, float* __restrict__ grad_acc,
+                                                      uint32_t grid_x, uint32_t capacity) {
+  __shared__ uint32_t s_end[256];     // CTA-local inclusive prefix of tile counts
+  __shared__ uint2 s_rect[256];
+  __shared__ uint32_t s_depth[256];
+  __shared__ uint32_t s_wsum[8];
+  const uint32_t cnt = block_vis[blockIdx.x];
+  if (cnt == 0) return;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t first = blockIdx.x * 256u;
+  uint32_t tiles = 0;
+  if (tid < cnt) {
+    const uint2 rc = __ldg(rects + first + tid);
+    s_rect[tid] = rc;
+    s_depth[tid] = __float_as_uint(__ldg(depths + first + tid));
+    tiles = ((rc.x >> 16) - (rc.x & 0xffffu)) * ((rc.y >> 16) - (rc.y & 0xffffu));
+    float4* acc = reinterpret_cast<float4*>(grad_acc + 12 * (size_t)(first + tid));
+    acc[0] = acc[1] = acc[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  uint32_t incl = tiles;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (uint32_t w = 0; w < warp; w++) woff += s_wsum[w];
+  s_end[tid] = woff + incl;
+  __syncthreads();
+  const uint32_t total = s_end[255];
+  for (uint32_t j = tid; j < total; j += 256u) {
+    uint32_t lo = 0, hi = cnt - 1;      // smallest t with s_end[t] > j
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s_end[mid] > j) hi = mid; else lo = mid + 1;
+    }
+    const uint32_t within = j - (lo == 0 ? 0u : s_end[lo - 1]);
+    const uint2 rc = s_rect[lo];
+    const uint32_t minx = rc.x & 0xffffu, w = (rc.x >> 16) - minx, miny = rc.y & 0xffffu;
+    const uint32_t row = within / w, col = within - row * w;
+    const uint32_t tile = (miny + row) * grid_x + (minx + col);
+    const uint32_t pos = atomicAdd(cursor + tile, 1u);
+    if (pos < capacity) comp[pos] = ((uint64_t)s_depth[lo] << 32) | (first + lo);
+  }
+}
+
+void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* comp, uint32_t grid_x, uint32_t capacity,
+                    cudaStream_t stream) {
+  if (P <= 0) return;
+  scatter_kernel<<<num_pre_blocks(P), 256, 0, stream>>>(g.block_vis, g.rect, g.depths, cursor, comp, g.grad_acc, grid_x, capacity);
+  count_launch();
+}
+
+// ------------------------------------------------------------------ tile-local sort (kernel)
+constexpr int TS_THREADS = 256;
+constexpr uint32_t TS_SMEM_KEYS = 4096;   // 32 KB of composite keys in shared memory
+
+__global__ void __launch_bounds__(TS_THREADS) tile_sort_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ comp,
+                                                               uint32_t* __restrict__ point_list, uint32_t capacity) {
+  __shared__ uint64_t s_keys[TS_SMEM_KEYS];
+  const uint2 rg = ranges[blockIdx.x];
+  const uint32_t start = rg.x, end = min(rg.y, capacity);
+  if (end <= start) return;
+  const uint32_t n = end - start;
+  uint32_t n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  if (n <= TS_SMEM_KEYS) {
+    for (uint32_t i = threadIdx.x; i < n; i += TS_THREADS) s_keys[i] = comp[start + i];
+    __syncthreads();
+    if (n > 1) bitonic_sort_block<uint64_t>(s_keys, n, n2);
+    for (uint32_t i = threadIdx.x; i < n; i += TS_THREADS) {
+      const uint64_t k = s_keys[i];
+      comp[start + i] = k;
+      point_list[start + i] = (uint32_t)k;
+    }
+  } else {
+    uint64_t* a = comp + start;      // large bucket: same network straight on global memory (L2 resident)
+    __syncthreads();
+    bitonic_sort_block<uint64_t>(a, n, n2);
+    for (uint32_t i = threadIdx.x; i < n; i += TS_THREADS) point_list[start + i] = (uint32_t)a[i];
+  }
+}
+
+void launch_tile_sort(int num_tiles, const uint2* ranges, uint64_t* comp, uint32_t* point_list, uint32_t capacity,
+                      cudaStream_t stream) {
+  if (num_tiles <= 0) return;
+  tile_sort_kernel<<<num_tiles, TS_THREADS, 0, stream>>>(ranges, comp, point_list, capacity);
   count_launch();
 }
 
@@ -319,35 +472,6 @@ int launch_onesweep(uint64_t* keys[2], uint32_t* vals[2], const uint32_t* n_ptr,
     cur ^= 1;
   }
   return cur;
-}
-
-// ------------------------------------------------------------------ tile ranges
-__global__ void __launch_bounds__(256) identify_tile_ranges_kernel(const uint32_t* __restrict__ n_ptr, uint32_t n_host,
-                                                                   const uint64_t* __restrict__ keys,
-                                                                   uint2* __restrict__ ranges) {
-  const uint32_t L = n_ptr ? min(*n_ptr, n_host) : n_host;
-  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= L) return;
-  const uint32_t cur = (uint32_t)(__ldg(keys + idx) >> 32);
-  if (idx == 0) {
-    ranges[cur].x = 0;
-  } else {
-    const uint32_t prev = (uint32_t)(__ldg(keys + idx - 1) >> 32);
-    if (cur != prev) {
-      ranges[prev].y = idx;
-      ranges[cur].x = idx;
-    }
-  }
-  if (idx == L - 1) ranges[cur].y = L;
-}
-
-void launch_identify_tile_ranges(const uint32_t* n_ptr, long long n, const uint64_t* keys, uint2* ranges, int num_tiles,
-                                 cudaStream_t stream) {
-  cudaMemsetAsync(ranges, 0, sizeof(uint2) * (size_t)num_tiles, stream);
-  if (n > 0) {
-    identify_tile_ranges_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n_ptr, (uint32_t)n, keys, ranges);
-    count_launch();
-  }
 }
 
 }  // namespace gsr

@@ -24,36 +24,35 @@ __device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f,
 // Scratch layout (private contract between this library's forward and backward).
 // All slabs 128-byte aligned.  SoA, sized for P Gaussians / R instances / N pixels.
 // ---------------------------------------------------------------------------------------
-// The forward compacts the visible Gaussians: everything downstream of preprocess (key
-// emission, sort payload, blending gathers, backward accumulators) is indexed by the visible
-// rank k in [0, Pv) — Gaussian order is preserved, so sort stability / tie order is unchanged —
-// and only `radii` stays indexed by Gaussian id.  All arrays are sized for the worst case Pv = P.
+// Visible Gaussians are compacted per preprocess CTA: CTA b owns the 256 "slots"
+// [256 b, 256 b + 256) and packs its visible Gaussians into the first block_vis[b] of them, in
+// Gaussian order.  Slot ids are what the sort carries and what the blend kernels gather by;
+// slot order == Gaussian order, so ties keep the reference's order.  No CTA depends on another.
 struct GeometryView {           // replaces GeometryState (reference rasterizer_impl.h:29-44)
-  float* depths;                // [Pv]  view-space z (sort key low bits)
-  float2* means2D;              // [Pv]  pixel-space centre
-  float4* conic_opacity;        // [Pv]  (conic.x, conic.y, conic.z, opacity)
-  float4* rgbd;                 // [Pv]  (r, g, b, depth): one 16-byte gather for the blend kernels
-  float* cov3D;                 // [6Pv]
-  uint2* rect;                  // [Pv]  tile rectangle: x = minx | maxx<<16, y = miny | maxy<<16
-  uint8_t* clamped;             // [Pv]  bit c set <=> channel c was clamped at 0
-  uint32_t* gid;                // [Pv]  Gaussian id of visible rank k (ascending)
-  uint32_t* tiles_touched;      // [Pv]
-  uint32_t* point_offsets;      // [Pv]  inclusive prefix sum of tiles_touched
-  unsigned long long* scan_status;  // [ceil(P/256)] decoupled look-back words (flag<<62 | visible<<32 | tiles)
-  uint32_t* counters;           // [32] 0: unused, 1: num_rendered, 2: num_visible, 3: overflow flag
-  float* grad_acc;              // [12Pv] backward accumulators (see render_bwd)
+  float* depths;                // [slots] view-space z
+  float2* means2D;              // [slots] pixel-space centre
+  float4* conic_opacity;        // [slots] (conic.x, conic.y, conic.z, opacity)
+  float4* rgbd;                 // [slots] (r, g, b, depth): one 16-byte gather for the blend kernels
+  float* cov3D;                 // [6 slots]
+  uint2* rect;                  // [slots] tile rectangle: x = minx | maxx<<16, y = miny | maxy<<16
+  uint8_t* clamped;             // [slots] bit c set <=> channel c was clamped at 0
+  uint32_t* gid;                // [slots] Gaussian id held by the slot
+  uint32_t* block_vis;          // [ceil(P/256)] visible Gaussians of each preprocess CTA
+  uint32_t* counters;           // [32] 1: num_rendered, 4: largest tile list
+  float* grad_acc;              // [12 slots] backward accumulators, zero between uses
 };
 
 struct ImageView {              // replaces ImageState (reference rasterizer_impl.h:46-52)
-  uint2* ranges;                // [T]
+  uint2* ranges;                // [T]   [start, end) of each tile in the sorted list, (0,0) if empty
   uint32_t* n_contrib;          // [N]
+  int* tile_diff;               // [(gy+1)(gx+1)] 2-D difference grid of tile coverage -> per-tile counts
+  uint32_t* tile_cursor;        // [T]   bucket write cursors
+  uint32_t* tile_order;         // [T]   tiles by descending list length: launch order of the blend CTAs
 };
 
 struct BinningView {            // replaces BinningState (reference rasterizer_impl.h:54-64)
-  uint64_t* keys[2];            // ping-pong; [0] holds the unsorted keys before the sort
-  uint32_t* vals[2];
-  char* sort_temp;
-  int final_buf;                // which of the two holds the sorted list (passes even -> 0)
+  uint64_t* comp;               // [R] depth bits << 32 | slot, bucketed by tile, then sorted per tile
+  uint32_t* point_list;         // [R] sorted slots
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -68,27 +67,29 @@ inline int num_pre_blocks(int P) { return (P + PRE_THREADS - 1) / PRE_THREADS; }
 
 inline char* carve_geometry(char* base, int P, GeometryView& g) {
   char* p = base;
-  carve(p, g.depths, (size_t)P);
-  carve(p, g.means2D, (size_t)P);
-  carve(p, g.conic_opacity, (size_t)P);
-  carve(p, g.rgbd, (size_t)P);
-  carve(p, g.cov3D, 6 * (size_t)P);
-  carve(p, g.rect, (size_t)P);
-  carve(p, g.clamped, (size_t)P);
-  carve(p, g.gid, (size_t)P);
-  carve(p, g.tiles_touched, (size_t)P);
-  carve(p, g.point_offsets, (size_t)P);
-  carve(p, g.scan_status, (size_t)num_pre_blocks(P) + 1);
+  const size_t S = (size_t)num_pre_blocks(P) * PRE_THREADS;
+  carve(p, g.depths, S);
+  carve(p, g.means2D, S);
+  carve(p, g.conic_opacity, S);
+  carve(p, g.rgbd, S);
+  carve(p, g.cov3D, 6 * S);
+  carve(p, g.rect, S);
+  carve(p, g.clamped, S);
+  carve(p, g.gid, S);
+  carve(p, g.block_vis, (size_t)num_pre_blocks(P) + 1);
   carve(p, g.counters, (size_t)32);
-  carve(p, g.grad_acc, 12 * (size_t)P);
+  carve(p, g.grad_acc, 12 * S);
   return p;
 }
 
 inline char* carve_image(char* base, int W, int H, ImageView& im) {
   char* p = base;
-  const size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
-  carve(p, im.ranges, T);
+  const size_t gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+  carve(p, im.ranges, gx * gy);
   carve(p, im.n_contrib, (size_t)W * H);
+  carve(p, im.tile_diff, (gx + 1) * (gy + 1));
+  carve(p, im.tile_cursor, gx * gy);
+  carve(p, im.tile_order, gx * gy);
   return p;
 }
 

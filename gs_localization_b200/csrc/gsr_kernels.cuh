@@ -27,6 +27,7 @@ struct PreprocessParams {
   int sh_vec4;          // SH rows are 16-byte aligned and a multiple of 4 floats long
   int* radii;
   int* n_touched;       // may be null
+  int* tile_diff;       // [(grid_y+1)(grid_x+1)], zeroed before the launch
   GeometryView geom;
 };
 
@@ -53,29 +54,34 @@ void carve_sort_temp(char* base, long long n, int passes, SortTemp& t);
 // zero hist/tickets/status (one memset)
 void sort_temp_reset(char* base, long long n, int passes, cudaStream_t stream);
 
-// All binning kernels take the element count both as a host upper bound (grid sizing) and, optionally,
-// as a device pointer (the exact value written by preprocess), so the chain can run without a host sync.
-// key = tile<<32 | depth bits, value = visible rank; block-cooperative expansion over the compact visible set
-void launch_emit_keys(int max_visible, const GeometryView& g, uint64_t* keys, uint32_t* vals, uint32_t grid_x,
-                      uint32_t capacity, cudaStream_t stream);
+// coverage grid -> per-tile list lengths -> ranges / bucket cursors / num_rendered (counters[1]) / longest list (counters[4])
+// + tile_order: tiles by descending list length (launch order of the blend CTAs)
+void launch_scan_tiles(int* tile_diff, uint32_t gx, uint32_t gy, uint2* ranges, uint32_t* cursor, uint32_t* tile_order,
+                       uint32_t* counters, cudaStream_t stream);
+// (Gaussian, tile) instances -> tile buckets as depth_bits << 32 | slot; also zeroes the slots' backward accumulators
+void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* comp, uint32_t grid_x, uint32_t capacity,
+                    cudaStream_t stream);
+// per-tile sort of the buckets on the composite key; writes the sorted slots to point_list
+void launch_tile_sort(int num_tiles, const uint2* ranges, uint64_t* comp, uint32_t* point_list, uint32_t capacity,
+                      cudaStream_t stream);
+// library radix sort (gsr_sort_pairs): the element count is a host upper bound and, optionally, a device pointer
 void launch_sort_histogram(const uint64_t* keys, const uint32_t* n_ptr, long long n_host, int end_bit, uint32_t* hist,
                            cudaStream_t stream);
 // exclusive scan of the histograms + all onesweep passes; returns index (0/1) of the buffer holding the result
 int launch_onesweep(uint64_t* keys[2], uint32_t* vals[2], const uint32_t* n_ptr, long long n_host, int end_bit,
                     const SortTemp& t, cudaStream_t stream);
-void launch_identify_tile_ranges(const uint32_t* n_ptr, long long n_host, const uint64_t* keys, uint2* ranges, int num_tiles,
-                                 cudaStream_t stream);
 
 // ---- blending (render.cu)
 struct RenderParams {
   int W, H;
   uint32_t grid_x, grid_y;
   const uint2* ranges;
-  const uint32_t* point_list;   // sorted visible ranks
+  const uint32_t* tile_order;   // CTA index -> tile (longest lists first)
+  const uint32_t* point_list;   // sorted slots
   const float2* means2D;
   const float4* conic_opacity;
-  const float4* rgbd;        // (r, g, b, depth) per visible rank
-  const uint32_t* gid;       // visible rank -> Gaussian id (n_touched only)
+  const float4* rgbd;        // (r, g, b, depth) per slot
+  const uint32_t* gid;       // slot -> Gaussian id (n_touched only)
   const float* bg;
   float* out_color;
   float* out_depth;
@@ -89,6 +95,7 @@ struct RenderBwdParams {
   int W, H;
   uint32_t grid_x, grid_y;
   const uint2* ranges;
+  const uint32_t* tile_order;
   const uint32_t* point_list;   // sorted visible ranks
   const float2* means2D;
   const float4* conic_opacity;
@@ -99,7 +106,7 @@ struct RenderBwdParams {
   const float* dL_dpix;
   const float* dL_ddepth;
   const float* dL_dalpha;
-  float* grad_acc;           // [Pv][12]: mean2D.xy, conic.xyw, opacity, rgb, depth, pad, pad
+  float* grad_acc;           // [slots][12]: mean2D.xy, conic.xyw, opacity, rgb, depth, pad, pad
 };
 void launch_render_bwd(const RenderBwdParams& p, cudaStream_t stream);
 
@@ -129,7 +136,7 @@ struct PreBwdParams {
   float* dL_drot;      // [P,4]
   float* dL_dtau;      // [6] or null
 };
-// one thread per visible Gaussian; max_visible is a host upper bound (P), the exact count is read on the device
-void launch_preprocess_bwd(const PreBwdParams& p, int max_visible, cudaStream_t stream);
+// one CTA per preprocess slot segment, threads beyond the segment's visible count idle
+void launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream);
 
 }  // namespace gsr

@@ -8,13 +8,16 @@
 //   cub::DeviceScan::InclusiveSum + its temp storage   cuda_rasterizer/rasterizer_impl.cu:278
 //   checkFrustum              cuda_rasterizer/rasterizer_impl.cu:54-66
 //
-// B200 design: 256 Gaussians per CTA; means are staged through shared memory with 128-bit
-// coalesced loads (the reference issues stride-3 scalar loads); the per-CTA tile-count sum
-// is chained across CTAs with a decoupled look-back (single pass, Merrill & Garland) so the
-// separate scan kernel, its 4P+4P bytes of traffic and its temp buffer disappear; CTA order
-// is taken from an atomic ticket so look-back never waits on an unscheduled CTA.
-// Arithmetic that decides binning is pinned with IEEE intrinsics to the reference's sm_100a
-// rounding sequence (gsr_common.cuh).
+// B200 design: 256 Gaussians per CTA and NO dependency between CTAs.  Means are staged through
+// shared memory with 128-bit coalesced loads (the reference issues stride-3 scalar loads).  The
+// CTA packs its visible Gaussians, in order, into the first slots of its own 256-slot segment
+// (ballot ranks, no scan), so everything downstream runs on dense records; colour (SH) is then
+// evaluated only for those, on dense lanes.  Instead of a prefix sum over tile counts
+// (cub::DeviceScan + its 4P+4P bytes + a chained look-back) each visible Gaussian adds its tile
+// rectangle to a 2-D difference grid with four atomics; the per-tile list lengths, the tile
+// ranges and num_rendered all fall out of one tiny prefix-sum kernel over the tile grid
+// (binning.cu).  Arithmetic that decides binning is pinned with IEEE intrinsics to the
+// reference's sm_100a rounding sequence (gsr_common.cuh).
 #include "gsr_kernels.cuh"
 
 namespace gsr {
@@ -129,16 +132,9 @@ __device__ __forceinline__ float3 color_from_sh(int deg, float3 pos, float3 camp
   return make_float3(fmaxf(r0, 0.f), fmaxf(r1, 0.f), fmaxf(r2, 0.f));
 }
 
-// status word of the decoupled look-back: flag (2 bits) | visible count (30 bits) | tile count (32 bits)
-__device__ __forceinline__ unsigned long long pack_status(uint32_t flag, uint32_t vis, uint32_t tiles) {
-  return ((unsigned long long)flag << 62) | ((unsigned long long)vis << 32) | tiles;
-}
-
 template <bool ALIGNED>
 __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_fwd_kernel(const PreprocessParams p) {
-  __shared__ uint32_t s_warp_tiles[PRE_THREADS / 32];
   __shared__ uint32_t s_warp_vis[PRE_THREADS / 32];
-  __shared__ uint32_t s_prefix_tiles, s_prefix_vis, s_block_vis;
   __shared__ __align__(16) float s_means[PRE_THREADS * 3];
   __shared__ float s_cam[16 + 16 + 4];
   __shared__ uint16_t s_vis_tid[PRE_THREADS];
@@ -149,8 +145,6 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_fwd_kernel(const Pr
   if (tid < 16) s_cam[tid] = p.viewmatrix[tid];
   else if (tid < 32) s_cam[tid] = p.projmatrix[tid - 16];
   else if (tid < 35) s_cam[tid] = p.campos[tid - 32];
-  // CTAs are dispatched in blockIdx order, so every predecessor the look-back waits on is
-  // already resident or finished (same assumption as CUB's single-pass scan).
   const uint32_t block = blockIdx.x;
   const int base = (int)block * PRE_THREADS;
   const int idx = base + tid;
@@ -235,79 +229,23 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_fwd_kernel(const Pr
     if (p.n_touched) p.n_touched[idx] = 0;
   }
 
-  // ---- CTA scan: tiles by shuffle, visible rank by ballot
+  // ---- pack the visible Gaussians into the CTA's slot segment (ballot ranks keep Gaussian order)
   const bool vis = tiles != 0;
   const uint32_t vis_mask = __ballot_sync(0xffffffffu, vis);
   const uint32_t vis_rank_in_warp = __popc(vis_mask & ((1u << lane) - 1u));
-  uint32_t incl = tiles;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += n;
-  }
-  if (lane == 31) s_warp_tiles[warp] = incl;
   if (lane == 0) s_warp_vis[warp] = __popc(vis_mask);
   __syncthreads();
-  if (warp == 0) {
-    const uint32_t wt = lane < PRE_THREADS / 32 ? s_warp_tiles[lane] : 0;
-    const uint32_t wv = lane < PRE_THREADS / 32 ? s_warp_vis[lane] : 0;
-    uint32_t it = wt, iv = wv;
+  uint32_t warp_off = 0, nvis = 0;
 #pragma unroll
-    for (int o = 1; o < PRE_THREADS / 32; o <<= 1) {
-      const uint32_t nt = __shfl_up_sync(0xffffffffu, it, o);
-      const uint32_t nv = __shfl_up_sync(0xffffffffu, iv, o);
-      if (lane >= o) it += nt, iv += nv;
-    }
-    if (lane < PRE_THREADS / 32) s_warp_tiles[lane] = it - wt, s_warp_vis[lane] = iv - wv;  // exclusive warp offsets
-    const uint32_t block_tiles = __shfl_sync(0xffffffffu, it, PRE_THREADS / 32 - 1);
-    const uint32_t block_vis = __shfl_sync(0xffffffffu, iv, PRE_THREADS / 32 - 1);
-
-    // ---- decoupled look-back across CTAs (flag 1 = aggregate, 2 = inclusive prefix)
-    volatile unsigned long long* status = p.geom.scan_status;
-    uint32_t ex_tiles = 0, ex_vis = 0;
-    if (block == 0) {
-      if (lane == 0) status[0] = pack_status(2, block_vis, block_tiles);
-    } else {
-      if (lane == 0) status[block] = pack_status(1, block_vis, block_tiles);
-      int look = (int)block - 1;
-      while (true) {
-        const int j = look - (int)lane;
-        unsigned long long w = j >= 0 ? status[j] : pack_status(2, 0, 0);
-        while (__any_sync(0xffffffffu, (w >> 62) == 0)) {
-          if ((w >> 62) == 0) w = status[j];
-        }
-        const uint32_t incl_mask = __ballot_sync(0xffffffffu, (w >> 62) == 2);
-        const uint32_t upto = incl_mask ? (uint32_t)(__ffs(incl_mask) - 1) : 31u;  // nearest inclusive word
-        uint32_t vt = lane <= upto ? (uint32_t)w : 0u;
-        uint32_t vv = lane <= upto ? (uint32_t)((w >> 32) & 0x3fffffffu) : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          vt += __shfl_xor_sync(0xffffffffu, vt, o);
-          vv += __shfl_xor_sync(0xffffffffu, vv, o);
-        }
-        ex_tiles += vt;
-        ex_vis += vv;
-        if (incl_mask) break;
-        look -= 32;
-      }
-      if (lane == 0) status[block] = pack_status(2, ex_vis + block_vis, ex_tiles + block_tiles);
-    }
-    if (lane == 0) {
-      s_prefix_tiles = ex_tiles;
-      s_prefix_vis = ex_vis;
-      s_block_vis = block_vis;
-      if (block == gridDim.x - 1) {
-        p.geom.counters[1] = ex_tiles + block_tiles;  // num_rendered
-        p.geom.counters[2] = ex_vis + block_vis;      // num_visible
-      }
-    }
+  for (int w = 0; w < PRE_THREADS / 32; w++) {
+    const uint32_t c = s_warp_vis[w];
+    if (w < (int)warp) warp_off += c;
+    nvis += c;
   }
-  __syncthreads();
-
-  // ---- compact per-visible records (Gaussian order preserved)
-  const uint32_t vis_base = s_prefix_vis;
+  const uint32_t vis_base = (uint32_t)base;     // first slot of this CTA
+  if (tid == 0) p.geom.block_vis[block] = nvis;
   if (vis) {
-    const uint32_t lr = s_warp_vis[warp] + vis_rank_in_warp;   // rank inside the CTA
+    const uint32_t lr = warp_off + vis_rank_in_warp;   // rank inside the CTA
     const uint32_t k = vis_base + lr;
     s_vis_tid[lr] = (uint16_t)tid;
     s_vis_depth[lr] = vz;
@@ -316,17 +254,21 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_fwd_kernel(const Pr
     p.geom.conic_opacity[k] = make_float4(conic.x, conic.y, conic.z, __ldg(p.opacities + idx));
     p.geom.rect[k] = rect;
     p.geom.gid[k] = (uint32_t)idx;
-    p.geom.tiles_touched[k] = tiles;
-    p.geom.point_offsets[k] = s_prefix_tiles + s_warp_tiles[warp] + incl;
     if (!p.cov3D_precomp) {
 #pragma unroll
       for (int q = 0; q < 6; q++) p.geom.cov3D[6 * (size_t)k + q] = cov3D[q];
     }
+    // tile coverage: +1/-1 at the rectangle corners of the 2-D difference grid
+    const uint32_t minx = rect.x & 0xffffu, maxx = rect.x >> 16, miny = rect.y & 0xffffu, maxy = rect.y >> 16;
+    const uint32_t stride = p.grid_x + 1;
+    atomicAdd(p.tile_diff + miny * stride + minx, 1);
+    atomicAdd(p.tile_diff + miny * stride + maxx, -1);
+    atomicAdd(p.tile_diff + maxy * stride + minx, -1);
+    atomicAdd(p.tile_diff + maxy * stride + maxx, 1);
   }
   __syncthreads();
 
   // ---- colour for the CTA's visible Gaussians only, on dense lanes
-  const uint32_t nvis = s_block_vis;
   for (uint32_t lr = tid; lr < nvis; lr += PRE_THREADS) {
     const uint32_t t = s_vis_tid[lr];
     const size_t g = (size_t)base + t;

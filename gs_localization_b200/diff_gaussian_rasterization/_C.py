@@ -185,11 +185,10 @@ def export_state(P, R, W, H, geomBuffer, binningBuffer, imgBuffer):
     out = dict(
         depths=z(P, torch.float32), means2D=z((P, 2), torch.float32), cov3D=z((P, 6), torch.float32),
         conic_opacity=z((P, 4), torch.float32), rgb=z((P, 3), torch.float32), clamped=z((P, 3), torch.uint8),
-        tiles_touched=z(P, torch.int32), point_offsets=z(P, torch.int32),
-        keys_unsorted=z(R, torch.int64), list_unsorted=z(R, torch.int32), keys=z(R, torch.int64), list=z(R, torch.int32),
+        tiles_touched=z(P, torch.int32), keys=z(R, torch.int64), list=z(R, torch.int32),
         ranges=z((T, 2), torch.int32), n_contrib=z((H, W), torch.int32))
-    order = ["depths", "means2D", "cov3D", "conic_opacity", "rgb", "clamped", "tiles_touched", "point_offsets",
-             "keys_unsorted", "list_unsorted", "keys", "list", "ranges", "n_contrib"]
+    order = ["depths", "means2D", "cov3D", "conic_opacity", "rgb", "clamped", "tiles_touched", "keys", "list", "ranges",
+             "n_contrib"]
     with torch.cuda.device(dev):
         rc = lib.gsr_export_state(P, int(R), W, H, _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imgBuffer),
                                   *[_ptr(out[k]) for k in order], _stream(dev))

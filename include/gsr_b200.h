@@ -126,16 +126,16 @@ GSR_API int gsr_mark_visible(int P, const float* means3D, const float* viewmatri
  * Introspection for parity tests (not on the hot path): copy the library's private
  * intermediates out of the scratch buffers in the REFERENCE's formats
  * (GeometryState / BinningState / ImageState, rasterizer_impl.h:29-64).  Any pointer may be NULL.
- *   depths[P] means2D[P,2] cov3D[P,6] conic_opacity[P,4] rgb[P,3] clamped[P,3](u8)
- *   tiles_touched[P] point_offsets[P]; keys_unsorted[R] list_unsorted[R] keys[R] list[R];
- *   ranges[T,2] n_contrib[H*W]
+ *   depths[P] means2D[P,2] cov3D[P,6] conic_opacity[P,4] rgb[P,3] clamped[P,3](u8) tiles_touched[P]
+ *   (pre-zeroed by the caller; only rows of visible Gaussians are written);
+ *   keys[R] = sorted tile<<32|depth keys, list[R] = sorted Gaussian ids (point_list); ranges[T,2]; n_contrib[H*W]
+ * The library never materialises the reference's unsorted key array or the per-Gaussian offsets.
  */
 GSR_API int gsr_export_state(
     int P, long long num_rendered, int width, int height,
     const char* geometry_buffer, const char* binning_buffer, const char* image_buffer,
     float* depths, float* means2D, float* cov3D, float* conic_opacity, float* rgb, unsigned char* clamped,
-    uint32_t* tiles_touched, uint32_t* point_offsets,
-    uint64_t* keys_unsorted, uint32_t* list_unsorted, uint64_t* keys, uint32_t* list,
+    uint32_t* tiles_touched, uint64_t* keys, uint32_t* list,
     uint32_t* ranges, uint32_t* n_contrib, void* stream);
 
 /*

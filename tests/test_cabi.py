@@ -43,7 +43,7 @@ def test_scratch_size_queries_need_no_gpu():
     g1, g2 = lib.gsr_geometry_bytes(1000), lib.gsr_geometry_bytes(2000)
     assert 0 < g1 < g2
     assert lib.gsr_binning_bytes(0, 640, 480) > 0
-    assert lib.gsr_binning_bytes(10_000, 640, 480) >= 10_000 * 24
+    assert lib.gsr_binning_bytes(10_000, 640, 480) >= 10_000 * 12
     assert lib.gsr_image_bytes(640, 480) >= 640 * 480 * 4 + 1200 * 8
 
 
