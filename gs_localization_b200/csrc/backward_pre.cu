@@ -20,7 +20,7 @@
 
 namespace gsr {
 
-constexpr int BW_THREADS = PRE_THREADS;   // one CTA per preprocess slot segment
+constexpr int BW_THREADS = 32;   // one single-warp CTA per preprocess slot segment, looping over its visible slots
 
 // reference auxiliary.h:107-117
 __device__ __forceinline__ float3 dnormvdv(float3 v, float3 dv) {
@@ -34,59 +34,79 @@ __device__ __forceinline__ float3 dnormvdv(float3 v, float3 dv) {
 }
 
 // SH backward (reference backward.cu:20-139).  Writes this Gaussian's dL_dsh row to `out`
-// (may be null) and returns dL_dmean through the view direction.
+// (may be null) and returns dL_dmean through the view direction.  Processed in groups of four
+// coefficients (three 16-byte loads + three 16-byte stores) to keep register pressure low;
+// w is the basis value, wx/wy/wz its derivative w.r.t. the (normalised) direction components.
 __device__ __forceinline__ float3 sh_backward(int deg, float3 pos, float3 campos, const float* __restrict__ sh,
-                                              float3 dL_dRGB, float* out) {
+                                              float3 dL_dRGB, float* out, bool vec4) {
   const float3 dir_orig = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
   const float inv_len = 1.0f / sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
   const float x = dir_orig.x * inv_len, y = dir_orig.y * inv_len, z = dir_orig.z * inv_len;
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+  const int ncoef = (deg + 1) * (deg + 1);
+  const int ngroups = (ncoef + 3) / 4;
   float3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
-  auto S = [&](int k) { return make_float3(__ldg(sh + 3 * k), __ldg(sh + 3 * k + 1), __ldg(sh + 3 * k + 2)); };
-  auto put = [&](int k, float w) {
-    if (out) {
-      out[3 * k] = w * dL_dRGB.x;
-      out[3 * k + 1] = w * dL_dRGB.y;
-      out[3 * k + 2] = w * dL_dRGB.z;
-    }
-  };
-  auto axpy = [](float3& a, float w, float3 s) { a.x += w * s.x; a.y += w * s.y; a.z += w * s.z; };
-  put(0, SH_C0);
-  if (deg > 0) {
-    put(1, -SH_C1 * y);
-    put(2, SH_C1 * z);
-    put(3, -SH_C1 * x);
-    axpy(dRGBdx, -SH_C1, S(3));
-    axpy(dRGBdy, -SH_C1, S(1));
-    axpy(dRGBdz, SH_C1, S(2));
-    if (deg > 1) {
-      const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-      put(4, SH_C2[0] * xy);
-      put(5, SH_C2[1] * yz);
-      put(6, SH_C2[2] * (2.f * zz - xx - yy));
-      put(7, SH_C2[3] * xz);
-      put(8, SH_C2[4] * (xx - yy));
-      const float3 s4 = S(4), s5 = S(5), s6 = S(6), s7 = S(7), s8 = S(8);
-      axpy(dRGBdx, SH_C2[0] * y, s4); axpy(dRGBdx, SH_C2[2] * 2.f * -x, s6); axpy(dRGBdx, SH_C2[3] * z, s7); axpy(dRGBdx, SH_C2[4] * 2.f * x, s8);
-      axpy(dRGBdy, SH_C2[0] * x, s4); axpy(dRGBdy, SH_C2[1] * z, s5); axpy(dRGBdy, SH_C2[2] * 2.f * -y, s6); axpy(dRGBdy, SH_C2[4] * 2.f * -y, s8);
-      axpy(dRGBdz, SH_C2[1] * y, s5); axpy(dRGBdz, SH_C2[2] * 2.f * 2.f * z, s6); axpy(dRGBdz, SH_C2[3] * x, s7);
-      if (deg > 2) {
-        put(9, SH_C3[0] * y * (3.f * xx - yy));
-        put(10, SH_C3[1] * xy * z);
-        put(11, SH_C3[2] * y * (4.f * zz - xx - yy));
-        put(12, SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy));
-        put(13, SH_C3[4] * x * (4.f * zz - xx - yy));
-        put(14, SH_C3[5] * z * (xx - yy));
-        put(15, SH_C3[6] * x * (xx - 3.f * yy));
-        const float3 s9 = S(9), s10 = S(10), s11 = S(11), s12 = S(12), s13 = S(13), s14 = S(14), s15 = S(15);
-        axpy(dRGBdx, SH_C3[0] * 3.f * 2.f * xy, s9); axpy(dRGBdx, SH_C3[1] * yz, s10); axpy(dRGBdx, SH_C3[2] * -2.f * xy, s11);
-        axpy(dRGBdx, SH_C3[3] * -3.f * 2.f * xz, s12); axpy(dRGBdx, SH_C3[4] * (-3.f * xx + 4.f * zz - yy), s13);
-        axpy(dRGBdx, SH_C3[5] * 2.f * xz, s14); axpy(dRGBdx, SH_C3[6] * 3.f * (xx - yy), s15);
-        axpy(dRGBdy, SH_C3[0] * 3.f * (xx - yy), s9); axpy(dRGBdy, SH_C3[1] * xz, s10);
-        axpy(dRGBdy, SH_C3[2] * (-3.f * yy + 4.f * zz - xx), s11); axpy(dRGBdy, SH_C3[3] * -3.f * 2.f * yz, s12);
-        axpy(dRGBdy, SH_C3[4] * -2.f * xy, s13); axpy(dRGBdy, SH_C3[5] * -2.f * yz, s14); axpy(dRGBdy, SH_C3[6] * -3.f * 2.f * xy, s15);
-        axpy(dRGBdz, SH_C3[1] * xy, s10); axpy(dRGBdz, SH_C3[2] * 4.f * 2.f * yz, s11);
-        axpy(dRGBdz, SH_C3[3] * 3.f * (2.f * zz - xx - yy), s12); axpy(dRGBdz, SH_C3[4] * 4.f * 2.f * xz, s13);
-        axpy(dRGBdz, SH_C3[5] * (xx - yy), s14);
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    if (g < ngroups) {
+      float w[4], wx[4], wy[4], wz[4];
+      if (g == 0) {
+        w[0] = SH_C0;       wx[0] = 0.f;    wy[0] = 0.f;    wz[0] = 0.f;
+        w[1] = -SH_C1 * y;  wx[1] = 0.f;    wy[1] = -SH_C1; wz[1] = 0.f;
+        w[2] = SH_C1 * z;   wx[2] = 0.f;    wy[2] = 0.f;    wz[2] = SH_C1;
+        w[3] = -SH_C1 * x;  wx[3] = -SH_C1; wy[3] = 0.f;    wz[3] = 0.f;
+      } else if (g == 1) {
+        w[0] = SH_C2[0] * xy;                     wx[0] = SH_C2[0] * y;        wy[0] = SH_C2[0] * x;        wz[0] = 0.f;
+        w[1] = SH_C2[1] * yz;                     wx[1] = 0.f;                 wy[1] = SH_C2[1] * z;        wz[1] = SH_C2[1] * y;
+        w[2] = SH_C2[2] * (2.f * zz - xx - yy);   wx[2] = SH_C2[2] * -2.f * x; wy[2] = SH_C2[2] * -2.f * y; wz[2] = SH_C2[2] * 4.f * z;
+        w[3] = SH_C2[3] * xz;                     wx[3] = SH_C2[3] * z;        wy[3] = 0.f;                 wz[3] = SH_C2[3] * x;
+      } else if (g == 2) {
+        w[0] = SH_C2[4] * (xx - yy);              wx[0] = SH_C2[4] * 2.f * x;  wy[0] = SH_C2[4] * -2.f * y; wz[0] = 0.f;
+        w[1] = SH_C3[0] * y * (3.f * xx - yy);    wx[1] = SH_C3[0] * 6.f * xy; wy[1] = SH_C3[0] * 3.f * (xx - yy); wz[1] = 0.f;
+        w[2] = SH_C3[1] * xy * z;                 wx[2] = SH_C3[1] * yz;       wy[2] = SH_C3[1] * xz;       wz[2] = SH_C3[1] * xy;
+        w[3] = SH_C3[2] * y * (4.f * zz - xx - yy);
+        wx[3] = SH_C3[2] * -2.f * xy; wy[3] = SH_C3[2] * (-3.f * yy + 4.f * zz - xx); wz[3] = SH_C3[2] * 8.f * yz;
+      } else {
+        w[0] = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+        wx[0] = SH_C3[3] * -6.f * xz; wy[0] = SH_C3[3] * -6.f * yz; wz[0] = SH_C3[3] * 3.f * (2.f * zz - xx - yy);
+        w[1] = SH_C3[4] * x * (4.f * zz - xx - yy);
+        wx[1] = SH_C3[4] * (-3.f * xx + 4.f * zz - yy); wy[1] = SH_C3[4] * -2.f * xy; wz[1] = SH_C3[4] * 8.f * xz;
+        w[2] = SH_C3[5] * z * (xx - yy);          wx[2] = SH_C3[5] * 2.f * xz; wy[2] = SH_C3[5] * -2.f * yz; wz[2] = SH_C3[5] * (xx - yy);
+        w[3] = SH_C3[6] * x * (xx - 3.f * yy);    wx[3] = SH_C3[6] * 3.f * (xx - yy); wy[3] = SH_C3[6] * -6.f * xy; wz[3] = 0.f;
+      }
+      float c[12];
+      if (vec4) {
+        const float4* s4 = reinterpret_cast<const float4*>(sh + 12 * g);
+        const float4 v0 = __ldg(s4), v1 = __ldg(s4 + 1), v2 = __ldg(s4 + 2);
+        c[0] = v0.x, c[1] = v0.y, c[2] = v0.z, c[3] = v0.w, c[4] = v1.x, c[5] = v1.y, c[6] = v1.z, c[7] = v1.w;
+        c[8] = v2.x, c[9] = v2.y, c[10] = v2.z, c[11] = v2.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 12; q++) c[q] = (4 * g + q / 3 < ncoef) ? __ldg(sh + 12 * g + q) : 0.f;
+      }
+      float o[12];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const bool on = 4 * g + k < ncoef;
+        const float wk = on ? w[k] : 0.f;
+        o[3 * k] = wk * dL_dRGB.x, o[3 * k + 1] = wk * dL_dRGB.y, o[3 * k + 2] = wk * dL_dRGB.z;
+        if (on) {
+          dRGBdx.x += wx[k] * c[3 * k]; dRGBdx.y += wx[k] * c[3 * k + 1]; dRGBdx.z += wx[k] * c[3 * k + 2];
+          dRGBdy.x += wy[k] * c[3 * k]; dRGBdy.y += wy[k] * c[3 * k + 1]; dRGBdy.z += wy[k] * c[3 * k + 2];
+          dRGBdz.x += wz[k] * c[3 * k]; dRGBdz.y += wz[k] * c[3 * k + 1]; dRGBdz.z += wz[k] * c[3 * k + 2];
+        }
+      }
+      if (out) {
+        if (vec4) {
+          float4* o4 = reinterpret_cast<float4*>(out + 12 * g);
+          o4[0] = make_float4(o[0], o[1], o[2], o[3]);
+          o4[1] = make_float4(o[4], o[5], o[6], o[7]);
+          o4[2] = make_float4(o[8], o[9], o[10], o[11]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 12; q++)
+            if (4 * g + q / 3 < ncoef) out[12 * g + q] = o[q];
+        }
       }
     }
   }
@@ -102,13 +122,15 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t nvis = p.geom.block_vis[blockIdx.x];
   if (nvis == 0) return;
-  const uint32_t k = blockIdx.x * BW_THREADS + tid;     // slot
   const int M = p.M;
   const int row = 3 * M;                 // floats per SH row
-  const bool visible = (uint32_t)tid < nvis;
   const float* vm = p.viewmatrix;
   const float* proj = p.projmatrix;
+  float tau[6] = {0, 0, 0, 0, 0, 0};
 
+  for (uint32_t t_in_seg = tid; t_in_seg < nvis; t_in_seg += BW_THREADS) {
+  const uint32_t k = blockIdx.x * PRE_THREADS + t_in_seg;     // slot
+  const bool visible = true;
   float3 g_mean2D = {0, 0, 0};
   float4 g_conic = {0, 0, 0, 0};
   float g_opacity = 0.f;
@@ -117,7 +139,6 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
   float g_cov[6] = {0, 0, 0, 0, 0, 0};
   float3 g_scale = {0, 0, 0};
   float4 g_rot = {0, 0, 0, 0};
-  float tau[6] = {0, 0, 0, 0, 0, 0};
   size_t idx = 0;
 
   if (visible) {
@@ -217,7 +238,8 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
       const float3 dL_dRGB = {(cm & 1) ? 0.f : g_color.x, (cm & 2) ? 0.f : g_color.y, (cm & 4) ? 0.f : g_color.z};
       const float3 cp = {__ldg(p.campos), __ldg(p.campos + 1), __ldg(p.campos + 2)};
       // rows of the SH gradient were zero-filled; coefficients above the active degree stay zero
-      g_sh_mean = sh_backward(p.D, mean, cp, p.shs + idx * row, dL_dRGB, p.dL_dsh ? p.dL_dsh + idx * row : nullptr);
+      const bool vec4 = (M % 4 == 0) && (((uintptr_t)p.shs | (uintptr_t)p.dL_dsh) % 16 == 0);
+      g_sh_mean = sh_backward(p.D, mean, cp, p.shs + idx * row, dL_dRGB, p.dL_dsh ? p.dL_dsh + idx * row : nullptr, vec4);
       g_mean.x += g_sh_mean.x; g_mean.y += g_sh_mean.y; g_mean.z += g_sh_mean.z;
     }
 
@@ -268,10 +290,10 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
       float gz = (raw[8] * r_w - raw[11] * rmul1) * g_mean2D.x + (raw[9] * r_w - raw[11] * rmul2) * g_mean2D.y;
       // (2) covariance path through t, (3) rendered depth through p_c.z
       gx += dL_dtx; gy += dL_dty; gz += dL_dtz + g_depth;
-      tau[0] = gx; tau[1] = gy; tau[2] = gz;
-      tau[3] = pcy * gz - pcz * gy;
-      tau[4] = pcz * gx - pcx * gz;
-      tau[5] = pcx * gy - pcy * gx;
+      tau[0] += gx; tau[1] += gy; tau[2] += gz;
+      tau[3] += pcy * gz - pcz * gy;
+      tau[4] += pcz * gx - pcx * gz;
+      tau[5] += pcx * gy - pcy * gx;
       // (4) covariance path through the rotation W: G[m][i] = dL/dR[m][i], Q = R G^T, dtheta = axial(Q - Q^T)
       float G[3][3];
 #pragma unroll
@@ -308,6 +330,7 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
     if (p.dL_dscale) { float* o = p.dL_dscale + 3 * idx; o[0] = g_scale.x; o[1] = g_scale.y; o[2] = g_scale.z; }
     if (p.dL_drot) reinterpret_cast<float4*>(p.dL_drot)[idx] = g_rot;
   }
+  }  // loop over the segment's visible slots
 
   // ---------------- pose gradient: CTA reduction, 6 atomics
   if (p.dL_dtau) {

@@ -80,29 +80,46 @@ __device__ __forceinline__ void bitonic_sort_block(Ptr a, uint32_t n, uint32_t n
 // One CTA.  diff is the (gy+1) x (gx+1) difference grid; after the 2-D inclusive prefix sum
 // diff[y][x] is the number of Gaussians whose rectangle covers tile (x, y).
 constexpr uint32_t ST_SMEM_CELLS = 10240;   // difference grids up to this many cells are scanned in shared memory
+constexpr int ST_THREADS = 1024;
+constexpr int ST_BUCKETS = 64;
 
-__global__ void __launch_bounds__(1024) scan_tiles_kernel(int* __restrict__ diff_g, uint32_t gx, uint32_t gy,
-                                                          uint2* __restrict__ ranges, uint32_t* __restrict__ cursor,
-                                                          uint32_t* __restrict__ tile_order, uint32_t* __restrict__ counters) {
-  __shared__ int s_grid[ST_SMEM_CELLS];
-  __shared__ uint32_t s_part[1024];
+// One CTA.  IN_SMEM: the whole grid fits in shared memory (any image up to ~2.5 Mpixel).
+template <bool IN_SMEM>
+__global__ void __launch_bounds__(ST_THREADS) scan_tiles_kernel(int* __restrict__ diff_g, uint32_t gx, uint32_t gy,
+                                                                uint2* __restrict__ ranges, uint32_t* __restrict__ cursor,
+                                                                uint32_t* __restrict__ tile_order,
+                                                                uint32_t* __restrict__ counters) {
+  __shared__ int s_grid[IN_SMEM ? ST_SMEM_CELLS : 1];
+  __shared__ uint32_t s_part[ST_THREADS];
   __shared__ uint32_t s_max[32];
-  const uint32_t tid = threadIdx.x, nt = blockDim.x;
+  __shared__ uint32_t s_bucket[ST_BUCKETS];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr uint32_t nt = ST_THREADS;
   const uint32_t stride = gx + 1;
   const uint32_t cells = stride * (gy + 1);
-  const bool in_smem = cells <= ST_SMEM_CELLS;
-  int* diff = in_smem ? s_grid : diff_g;
-  if (in_smem) {
+  int* diff = IN_SMEM ? s_grid : diff_g;
+  if (IN_SMEM) {
     for (uint32_t i = tid; i < cells; i += nt) s_grid[i] = diff_g[i];
-    __syncthreads();
   }
-  for (uint32_t y = tid; y <= gy; y += nt) {      // along rows
-    int run = 0;
+  if (tid < ST_BUCKETS) s_bucket[tid] = 0;
+  __syncthreads();
+  // prefix along rows: one warp per row, shuffle scan over 32-wide pieces
+  for (uint32_t y = warp; y <= gy; y += nt / 32) {
+    int carry = 0;
     int* row = diff + y * stride;
-    for (uint32_t x = 0; x <= gx; x++) { run += row[x]; row[x] = run; }
+    for (uint32_t x0 = 0; x0 <= gx; x0 += 32) {
+      const uint32_t x = x0 + lane;
+      int v = x <= gx ? row[x] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += n; }
+      v += carry;
+      if (x <= gx) row[x] = v;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+    }
   }
   __syncthreads();
-  for (uint32_t x = tid; x <= gx; x += nt) {      // along columns
+  // prefix along columns: one thread per column
+  for (uint32_t x = tid; x <= gx; x += nt) {
     int run = 0;
     for (uint32_t y = 0; y <= gy; y++) { run += diff[y * stride + x]; diff[y * stride + x] = run; }
   }
@@ -112,57 +129,81 @@ __global__ void __launch_bounds__(1024) scan_tiles_kernel(int* __restrict__ diff
   const uint32_t chunk = (T + nt - 1) / nt;
   const uint32_t t0 = min(T, tid * chunk), t1 = min(T, t0 + chunk);
   uint32_t sum = 0, mx = 0;
-  for (uint32_t t = t0; t < t1; t++) {
-    const uint32_t c = (uint32_t)diff[(t / gx) * stride + (t % gx)];
-    sum += c;
-    mx = max(mx, c);
+  {
+    uint32_t ty = t0 / gx, tx = t0 - ty * gx;
+    for (uint32_t t = t0; t < t1; t++) {
+      const uint32_t c = (uint32_t)diff[ty * stride + tx];
+      sum += c;
+      mx = max(mx, c);
+      if (++tx == gx) tx = 0, ty++;
+    }
   }
-  s_part[tid] = sum;
-  mx = __reduce_max_sync(0xffffffffu, mx);
-  if ((tid & 31) == 0) s_max[tid >> 5] = mx;
-  __syncthreads();
-  if (tid < 32) {   // scan the 1024 partials: 32 per lane, then across lanes
-    uint32_t loc = 0;
-    for (uint32_t i = 0; i < nt / 32; i++) { const uint32_t v = s_part[tid * (nt / 32) + i]; s_part[tid * (nt / 32) + i] = loc; loc += v; }
-    uint32_t incl = loc;
+  // block scan of the per-thread sums
+  uint32_t incl = sum;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= (uint32_t)o) incl += v; }
-    const uint32_t excl = incl - loc;
-    for (uint32_t i = 0; i < nt / 32; i++) s_part[tid * (nt / 32) + i] += excl;
-    uint32_t m = tid < nt / 32 ? s_max[tid] : 0;
-    m = __reduce_max_sync(0xffffffffu, m);
-    if (tid == 31) counters[1] = incl;   // num_rendered
-    if (tid == 0) counters[4] = m;       // longest tile list
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += n; }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if (lane == 31) s_part[warp] = incl;
+  if (lane == 0) s_max[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = s_part[lane];
+    uint32_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= (uint32_t)o) wi += n; }
+    s_part[lane] = wi - w;                       // exclusive offset of each warp
+    const uint32_t m = __reduce_max_sync(0xffffffffu, s_max[lane]);
+    if (lane == 31) counters[1] = wi;            // num_rendered
+    if (lane == 0) counters[4] = m, s_max[0] = m;  // longest tile list
   }
   __syncthreads();
-  uint32_t run = s_part[tid];
-  for (uint32_t t = t0; t < t1; t++) {
-    const uint32_t c = (uint32_t)diff[(t / gx) * stride + (t % gx)];
-    ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);   // untouched tiles stay (0,0) like the reference
-    cursor[t] = run;
-    run += c;
+  const uint32_t longest = s_max[0];
+  // ranges + bucket cursors + launch order of the blend CTAs (longest lists first: counting sort on 64 length classes)
+  uint32_t run = s_part[warp] + incl - sum;
+  uint32_t my_bucket[(8192 + ST_THREADS - 1) / ST_THREADS + 1];
+  const bool order_ok = chunk <= sizeof(my_bucket) / sizeof(uint32_t);
+  {
+    uint32_t ty = t0 / gx, tx = t0 - ty * gx;
+    for (uint32_t t = t0, i = 0; t < t1; t++, i++) {
+      const uint32_t c = (uint32_t)diff[ty * stride + tx];
+      ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);   // untouched tiles stay (0,0) like the reference
+      cursor[t] = run;
+      run += c;
+      if (order_ok) {
+        const uint32_t bk = (ST_BUCKETS - 1) - min((uint32_t)(ST_BUCKETS - 1), (uint32_t)(((unsigned long long)c * ST_BUCKETS) / (longest + 1)));
+        my_bucket[i] = bk;
+        atomicAdd(&s_bucket[bk], 1u);
+      }
+      if (++tx == gx) tx = 0, ty++;
+    }
   }
-  // launch order of the blend CTAs: longest lists first, so the short ones fill the tail of the grid
-  if (T <= 8192 && in_smem) {
-    __syncthreads();
-    uint32_t* keys = reinterpret_cast<uint32_t*>(s_grid);
-    uint32_t cnt_of[8];
-    for (uint32_t i = 0, t = tid; t < T; t += nt, i++) cnt_of[i] = (uint32_t)diff[(t / gx) * stride + (t % gx)];
-    __syncthreads();   // counts are in registers; the grid memory is reused for the sort keys
-    for (uint32_t i = 0, t = tid; t < T; t += nt, i++) keys[t] = ~((min(cnt_of[i], 0x7ffffu) << 13) | t);
-    __syncthreads();
-    uint32_t n2 = 1;
-    while (n2 < T) n2 <<= 1;
-    bitonic_sort_block<uint32_t>(keys, T, n2);
-    for (uint32_t t = tid; t < T; t += nt) tile_order[t] = (~keys[t]) & 0x1fffu;
-  } else {
+  __syncthreads();
+  if (!order_ok) {
     for (uint32_t t = tid; t < T; t += nt) tile_order[t] = t;
+    return;
   }
+  if (warp == 0) {   // exclusive scan of the 64 class sizes
+    const uint32_t a = s_bucket[lane], b = s_bucket[lane + 32];
+    uint32_t ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t na = __shfl_up_sync(0xffffffffu, ia, o), nb = __shfl_up_sync(0xffffffffu, ib, o);
+      if (lane >= (uint32_t)o) ia += na, ib += nb;
+    }
+    const uint32_t tot_a = __shfl_sync(0xffffffffu, ia, 31);
+    s_bucket[lane] = ia - a;
+    s_bucket[lane + 32] = tot_a + ib - b;
+  }
+  __syncthreads();
+  for (uint32_t t = t0, i = 0; t < t1; t++, i++) tile_order[atomicAdd(&s_bucket[my_bucket[i]], 1u)] = t;
 }
 
 void launch_scan_tiles(int* tile_diff, uint32_t gx, uint32_t gy, uint2* ranges, uint32_t* cursor, uint32_t* tile_order,
                        uint32_t* counters, cudaStream_t stream) {
-  scan_tiles_kernel<<<1, 1024, 0, stream>>>(tile_diff, gx, gy, ranges, cursor, tile_order, counters);
+  if ((gx + 1) * (gy + 1) <= ST_SMEM_CELLS)
+    scan_tiles_kernel<true><<<1, ST_THREADS, 0, stream>>>(tile_diff, gx, gy, ranges, cursor, tile_order, counters);
+  else
+    scan_tiles_kernel<false><<<1, ST_THREADS, 0, stream>>>(tile_diff, gx, gy, ranges, cursor, tile_order, counters);
   count_launch();
 }
 

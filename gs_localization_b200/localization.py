@@ -1,0 +1,115 @@
+"""Pose refinement on the B200 rasterizer: the loop body of LoGS' `gradient_decent`
+(gs_localization/pipelines/7scenes_localize_full_dslam.py:29-93) without its dataset I/O.
+
+A `PoseCamera` carries the world-to-camera pose and the two zero-initialised Adam parameters
+`cam_rot_delta` / `cam_trans_delta` (tools/camera_utils.py:38-110); each iteration renders through
+`diff_gaussian_rasterization_pose`, takes an L1 (+ optional depth L1) tracking loss
+(tools/descent_utils.py:85-123 with all-ones masks), steps Adam and folds the deltas into the pose
+with the left-multiplicative SE(3) update of tools/pose_utils.py:105-122.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import synthetic as syn
+from .diff_gaussian_rasterization_pose import GaussianRasterizationSettings, GaussianRasterizer
+
+
+def so3_exp(theta: torch.Tensor) -> torch.Tensor:
+    """tools/pose_utils.py:54-70 on device tensors."""
+    z = torch.zeros((), dtype=theta.dtype, device=theta.device)
+    Wm = torch.stack([torch.stack([z, -theta[2], theta[1]]), torch.stack([theta[2], z, -theta[0]]),
+                      torch.stack([-theta[1], theta[0], z])])
+    W2 = Wm @ Wm
+    a = torch.linalg.norm(theta)
+    I = torch.eye(3, dtype=theta.dtype, device=theta.device)
+    if float(a) < 1e-5:
+        return I + Wm + 0.5 * W2, Wm, W2, a
+    return I + (torch.sin(a) / a) * Wm + ((1 - torch.cos(a)) / a**2) * W2, Wm, W2, a
+
+
+def se3_exp(tau: torch.Tensor) -> torch.Tensor:
+    """tools/pose_utils.py:73-102; tau = [rho, theta]."""
+    rho, theta = tau[:3], tau[3:]
+    Rm, Wm, W2, a = so3_exp(theta)
+    I = torch.eye(3, dtype=tau.dtype, device=tau.device)
+    if float(a) < 1e-5:
+        V = I + 0.5 * Wm + (1.0 / 6.0) * W2
+    else:
+        V = I + Wm * ((1.0 - torch.cos(a)) / a**2) + W2 * ((a - torch.sin(a)) / a**3)
+    T = torch.eye(4, dtype=tau.dtype, device=tau.device)
+    T[:3, :3] = Rm
+    T[:3, 3] = V @ rho
+    return T
+
+
+class PoseCamera:
+    """Mirror of the MonoGS-derived Camera used by LoGS (tools/camera_utils.py): pose + pose deltas."""
+
+    def __init__(self, cam: syn.Camera, device):
+        self.device = torch.device(device)
+        self.W, self.H = cam.W, cam.H
+        self.tanfovx, self.tanfovy = cam.tanfovx, cam.tanfovy
+        self.w2c = cam.w2c.to(torch.float32).to(self.device)        # R | T
+        self.projection_matrix = syn.projection_matrix2(cam.znear, cam.zfar, cam.cx, cam.cy, cam.fx, cam.fy, cam.W,
+                                                        cam.H).t().contiguous().float().to(self.device)
+        self.cam_rot_delta = torch.nn.Parameter(torch.zeros(3, device=self.device))
+        self.cam_trans_delta = torch.nn.Parameter(torch.zeros(3, device=self.device))
+
+    # tools/camera_utils.py:144-158
+    @property
+    def world_view_transform(self):
+        return self.w2c.t().contiguous()
+
+    @property
+    def full_proj_transform(self):
+        return self.world_view_transform @ self.projection_matrix
+
+    @property
+    def camera_center(self):
+        Rm, t = self.w2c[:3, :3], self.w2c[:3, 3]
+        return -(Rm.t() @ t)
+
+    def update_pose(self, converged_threshold: float = 1e-4) -> bool:
+        """tools/pose_utils.py:105-122."""
+        with torch.no_grad():
+            tau = torch.cat([self.cam_trans_delta, self.cam_rot_delta])
+            self.w2c = se3_exp(tau) @ self.w2c
+            converged = bool(tau.norm() < converged_threshold)
+            self.cam_rot_delta.zero_()
+            self.cam_trans_delta.zero_()
+        return converged
+
+
+def render_pose(gmap: syn.GaussianMap, cam: PoseCamera, bg: torch.Tensor):
+    """tools/__init__.py:24-153 reduced to its rasterizer call."""
+    rs = GaussianRasterizationSettings(
+        image_height=cam.H, image_width=cam.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=bg, scale_modifier=1.0,
+        viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, projmatrix_raw=cam.projection_matrix,
+        sh_degree=gmap.sh_degree, campos=cam.camera_center, prefiltered=False, debug=False)
+    means2D = torch.zeros_like(gmap.means3D)
+    return GaussianRasterizer(rs)(means3D=gmap.means3D, means2D=means2D, opacities=gmap.opacities, shs=gmap.shs,
+                                  scales=gmap.scales, rotations=gmap.rotations, theta=cam.cam_rot_delta,
+                                  rho=cam.cam_trans_delta)
+
+
+def refine_pose(gmap: syn.GaussianMap, cam: PoseCamera, target: torch.Tensor, iters: int = 50, lr: float = 1e-3,
+                target_depth: torch.Tensor | None = None, depth_weight: float = 0.01, converge: bool = False):
+    """`gradient_decent` (7scenes_localize_full_dslam.py:29-93): Adam on (rot, trans) deltas, fixed iteration count
+    unless `converge` re-enables the reference's early break.  The map carries no gradient (pose-only refinement)."""
+    bg = torch.zeros(3, device=cam.device)
+    opt = torch.optim.Adam([{"params": [cam.cam_rot_delta], "lr": lr}, {"params": [cam.cam_trans_delta], "lr": lr}])
+    loss = None
+    for _ in range(iters):
+        image, radii, depth, opacity, n_touched = render_pose(gmap, cam, bg)
+        loss = (image - target).abs().mean()
+        if target_depth is not None:
+            loss = loss + depth_weight * (depth - target_depth).abs().mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        if cam.update_pose() and converge:
+            break
+    return cam.w2c, loss

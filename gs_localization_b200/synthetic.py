@@ -199,5 +199,8 @@ def pose_error(w2c_a: torch.Tensor, w2c_b: torch.Tensor):
     ca = -a[:3, :3].t() @ a[:3, 3]
     cb = -b[:3, :3].t() @ b[:3, 3]
     dR = a[:3, :3] @ b[:3, :3].t()
-    cos = max(-1.0, min(1.0, (float(torch.trace(dR)) - 1) / 2))
-    return float((ca - cb).norm()), math.degrees(math.acos(cos))
+    # atan2 of (sin, cos) from the antisymmetric part: well conditioned for tiny angles, unlike acos(trace)
+    A = dR - dR.t()
+    sin = 0.5 * float(torch.stack([A[2, 1], A[0, 2], A[1, 0]]).norm())
+    cos = (float(torch.trace(dR)) - 1) / 2
+    return float((ca - cb).norm()), math.degrees(math.atan2(sin, cos))
