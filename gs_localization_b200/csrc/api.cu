@@ -5,6 +5,7 @@
 // buffer-carving helpers (rasterizer_impl.cu:155-193, rasterizer_impl.h:21-27,66-72).
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -44,10 +45,12 @@ int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail(GSR_ERR_CUDA, "stage %s: %s", name, cudaGetErrorString(e__)); \
   } while (0)
 
-char* carve_binning(char* base, long long R, BinningView& b) {
-  char* p = base;
-  carve(p, b.comp, (size_t)R);
-  carve(p, b.point_list, (size_t)R);
+// [header: capacity (u64), 128 B][point_list u32[cap]][comp u64[cap]] — the backward only needs point_list, whose
+// offset does not depend on the capacity the forward happened to allocate (speculative launches over-allocate)
+char* carve_binning(char* base, long long cap, BinningView& b) {
+  char* p = base + 128;
+  carve(p, b.point_list, (size_t)cap);
+  carve(p, b.comp, (size_t)cap);
   return p;
 }
 
@@ -118,13 +121,52 @@ SideStream* side_stream() {
   return &s;
 }
 
-// pinned 4-byte mailbox for num_rendered, one per host thread
-uint32_t* pinned_mailbox() {
-  thread_local uint32_t* box = nullptr;
-  if (!box) {
-    if (cudaHostAlloc((void**)&box, 64, cudaHostAllocDefault) != cudaSuccess) box = nullptr;
+// pinned mailbox for num_rendered + the event that says it has landed, one per host thread
+struct Mailbox {
+  uint32_t* value = nullptr;
+  cudaEvent_t ready = nullptr;
+};
+Mailbox* pinned_mailbox() {
+  thread_local Mailbox box;
+  if (!box.value) {
+    if (cudaHostAlloc((void**)&box.value, 64, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&box.ready, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   }
-  return box;
+  return &box;
+}
+
+// Binning-capacity history for the speculative launch: the last 16 num_rendered values seen per (P, W, H),
+// per host thread.  The guess is their maximum plus 25 % headroom: consecutive refinement iterations barely
+// change num_rendered, and a caller cycling through a handful of views is covered by the maximum.
+struct CountHistory {
+  int P = -1, W = 0, H = 0, n = 0, pos = 0;
+  long long R[16] = {};
+};
+thread_local CountHistory t_hist[4];
+long long capacity_guess(int P, int W, int H) {
+  static const bool disabled = getenv("GSR_NO_SPECULATION") != nullptr;   // A/B switch for measurements
+  if (disabled) return 0;
+  for (auto& h : t_hist)
+    if (h.P == P && h.W == W && h.H == H && h.n > 0) {
+      long long m = 0;
+      for (int i = 0; i < h.n; i++) m = std::max(m, h.R[i]);
+      return m + m / 4 + 4096;
+    }
+  return 0;
+}
+void remember_count(int P, int W, int H, long long R) {
+  for (auto& h : t_hist)
+    if (h.P == P && h.W == W && h.H == H) {
+      h.R[h.pos] = R;
+      h.pos = (h.pos + 1) % 16;
+      h.n = std::min(h.n + 1, 16);
+      return;
+    }
+  static thread_local int next = 0;
+  CountHistory& h = t_hist[next];
+  h = CountHistory{};
+  h.P = P, h.W = W, h.H = H, h.n = 1, h.pos = 1, h.R[0] = R;
+  next = (next + 1) % 4;
 }
 }  // namespace
 
@@ -182,6 +224,7 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
   long long R = 0;
   GeometryView g{};
   BinningView bl{};
+  Mailbox* box = nullptr;
   if (P > 0) {
     char* geom_base = geometry_alloc(gsr_geometry_bytes(P), user);
     if (!geom_base) return fail(GSR_ERR_ALLOC, "geometry_alloc returned NULL");
@@ -211,48 +254,97 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     }
     GSR_STAGE("scan_tiles", debug, stream);
 
-    // num_rendered -> host: the one sync the reference also has (rasterizer_impl.cu:282)
-    uint32_t* box = pinned_mailbox();
+    // num_rendered -> pinned host mailbox, asynchronously; `r_ready` fires when it has landed
+    box = pinned_mailbox();
     if (!box) return fail(GSR_ERR_CUDA, "cudaHostAlloc failed");
-    GSR_CUDA(cudaMemcpyAsync(box, g.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    GSR_CUDA(cudaStreamSynchronize(stream));
-    R = (long long)box[0];
+    *reinterpret_cast<volatile uint32_t*>(box->value) = 0xffffffffu;   // sentinel: num_rendered is always < 2^31
+    GSR_CUDA(cudaMemcpyAsync(box->value, g.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    GSR_CUDA(cudaEventRecord(box->ready, stream));
   } else {
     GSR_CUDA(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)T, stream));
   }
 
-  {
-    char* bin_base = binning_alloc(gsr_binning_bytes(R, width, height), user);
+  // The reference blocks here until num_rendered is on the host (rasterizer_impl.cu:282) and only then
+  // sizes the binning buffer and launches the rest, so the GPU idles for a host round trip every
+  // forward.  Here the rest of the forward is launched SPECULATIVELY into a binning buffer sized from the
+  // previous call with the same (P, W, H); the host then waits for num_rendered while the GPU keeps
+  // working.  If the guess was too small (kernels clamp to the capacity, nothing overruns) the tail is
+  // simply re-run with the exact size.  First call / no history: the reference's order.
+  unsigned long long* bin_header = nullptr;
+  auto run_tail = [&](long long capacity) -> int {
+    if (capacity > 0) {
+      {
+        StageScope ts(ST_DUPLICATE, stream);
+        launch_scatter(P, g, im.tile_cursor, bl.comp, gx, (uint32_t)capacity, bin_header, stream);
+      }
+      GSR_STAGE("scatter", debug, stream);
+      {
+        StageScope ts(ST_SORT, stream);
+        launch_tile_sort(T, im.ranges, bl.comp, bl.point_list, (uint32_t)capacity, stream);
+      }
+      GSR_STAGE("tile_sort", debug, stream);
+    }
+    RenderParams rp{};
+    rp.W = width, rp.H = height, rp.grid_x = gx, rp.grid_y = gy;
+    rp.ranges = im.ranges, rp.point_list = bl.point_list, rp.tile_order = (P > 0) ? im.tile_order : nullptr;
+    rp.means2D = g.means2D, rp.conic_opacity = g.conic_opacity, rp.rgbd = g.rgbd, rp.gid = g.gid;
+    rp.bg = background, rp.out_color = out_color, rp.out_depth = out_depth, rp.out_alpha = out_alpha;
+    rp.n_contrib = im.n_contrib, rp.n_touched = (P > 0) ? n_touched : nullptr;
+    rp.capacity = (uint32_t)capacity;
+    {
+      StageScope ts(ST_RENDER, stream);
+      launch_render_fwd(rp, stream);
+    }
+    GSR_STAGE("render", debug, stream);
+    return GSR_OK;
+  };
+  auto alloc_binning = [&](long long cap) -> int {
+    char* bin_base = binning_alloc(gsr_binning_bytes(cap, width, height), user);
     if (!bin_base) return fail(GSR_ERR_ALLOC, "binning_alloc returned NULL");
-    carve_binning(bin_base, R, bl);
-  }
-  if (R > 0) {
-    {
-      StageScope ts(ST_DUPLICATE, stream);
-      launch_scatter(P, g, im.tile_cursor, bl.comp, gx, (uint32_t)R, stream);
-    }
-    GSR_STAGE("scatter", debug, stream);
-    {
-      StageScope ts(ST_SORT, stream);
-      launch_tile_sort(T, im.ranges, bl.comp, bl.point_list, (uint32_t)R, stream);
-    }
-    GSR_STAGE("tile_sort", debug, stream);
-  }
+    carve_binning(bin_base, cap, bl);
+    bin_header = reinterpret_cast<unsigned long long*>(bin_base);   // capacity is recorded there by the scatter kernel
+    return GSR_OK;
+  };
 
-  RenderParams rp{};
-  rp.W = width, rp.H = height, rp.grid_x = gx, rp.grid_y = gy;
-  rp.ranges = im.ranges, rp.point_list = bl.point_list, rp.tile_order = (P > 0) ? im.tile_order : nullptr;
-  rp.means2D = g.means2D, rp.conic_opacity = g.conic_opacity, rp.rgbd = g.rgbd, rp.gid = g.gid;
-  rp.bg = background, rp.out_color = out_color, rp.out_depth = out_depth, rp.out_alpha = out_alpha;
-  rp.n_contrib = im.n_contrib, rp.n_touched = (P > 0) ? n_touched : nullptr;
-  {
-    StageScope ts(ST_RENDER, stream);
-    launch_render_fwd(rp, stream);
+  long long guess = (P > 0 && !debug && !g_timer.enabled) ? capacity_guess(P, width, height) : 0;
+  bool speculated = false;
+  if (guess > 0) {
+    if (int rc = alloc_binning(guess)) return rc;
+    if (int rc = run_tail(guess)) return rc;
+    speculated = true;
   }
-  GSR_STAGE("render", debug, stream);
+  if (P > 0) {
+    // poll the pinned word the copy engine writes (cheaper than a driver-level wait), with the event as a safety net
+    {
+      volatile uint32_t* v = reinterpret_cast<volatile uint32_t*>(box->value);
+      int spins = 0;
+      while (*v == 0xffffffffu) {
+        if (++spins > 2000) {
+          const cudaError_t q = cudaEventQuery(box->ready);
+          if (q == cudaSuccess) break;
+          if (q != cudaErrorNotReady) return fail(GSR_ERR_CUDA, "waiting for num_rendered: %s", cudaGetErrorString(q));
+          spins = 0;
+        }
+      }
+      if (*v == 0xffffffffu) GSR_CUDA(cudaEventSynchronize(box->ready));
+    }
+    R = (long long)*box->value;
+    remember_count(P, width, height, R);
+  }
+  if (!speculated || R > guess) {
+    if (speculated) {
+      // overflow: the scatter consumed the cursors; rebuild them from the ranges before re-running
+      GSR_CUDA(cudaStreamSynchronize(stream));
+      launch_reset_cursors(T, im.ranges, im.tile_cursor, stream);
+      if (n_touched) GSR_CUDA(cudaMemsetAsync(n_touched, 0, sizeof(int) * (size_t)P, stream));
+    }
+    if (int rc = alloc_binning(R)) return rc;
+    if (int rc = run_tail(R)) return rc;
+  }
   stage_collect(stream);
   return R;
 }
+
 
 int gsr_rasterize_backward(int P, int D, int M, long long R, const float* background, int width, int height,
                            const float* means3D, const float* shs, const float* colors_precomp, const float* out_alpha,
@@ -407,7 +499,10 @@ int gsr_export_state(int P, long long R, int width, int height, const char* geom
   }
   if (R > 0 && binning_buffer && image_buffer && P > 0 && geometry_buffer && (keys || list)) {
     BinningView bl;
-    carve_binning(const_cast<char*>(binning_buffer), R, bl);
+    unsigned long long cap = 0;
+    GSR_CUDA(cudaStreamSynchronize(stream));
+    GSR_CUDA(cudaMemcpy(&cap, binning_buffer, sizeof(cap), cudaMemcpyDeviceToHost));
+    carve_binning(const_cast<char*>(binning_buffer), (long long)cap, bl);
     export_sorted_kernel<<<gx * gy, 256, 0, stream>>>(im.ranges, bl.comp, g.gid, keys, list);
   }
   if (image_buffer) {

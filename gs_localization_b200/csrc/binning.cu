@@ -207,16 +207,32 @@ void launch_scan_tiles(int* tile_diff, uint32_t gx, uint32_t gy, uint2* ranges, 
   count_launch();
 }
 
+// cursors back to the start of each tile's range (re-run of the tail after a speculative launch overflowed)
+__global__ void reset_cursors_kernel(int T, const uint2* __restrict__ ranges, const int* __restrict__ diff, uint32_t gx,
+                                     uint32_t* __restrict__ cursor) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  // empty tiles have range (0,0) but their cursor was the running prefix; they receive no instance, any value works
+  cursor[t] = ranges[t].x;
+  (void)diff, (void)gx;
+}
+void launch_reset_cursors(int T, const uint2* ranges, uint32_t* cursor, cudaStream_t stream) {
+  if (T <= 0) return;
+  reset_cursors_kernel<<<(T + 255) / 256, 256, 0, stream>>>(T, ranges, nullptr, 0, cursor);
+  count_launch();
+}
+
 // ------------------------------------------------------------------ instances -> tile buckets
 // One CTA per preprocess slot segment.  Also zeroes the backward accumulator rows of its slots.
 __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict__ block_vis, const uint2* __restrict__ rects,
                                                       const float* __restrict__ depths, uint32_t* __restrict__ cursor,
                                                       uint64_t* __restrict__ comp, float* __restrict__ grad_acc,
-                                                      uint32_t grid_x, uint32_t capacity) {
+                                                      uint32_t grid_x, uint32_t capacity, unsigned long long* header) {
   __shared__ uint32_t s_end[256];     // CTA-local inclusive prefix of tile counts
   __shared__ uint2 s_rect[256];
   __shared__ uint32_t s_depth[256];
   __shared__ uint32_t s_wsum[8];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && header) *header = capacity;
   const uint32_t cnt = block_vis[blockIdx.x];
   if (cnt == 0) return;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -257,9 +273,10 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict
 }
 
 void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* comp, uint32_t grid_x, uint32_t capacity,
-                    cudaStream_t stream) {
+                    unsigned long long* header, cudaStream_t stream) {
   if (P <= 0) return;
-  scatter_kernel<<<num_pre_blocks(P), 256, 0, stream>>>(g.block_vis, g.rect, g.depths, cursor, comp, g.grad_acc, grid_x, capacity);
+  scatter_kernel<<<num_pre_blocks(P), 256, 0, stream>>>(g.block_vis, g.rect, g.depths, cursor, comp, g.grad_acc, grid_x, capacity,
+                                                       header);
   count_launch();
 }
 

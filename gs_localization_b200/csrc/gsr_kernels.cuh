@@ -60,7 +60,8 @@ void launch_scan_tiles(int* tile_diff, uint32_t gx, uint32_t gy, uint2* ranges, 
                        uint32_t* counters, cudaStream_t stream);
 // (Gaussian, tile) instances -> tile buckets as depth_bits << 32 | slot; also zeroes the slots' backward accumulators
 void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* comp, uint32_t grid_x, uint32_t capacity,
-                    cudaStream_t stream);
+                    unsigned long long* header, cudaStream_t stream);
+void launch_reset_cursors(int T, const uint2* ranges, uint32_t* cursor, cudaStream_t stream);
 // per-tile sort of the buckets on the composite key; writes the sorted slots to point_list
 void launch_tile_sort(int num_tiles, const uint2* ranges, uint64_t* comp, uint32_t* point_list, uint32_t capacity,
                       cudaStream_t stream);
@@ -88,6 +89,7 @@ struct RenderParams {
   float* out_alpha;
   uint32_t* n_contrib;
   int* n_touched;            // may be null
+  uint32_t capacity;         // entries of point_list that exist (speculative launch: ranges may exceed it)
 };
 void launch_render_fwd(const RenderParams& p, cudaStream_t stream);
 

@@ -21,13 +21,15 @@ def _ptr(t: torch.Tensor):
     """Device pointer of a contiguous float/int tensor; None for the reference's empty placeholders."""
     if t is None or t.numel() == 0:
         return None
-    return C.c_void_p(t.data_ptr())
+    return t.data_ptr()
 
 
 def _cf(t: torch.Tensor, dev, dtype=torch.float32):
     """.contiguous().data<float>() of the reference (rasterize_points.cu:96-115)."""
     if t is None or t.numel() == 0:
         return None
+    if t.dtype is dtype and t.is_contiguous() and t.device == dev:   # the hot case: nothing to do
+        return t
     if t.device != dev:
         t = t.to(dev)
     if t.dtype != dtype:
@@ -36,7 +38,42 @@ def _cf(t: torch.Tensor, dev, dtype=torch.float32):
 
 
 def _stream(dev):
-    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+class _DeviceGuard:
+    """torch.cuda.device(dev) only when dev is not already current (the context manager is not free)."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.ctx = None
+
+    def __enter__(self):
+        if torch.cuda.current_device() != (self.dev.index if self.dev.index is not None else torch.cuda.current_device()):
+            self.ctx = torch.cuda.device(self.dev)
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
+# Scratch allocation callbacks (gsr_alloc_fn).  Created once: building a ctypes callback per call is slow.
+# The library calls them synchronously from inside gsr_rasterize_forward on the calling thread.
+import threading
+
+_tls = threading.local()
+
+
+def _make_alloc(name):
+    def alloc(nbytes, _user):
+        t = torch.empty(int(nbytes), dtype=torch.uint8, device=_tls.dev)
+        _tls.bufs[name] = t
+        return t.data_ptr()
+    return _lib.ALLOC_FN(alloc)
+
+
+_ALLOC_GEOM, _ALLOC_BINNING, _ALLOC_IMG = _make_alloc("geom"), _make_alloc("binning"), _make_alloc("img")
 
 
 def _require_cuda(means3D):
@@ -72,18 +109,10 @@ def _forward_impl(background, means3D, colors, opacity, scales, rotations, scale
             _cf(rotations, dev), _cf(cov3D_precomp, dev), _cf(viewmatrix, dev), _cf(projmatrix, dev), _cf(campos, dev)]
     bg, m3, shc, col, opa, sc, rot, cov, vm, pm, cp = keep
     bufs = {}
-
-    def make_alloc(name):
-        def alloc(nbytes, _user):
-            t = torch.empty(int(nbytes), **byte)
-            bufs[name] = t
-            return t.data_ptr()
-        return _lib.ALLOC_FN(alloc)
-
-    cbs = [make_alloc("geom"), make_alloc("binning"), make_alloc("img")]
-    with torch.cuda.device(dev):
+    _tls.dev, _tls.bufs = dev, bufs
+    with _DeviceGuard(dev):
         R = lib.gsr_rasterize_forward(
-            cbs[0], cbs[1], cbs[2], None, P, int(degree), M,
+            _ALLOC_GEOM, _ALLOC_BINNING, _ALLOC_IMG, None, P, int(degree), M,
             _ptr(bg), W, H, _ptr(m3), _ptr(shc), _ptr(col), _ptr(opa),
             _ptr(sc), float(scale_modifier), _ptr(rot), _ptr(cov),
             _ptr(vm), _ptr(pm), _ptr(cp), float(tan_fovx), float(tan_fovy), int(bool(prefiltered)),
@@ -136,7 +165,7 @@ def _backward_impl(background, means3D, radii, colors, scales, rotations, scale_
             _cf(dL_dout_depth, dev), _cf(dL_dout_alpha, dev)]
     bg, m3, shc, col, alp, sc, rot, cov, vm, pm, praw, cp, rad, gC, gD, gA = keep
     if P > 0:
-        with torch.cuda.device(dev):
+        with _DeviceGuard(dev):
             rc = lib.gsr_rasterize_backward(
                 P, int(degree), M, int(R), _ptr(bg), W, H, _ptr(m3), _ptr(shc), _ptr(col), _ptr(alp),
                 _ptr(sc), float(scale_modifier), _ptr(rot), _ptr(cov), _ptr(vm), _ptr(pm), _ptr(praw), _ptr(cp),
@@ -169,8 +198,8 @@ def mark_visible(means3D, viewmatrix, projmatrix):
     present = torch.zeros(P, dtype=torch.bool, device=dev)
     if P != 0:
         m3, vm, pm = _cf(means3D, dev), _cf(viewmatrix, dev), _cf(projmatrix, dev)
-        with torch.cuda.device(dev):
-            _lib.check(lib.gsr_mark_visible(P, _ptr(m3), _ptr(vm), _ptr(pm), C.c_void_p(present.data_ptr()), _stream(dev)),
+        with _DeviceGuard(dev):
+            _lib.check(lib.gsr_mark_visible(P, _ptr(m3), _ptr(vm), _ptr(pm), present.data_ptr(), _stream(dev)),
                        "gsr_mark_visible")
     return present
 
