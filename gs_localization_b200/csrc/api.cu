@@ -470,13 +470,13 @@ __global__ void export_geometry_kernel(GeometryView g, float* depths, float* mea
   }
 }
 // the reference's sorted arrays: keys = tile << 32 | depth bits, point_list = Gaussian ids
-__global__ void export_sorted_kernel(const uint2* ranges, const uint64_t* comp, const uint32_t* gid, uint64_t* keys,
-                                     uint32_t* list) {
+__global__ void export_sorted_kernel(const uint2* ranges, const uint32_t* point_list, const float* depths, const uint32_t* gid,
+                                     uint64_t* keys, uint32_t* list) {
   const uint2 rg = ranges[blockIdx.x];
   for (uint32_t i = rg.x + threadIdx.x; i < rg.y; i += blockDim.x) {
-    const uint64_t c = comp[i];
-    if (keys) keys[i] = ((uint64_t)blockIdx.x << 32) | (c >> 32);
-    if (list) list[i] = gid[(uint32_t)c];
+    const uint32_t slot = point_list[i];
+    if (keys) keys[i] = ((uint64_t)blockIdx.x << 32) | __float_as_uint(depths[slot]);
+    if (list) list[i] = gid[slot];
   }
 }
 }  // namespace
@@ -503,7 +503,7 @@ int gsr_export_state(int P, long long R, int width, int height, const char* geom
     GSR_CUDA(cudaStreamSynchronize(stream));
     GSR_CUDA(cudaMemcpy(&cap, binning_buffer, sizeof(cap), cudaMemcpyDeviceToHost));
     carve_binning(const_cast<char*>(binning_buffer), (long long)cap, bl);
-    export_sorted_kernel<<<gx * gy, 256, 0, stream>>>(im.ranges, bl.comp, g.gid, keys, list);
+    export_sorted_kernel<<<gx * gy, 256, 0, stream>>>(im.ranges, bl.point_list, g.depths, g.gid, keys, list);
   }
   if (image_buffer) {
     if (ranges) GSR_CUDA(cudaMemcpyAsync(ranges, im.ranges, sizeof(uint2) * (size_t)gx * gy, cudaMemcpyDeviceToDevice, stream));

@@ -284,27 +284,148 @@ void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* co
 constexpr int TS_THREADS = 256;
 constexpr uint32_t TS_SMEM_KEYS = 4096;   // 32 KB of composite keys in shared memory
 
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int mask) {
+  const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, mask);
+  const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), mask);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// Register-resident bitonic sort of N2 = 256*E keys held E per thread (thread t owns indices [tE, tE+E)).
+// Same network as bitonic_sort_block (mirror step, then half-cleaners, always ascending), but a
+// compare-exchange whose partner lives in the same thread is a register swap, one whose partner lives in
+// the same warp is two shuffles, and only the few steps that cross warps go through shared memory.
+// For N2 = 1024 that is 6 shared-memory steps out of 55.  Padding is real +inf keys in registers.
+// The k / j loops stay rolled (the fully unrolled network is ~30k instructions and thrashes the
+// instruction cache); only the per-thread element loops are unrolled.
+template <int E, int J>
+__device__ __forceinline__ void cx_in_thread(uint64_t (&v)[E]) {   // partner r ^ J, J < E
+#pragma unroll
+  for (int r = 0; r < E; r++) {
+    if ((r & J) == 0 && (r | J) < E) {
+      const uint64_t a = v[r], b = v[r | J];
+      v[r] = min(a, b);
+      v[r | J] = max(a, b);
+    }
+  }
+}
+template <int E, int K>
+__device__ __forceinline__ void mirror_in_thread(uint64_t (&v)[E]) {   // partner r ^ (K-1), K <= E
+#pragma unroll
+  for (int r = 0; r < E; r++) {
+    const int rp = r ^ (K - 1);
+    if (r < rp && rp < E) {
+      const uint64_t a = v[r], b = v[rp];
+      v[r] = min(a, b);
+      v[rp] = max(a, b);
+    }
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void bitonic_sort_regs(uint64_t (&v)[E], uint64_t* s) {
+  constexpr int N2 = TS_THREADS * E;
+  const uint32_t t = threadIdx.x;
+  for (int k = 2; k <= N2; k <<= 1) {
+    // ---- mirror step: i <-> i ^ (k-1)
+    if (k <= E) {
+      switch (k) {
+        case 2: mirror_in_thread<E, 2>(v); break;
+        case 4: mirror_in_thread<E, 4>(v); break;
+        case 8: mirror_in_thread<E, 8>(v); break;
+        default: mirror_in_thread<E, 16>(v); break;
+      }
+    } else if (k <= 32 * E) {
+      const int m = k / E - 1;
+      const bool lower = (t & (k / (2 * E))) == 0;
+      uint64_t w[E];
+#pragma unroll
+      for (int r = 0; r < E; r++) w[r] = v[r];
+#pragma unroll
+      for (int r = 0; r < E; r++) {
+        const uint64_t pv = shfl_xor_u64(w[E - 1 - r], m);
+        v[r] = lower ? min(w[r], pv) : max(w[r], pv);
+      }
+    } else {
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < E; r++) s[t * E + r] = v[r];
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < E; r++) {
+        const uint32_t i = t * E + r, ip = i ^ (uint32_t)(k - 1);
+        const uint64_t pv = s[ip];
+        v[r] = (i < ip) ? min(v[r], pv) : max(v[r], pv);
+      }
+    }
+    // ---- half-cleaners: i <-> i ^ j
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      if (j < E) {
+        switch (j) {
+          case 1: cx_in_thread<E, 1>(v); break;
+          case 2: cx_in_thread<E, 2>(v); break;
+          case 4: cx_in_thread<E, 4>(v); break;
+          default: cx_in_thread<E, 8>(v); break;
+        }
+      } else if (j < 32 * E) {
+        const int m = j / E;
+        const bool lower = (t & m) == 0;
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+          const uint64_t pv = shfl_xor_u64(v[r], m);
+          v[r] = lower ? min(v[r], pv) : max(v[r], pv);
+        }
+      } else {
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < E; r++) s[t * E + r] = v[r];
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < E; r++) {
+          const uint32_t i = t * E + r, ip = i ^ (uint32_t)j;
+          const uint64_t pv = s[ip];
+          v[r] = (i < ip) ? min(v[r], pv) : max(v[r], pv);
+        }
+      }
+    }
+  }
+}
+
+template <int E>
+__device__ __forceinline__ void tile_sort_small(const uint64_t* __restrict__ comp, uint32_t* __restrict__ point_list,
+                                                uint32_t start, uint32_t n, uint64_t* s) {
+  uint64_t v[E];
+  const uint32_t base = threadIdx.x * E;
+#pragma unroll
+  for (int r = 0; r < E; r++) v[r] = (base + r < n) ? __ldg(comp + start + base + r) : ~0ull;
+  bitonic_sort_regs<E>(v, s);
+#pragma unroll
+  for (int r = 0; r < E; r++)
+    if (base + r < n) point_list[start + base + r] = (uint32_t)v[r];
+}
+
 __global__ void __launch_bounds__(TS_THREADS) tile_sort_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ comp,
                                                                uint32_t* __restrict__ point_list, uint32_t capacity) {
   __shared__ uint64_t s_keys[TS_SMEM_KEYS];
   const uint2 rg = ranges[blockIdx.x];
-  const uint32_t start = rg.x, end = min(rg.y, capacity);
+  const uint32_t start = min(rg.x, capacity), end = min(rg.y, capacity);
   if (end <= start) return;
   const uint32_t n = end - start;
-  uint32_t n2 = 1;
-  while (n2 < n) n2 <<= 1;
-  if (n <= TS_SMEM_KEYS) {
-    for (uint32_t i = threadIdx.x; i < n; i += TS_THREADS) s_keys[i] = comp[start + i];
-    __syncthreads();
-    if (n > 1) bitonic_sort_block<uint64_t>(s_keys, n, n2);
-    for (uint32_t i = threadIdx.x; i < n; i += TS_THREADS) {
-      const uint64_t k = s_keys[i];
-      comp[start + i] = k;
-      point_list[start + i] = (uint32_t)k;
-    }
+  if (n == 1) {
+    if (threadIdx.x == 0) point_list[start] = (uint32_t)comp[start];
+  } else if (n <= 1 * TS_THREADS) {
+    tile_sort_small<1>(comp, point_list, start, n, s_keys);
+  } else if (n <= 2 * TS_THREADS) {
+    tile_sort_small<2>(comp, point_list, start, n, s_keys);
+  } else if (n <= 4 * TS_THREADS) {
+    tile_sort_small<4>(comp, point_list, start, n, s_keys);
+  } else if (n <= 8 * TS_THREADS) {
+    tile_sort_small<8>(comp, point_list, start, n, s_keys);
+  } else if (n <= 16 * TS_THREADS) {
+    tile_sort_small<16>(comp, point_list, start, n, s_keys);
   } else {
-    uint64_t* a = comp + start;      // large bucket: same network straight on global memory (L2 resident)
-    __syncthreads();
+    uint32_t n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    uint64_t* a = comp + start;      // large bucket: the generic network straight on global memory (L2 resident)
     bitonic_sort_block<uint64_t>(a, n, n2);
     for (uint32_t i = threadIdx.x; i < n; i += TS_THREADS) point_list[start + i] = (uint32_t)a[i];
   }
