@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline", choices=list(syn.CONFIGS))
+    ap.add_argument("--queries", type=int, default=6, help="pose-refinement queries per rank for the queries/s figure (ours only)")
+    ap.add_argument("--query-iters", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-split", action="store_true")
     return ap.parse_args()
@@ -270,8 +272,35 @@ def run_gpu_arm(args, rank, world, local_rank):
         workload_stats = dict(P=cfg["P"], Pv=Pv, R=int(Rq), N=W * H, T=int(rng.shape[0]), n_contrib_sum=n_contrib_sum,
                               mean_n_contrib=n_contrib_sum / (W * H))
         roofline = make_roofline(split, workload_stats, cfg)
+    # ---- localized queries/s (second half of BASELINE's metric): full pose refinements through the pose API,
+    # queries sharded over ranks with no collective; fixed iteration count, convergence break disabled
+    queries_s = None
+    if args.impl == "ours" and args.queries > 0:
+        from gs_localization_b200 import localization as loc
+        qs = []
+        for q in range(args.queries + 1):   # first one is a warm-up
+            gq = rank * args.queries + q
+            gt = syn.make_camera(cfg, 10_000 + gq)
+            v, p_, _, c = gt.matrices(device)
+            with torch.no_grad():
+                target = arm.c_forward(m, bg, v, p_, c, gt)[1].clone()
+            qs.append((loc.PoseCamera(gt.perturbed(syn.initial_perturbation(gq)), device), target, gt))
+        loc.refine_pose(m, qs[0][0], qs[0][1], iters=args.query_iters)
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        t0 = time.perf_counter()
+        errs = []
+        for cam_q, target, gt in qs[1:]:
+            w2c, _ = loc.refine_pose(m, cam_q, target, iters=args.query_iters)
+            errs.append(w2c)
+        torch.cuda.synchronize()
+        queries_s = time.perf_counter() - t0
+        if world > 1:
+            torch.distributed.barrier()
+        stats["final_pose_err"] = [syn.pose_error(w.cpu(), q[2].w2c) for w, q in zip(errs, qs[1:])]
     stats.update(ms_total=ms_total, clocks=clocks, launches=launches, e2e_s=e2e_s, h2d=h2d, d2h=d2h, split=split,
-                 roofline=roofline, workload_stats=workload_stats, mean_R=sum(Rs) / max(1, len(Rs)))
+                 roofline=roofline, workload_stats=workload_stats, mean_R=sum(Rs) / max(1, len(Rs)), queries_s=queries_s)
     return stats
 
 
@@ -374,11 +403,11 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     st = run_gpu_arm(args, rank, world, local_rank)
 
-    ms_total, e2e_s = st["ms_total"], st["e2e_s"]
+    ms_total, e2e_s, queries_s = st["ms_total"], st["e2e_s"], st["queries_s"] or 0.0
     if world > 1:
-        t = torch.tensor([ms_total, e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
+        t = torch.tensor([ms_total, e2e_s, queries_s], device=f"cuda:{local_rank}", dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms_total, e2e_s = float(t[0]), float(t[1])
+        ms_total, e2e_s, queries_s = float(t[0]), float(t[1]), float(t[2])
     if rank == 0:
         value = world * args.steps / (ms_total * 1e-3)
         line = dict(base, value=round(value, 3), ms_per_step=round(ms_total / args.steps, 4), clocks=st["clocks"],
@@ -388,6 +417,13 @@ def main():
         if args.impl == "reference":
             line["impl"] = "reference"
             line["config"]["reference"] = "unmodified reference CUDA rasterizer built for sm_100a (oracle/_ref) on this GPU"
+        if queries_s > 0:
+            errs = st.get("final_pose_err") or []
+            line["localization"] = {
+                "queries_per_s": round(world * args.queries / queries_s, 3), "iters_per_query": args.query_iters,
+                "queries": world * args.queries, "workload": f"{args.workload} map, pose-only refinement (Adam on 6 pose deltas)",
+                "median_final_err_m_deg": [round(sorted(e[0] for e in errs)[len(errs) // 2], 5),
+                                           round(sorted(e[1] for e in errs)[len(errs) // 2], 4)] if errs else None}
         if st["roofline"]:
             line["roofline"] = st["roofline"]
         if st["split"]:

@@ -89,8 +89,8 @@ def render_pose(gmap: syn.GaussianMap, cam: PoseCamera, bg: torch.Tensor):
         image_height=cam.H, image_width=cam.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=bg, scale_modifier=1.0,
         viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform, projmatrix_raw=cam.projection_matrix,
         sh_degree=gmap.sh_degree, campos=cam.camera_center, prefiltered=False, debug=False)
-    means2D = torch.zeros_like(gmap.means3D)
-    return GaussianRasterizer(rs)(means3D=gmap.means3D, means2D=means2D, opacities=gmap.opacities, shs=gmap.shs,
+    # means2D is only a gradient sink in the reference API (never read by the kernels): no need to allocate one here
+    return GaussianRasterizer(rs)(means3D=gmap.means3D, means2D=gmap.means3D, opacities=gmap.opacities, shs=gmap.shs,
                                   scales=gmap.scales, rotations=gmap.rotations, theta=cam.cam_rot_delta,
                                   rho=cam.cam_trans_delta)
 
