@@ -527,6 +527,25 @@ int gsr_stage_times(double* total_ms, unsigned long long* calls, int n) {
   return ST_COUNT;
 }
 
+int gsr_l1_loss_grad(const float* image, const float* target, float* dL_dimage, long long n, float weight, float* loss_accum,
+                     void* stream_) {
+  if (n < 0 || (n > 0 && (!image || !target || !dL_dimage || !loss_accum))) return fail(GSR_ERR_INVALID_ARGUMENT, "bad arguments");
+  launch_l1_loss_grad(image, target, dL_dimage, (size_t)n, weight, loss_accum, (cudaStream_t)stream_);
+  GSR_STAGE("l1_loss_grad", 0, (cudaStream_t)stream_);
+  return GSR_OK;
+}
+
+int gsr_pose_adam_step(const float* dL_dtau, float* adam_m, float* adam_v, float* step_count, float lr_trans, float lr_rot,
+                       float* w2c, const float* projmatrix_raw, float* viewmatrix, float* projmatrix, float* campos,
+                       float* tau_norm, void* stream_) {
+  if (!dL_dtau || !adam_m || !adam_v || !step_count || !w2c || !projmatrix_raw || !viewmatrix || !projmatrix || !campos)
+    return fail(GSR_ERR_INVALID_ARGUMENT, "null pointer");
+  launch_pose_adam_step(dL_dtau, adam_m, adam_v, step_count, lr_trans, lr_rot, w2c, projmatrix_raw, viewmatrix, projmatrix, campos,
+                        tau_norm, (cudaStream_t)stream_);
+  GSR_STAGE("pose_adam_step", 0, (cudaStream_t)stream_);
+  return GSR_OK;
+}
+
 size_t gsr_sort_temp_bytes(long long n) { return sort_temp_bytes(n, SORT_MAX_PASSES); }
 
 int gsr_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in, uint32_t* vals_out, uint64_t* keys_tmp,

@@ -141,4 +141,11 @@ struct PreBwdParams {
 // one CTA per preprocess slot segment, threads beyond the segment's visible count idle
 void launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream);
 
+// ---- pose-refinement glue (pose_step.cu)
+void launch_l1_loss_grad(const float* image, const float* target, float* dL_dimage, size_t n, float weight, float* loss_out,
+                         cudaStream_t stream);
+void launch_pose_adam_step(const float* dL_dtau, float* adam_m, float* adam_v, float* step_count, float lr_trans, float lr_rot,
+                           float* w2c, const float* raw, float* viewmatrix, float* projmatrix, float* campos, float* tau_norm,
+                           cudaStream_t stream);
+
 }  // namespace gsr

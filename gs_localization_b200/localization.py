@@ -113,3 +113,59 @@ def refine_pose(gmap: syn.GaussianMap, cam: PoseCamera, target: torch.Tensor, it
         if cam.update_pose() and converge:
             break
     return cam.w2c, loss
+
+
+def refine_pose_fused(gmap: syn.GaussianMap, cam: PoseCamera, target: torch.Tensor, iters: int = 50, lr: float = 1e-3,
+                      lr_rot: float | None = None, target_depth: torch.Tensor | None = None, depth_weight: float = 0.01,
+                      converge_threshold: float | None = None):
+    """Same loop as `refine_pose`, without framework ops on the per-iteration path: the rasterizer's C ABI
+    forward, a fused L1 loss+gradient kernel, the pose-only backward (SE(3) chain rule fused, no per-Gaussian
+    gradients written) and one single-thread kernel doing Adam + SE3_exp + the new view constants.  The only
+    host wait per iteration is the rasterizer's num_rendered poll; everything else is queued ahead."""
+    import ctypes as C
+
+    from . import _lib
+    from .diff_gaussian_rasterization import _C
+
+    lib = _lib.load()
+    dev = cam.device
+    H, W = cam.H, cam.W
+    f32 = dict(dtype=torch.float32, device=dev)
+    w2c = cam.w2c.contiguous().clone()
+    view = cam.world_view_transform.contiguous().clone()
+    proj = cam.full_proj_transform.contiguous().clone()
+    campos = cam.camera_center.contiguous().clone()
+    raw = cam.projection_matrix.contiguous()
+    adam_m, adam_v, step, tau_norm = torch.zeros(6, **f32), torch.zeros(6, **f32), torch.zeros(1, **f32), torch.zeros(1, **f32)
+    loss = torch.zeros(1, **f32)
+    dL_dpix = torch.empty(3, H, W, **f32)
+    dL_ddepth = torch.zeros(1, H, W, **f32)
+    zeros_a = torch.zeros(1, H, W, **f32)
+    bg = torch.zeros(3, **f32)
+    e = torch.Tensor([])
+    needs = dict(means3D=False, means2D=False, sh=False, colors=False, opacity=False, scales=False, rotations=False, cov3D=False)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    p = lambda t: t.data_ptr()
+    lr_rot = lr if lr_rot is None else lr_rot
+    target = target.contiguous()
+    for it in range(iters):
+        fwd = _C._forward_impl(bg, gmap.means3D, e, gmap.opacities, gmap.scales, gmap.rotations, 1.0, e, view.view(4, 4),
+                               proj.view(4, 4), cam.tanfovx, cam.tanfovy, H, W, gmap.shs, gmap.sh_degree, campos, False, False)
+        R, color, depth, alpha, radii, geom, binning, img, _ = fwd
+        loss.zero_()
+        _lib.check(lib.gsr_l1_loss_grad(p(color), p(target), p(dL_dpix), 3 * H * W, 1.0, p(loss), stream), "gsr_l1_loss_grad")
+        gD = zeros_a
+        if target_depth is not None:
+            _lib.check(lib.gsr_l1_loss_grad(p(depth), p(target_depth), p(dL_ddepth), H * W, depth_weight, p(loss), stream),
+                       "gsr_l1_loss_grad")
+            gD = dL_ddepth
+        _, dL_dtau = _C._backward_impl(bg, gmap.means3D, radii, e, gmap.scales, gmap.rotations, 1.0, e, view.view(4, 4),
+                                       proj.view(4, 4), cam.tanfovx, cam.tanfovy, dL_dpix, gD, zeros_a, gmap.shs,
+                                       gmap.sh_degree, campos, geom, R, binning, img, alpha, False, projmatrix_raw=raw,
+                                       want_pose=True, needs=needs)
+        _lib.check(lib.gsr_pose_adam_step(p(dL_dtau), p(adam_m), p(adam_v), p(step), float(lr), float(lr_rot), p(w2c), p(raw),
+                                          p(view), p(proj), p(campos), p(tau_norm), stream), "gsr_pose_adam_step")
+        if converge_threshold is not None and float(tau_norm) < converge_threshold:   # the reference's early break (host sync)
+            break
+    cam.w2c = w2c.view(4, 4)
+    return cam.w2c, loss

@@ -148,6 +148,26 @@ GSR_API int gsr_export_state(
 GSR_API void gsr_stage_timing(int enable);
 GSR_API int gsr_stage_times(double* total_ms, unsigned long long* calls, int n);
 
+/*
+ * Device-side glue of LoGS' pose-refinement loop (gradient_decent,
+ * gs_localization/pipelines/7scenes_localize_full_dslam.py:66-91), so that an iteration is
+ * forward -> loss -> backward -> pose update with no host round trip and no framework ops.
+ *
+ * gsr_l1_loss_grad: tracking loss with all-ones masks (tools/descent_utils.py:85-123) and its
+ *   gradient in one pass: *loss_accum += weight * mean|image - target| ; dL_dimage = weight * sign(.)/n.
+ *   loss_accum must be zeroed by the caller.
+ * gsr_pose_adam_step: torch.optim.Adam (betas 0.9/0.999, eps 1e-8, per-group lr) on the six pose deltas
+ *   given dL_dtau = [d/drho, d/dtheta]; then T_w2c <- SE3_exp(tau) T_w2c (tools/pose_utils.py:54-122) and
+ *   the per-view constants viewmatrix = T_w2c^T, projmatrix = viewmatrix @ projmatrix_raw, campos
+ *   (tools/camera_utils.py:144-158).  adam_m[6], adam_v[6], step_count[1], w2c[16] (row-major) are state
+ *   updated in place; tau_norm[1] (optional) receives |tau| for the caller's convergence test.
+ */
+GSR_API int gsr_l1_loss_grad(const float* image, const float* target, float* dL_dimage, long long n, float weight,
+                             float* loss_accum, void* stream);
+GSR_API int gsr_pose_adam_step(const float* dL_dtau, float* adam_m, float* adam_v, float* step_count, float lr_trans,
+                               float lr_rot, float* w2c, const float* projmatrix_raw, float* viewmatrix, float* projmatrix,
+                               float* campos, float* tau_norm, void* stream);
+
 /* Stand-alone stable LSD radix sort of (u64 key, u32 value) pairs on bits [0, end_bit) —
  * the hand-written onesweep that replaces cub::DeviceRadixSort::SortPairs
  * (rasterizer_impl.cu:304-309).  temp must hold gsr_sort_temp_bytes(n) bytes. */

@@ -108,3 +108,20 @@ def test_pose_api_grad_flow_matches_plain_api():
     for a, b in zip(outs[0][1], outs[1][1]):
         assert util.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
     assert util.rel_err(outs[0][2].cpu().numpy(), outs[1][2].cpu().numpy()) < 1e-5
+
+
+def test_fused_refinement_matches_framework_loop():
+    """refine_pose_fused (C-ABI kernels only) follows the same trajectory as the torch.optim.Adam / autograd loop."""
+    cfg = dict(P=20_000, W=160, H=128, deg=2, f=120.0, box=1.0, sigma0=0.06)
+    m = syn.make_map(cfg["P"], cfg["deg"], cfg["sigma0"], 1.0, seed=0).to(DEV)
+    gt = syn.make_camera(cfg, 2)
+    target = loc.render_pose(m, loc.PoseCamera(gt, DEV), torch.zeros(3, device=DEV))[0].detach()
+    start = gt.perturbed(syn.initial_perturbation(2, trans_m=0.02, rot_deg=1.0))
+    a, b = loc.PoseCamera(start, DEV), loc.PoseCamera(start, DEV)
+    w_ref, loss_ref = loc.refine_pose(m, a, target, iters=30, lr=1e-3)
+    w_fused, loss_fused = loc.refine_pose_fused(m, b, target, iters=30, lr=1e-3)
+    dt, dr = syn.pose_error(w_ref.cpu(), w_fused.cpu())
+    assert dt <= 1e-4 and dr <= 0.005, (dt, dr)
+    assert abs(float(loss_ref) - float(loss_fused)) <= 1e-4
+    e0, e1 = syn.pose_error(start.w2c, gt.w2c), syn.pose_error(w_fused.cpu(), gt.w2c)
+    assert e1[0] < 0.5 * e0[0] and e1[1] < 0.5 * e0[1], (e0, e1)
