@@ -45,14 +45,33 @@ int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail(GSR_ERR_CUDA, "stage %s: %s", name, cudaGetErrorString(e__)); \
   } while (0)
 
-// [header: capacity (u64), 128 B][point_list u32[cap]][comp u64[cap]] — the backward only needs point_list, whose
-// offset does not depend on the capacity the forward happened to allocate (speculative launches over-allocate)
-char* carve_binning(char* base, long long cap, BinningView& b) {
+// Binning buffer: [header 128 B][point_list u32[cap]] then, depending on the path,
+//   tile-local sort : [comp u64[cap]]
+//   global radix    : [vals u32[cap]][keys u64[cap]][keys u64[cap]][sort temp]
+// The backward only needs point_list, whose offset depends on neither the path nor the capacity the
+// forward happened to allocate (speculative launches over-allocate).
+int sort_end_bit(int W, int H) {
+  const uint32_t gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
+  return 32 + (int)get_higher_msb(gx * gy);   // reference rasterizer_impl.cu:301,309
+}
+char* carve_binning(char* base, long long cap, BinningView& b, bool global_path = false, int W = 0, int H = 0) {
   char* p = base + 128;
   carve(p, b.point_list, (size_t)cap);
-  carve(p, b.comp, (size_t)cap);
+  if (!global_path) {
+    carve(p, b.comp, (size_t)cap);
+    b.keys[0] = b.keys[1] = nullptr, b.vals_other = nullptr, b.sort_temp = nullptr;
+  } else {
+    carve(p, b.vals_other, (size_t)cap);
+    carve(p, b.keys[0], (size_t)cap);
+    carve(p, b.keys[1], (size_t)cap);
+    p = (char*)align_up((size_t)p, 128);
+    b.sort_temp = p;
+    p += sort_temp_bytes(cap, sort_passes(sort_end_bit(W, H)));
+    b.comp = nullptr;
+  }
   return p;
 }
+constexpr long long LOCAL_SORT_MAX = 4096;   // longest tile list the shared-memory tile sort handles (binning.cu TS_SMEM_KEYS)
 
 // ---- optional per-stage device timing (bench.py's stage split; off on the hot path)
 enum Stage { ST_PREPROCESS, ST_DUPLICATE, ST_SORT, ST_RANGES, ST_RENDER, ST_BWD_RENDER, ST_BWD_PREPROCESS, ST_COUNT };
@@ -140,24 +159,26 @@ Mailbox* pinned_mailbox() {
 // change num_rendered, and a caller cycling through a handful of views is covered by the maximum.
 struct CountHistory {
   int P = -1, W = 0, H = 0, n = 0, pos = 0;
-  long long R[16] = {};
+  long long R[16] = {}, longest[16] = {};
 };
 thread_local CountHistory t_hist[4];
-long long capacity_guess(int P, int W, int H) {
+void capacity_guess(int P, int W, int H, long long& cap, long long& longest) {
   static const bool disabled = getenv("GSR_NO_SPECULATION") != nullptr;   // A/B switch for measurements
-  if (disabled) return 0;
+  cap = longest = 0;
+  if (disabled) return;
   for (auto& h : t_hist)
     if (h.P == P && h.W == W && h.H == H && h.n > 0) {
-      long long m = 0;
-      for (int i = 0; i < h.n; i++) m = std::max(m, h.R[i]);
-      return m + m / 4 + 4096;
+      long long m = 0, l = 0;
+      for (int i = 0; i < h.n; i++) m = std::max(m, h.R[i]), l = std::max(l, h.longest[i]);
+      cap = m + m / 4 + 4096;
+      longest = l + l / 4;
+      return;
     }
-  return 0;
 }
-void remember_count(int P, int W, int H, long long R) {
+void remember_count(int P, int W, int H, long long R, long long longest) {
   for (auto& h : t_hist)
     if (h.P == P && h.W == W && h.H == H) {
-      h.R[h.pos] = R;
+      h.R[h.pos] = R, h.longest[h.pos] = longest;
       h.pos = (h.pos + 1) % 16;
       h.n = std::min(h.n + 1, 16);
       return;
@@ -165,7 +186,7 @@ void remember_count(int P, int W, int H, long long R) {
   static thread_local int next = 0;
   CountHistory& h = t_hist[next];
   h = CountHistory{};
-  h.P = P, h.W = W, h.H = H, h.n = 1, h.pos = 1, h.R[0] = R;
+  h.P = P, h.W = W, h.H = H, h.n = 1, h.pos = 1, h.R[0] = R, h.longest[0] = longest;
   next = (next + 1) % 4;
 }
 }  // namespace
@@ -187,9 +208,13 @@ size_t gsr_image_bytes(int width, int height) {
   return (size_t)end + 128;
 }
 size_t gsr_binning_bytes(long long num_rendered, int width, int height) {
-  (void)width, (void)height;
+  BinningView b;   // worst case: the global radix-sort layout
+  char* end = carve_binning(nullptr, num_rendered, b, true, width, height);
+  return (size_t)end + 128;
+}
+static size_t binning_bytes_for(long long cap, bool global_path, int width, int height) {
   BinningView b;
-  char* end = carve_binning(nullptr, num_rendered, b);
+  char* end = carve_binning(nullptr, cap, b, global_path, width, height);
   return (size_t)end + 128;
 }
 
@@ -258,7 +283,8 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     box = pinned_mailbox();
     if (!box) return fail(GSR_ERR_CUDA, "cudaHostAlloc failed");
     *reinterpret_cast<volatile uint32_t*>(box->value) = 0xffffffffu;   // sentinel: num_rendered is always < 2^31
-    GSR_CUDA(cudaMemcpyAsync(box->value, g.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    GSR_CUDA(cudaMemcpyAsync(box->value + 4, g.counters + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));   // longest tile list
+    GSR_CUDA(cudaMemcpyAsync(box->value, g.counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));       // num_rendered (last: it is the flag)
     GSR_CUDA(cudaEventRecord(box->ready, stream));
   } else {
     GSR_CUDA(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)T, stream));
@@ -271,8 +297,8 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
   // working.  If the guess was too small (kernels clamp to the capacity, nothing overruns) the tail is
   // simply re-run with the exact size.  First call / no history: the reference's order.
   unsigned long long* bin_header = nullptr;
-  auto run_tail = [&](long long capacity) -> int {
-    if (capacity > 0) {
+  auto run_tail = [&](long long capacity, bool global_path) -> int {
+    if (capacity > 0 && !global_path) {
       {
         StageScope ts(ST_DUPLICATE, stream);
         launch_scatter(P, g, im.tile_cursor, bl.comp, gx, (uint32_t)capacity, bin_header, stream);
@@ -283,6 +309,30 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
         launch_tile_sort(T, im.ranges, bl.comp, bl.point_list, (uint32_t)capacity, stream);
       }
       GSR_STAGE("tile_sort", debug, stream);
+    } else if (capacity > 0) {
+      // tile lists too long for the shared-memory sort: the reference's global formulation — instances in
+      // Gaussian order with tile|depth keys, stable onesweep radix sort over the low 32+bit bits.  The last
+      // pass is steered into point_list; the tile ranges are already known from scan_tiles.
+      const int end_bit = sort_end_bit(width, height);
+      const int passes = sort_passes(end_bit);
+      uint64_t* keys[2] = {bl.keys[0], bl.keys[1]};
+      uint32_t* vals[2];
+      vals[passes & 1] = bl.point_list;
+      vals[(passes & 1) ^ 1] = bl.vals_other;
+      SortTemp st;
+      carve_sort_temp(bl.sort_temp, capacity, passes, st);
+      {
+        StageScope ts(ST_DUPLICATE, stream);
+        sort_temp_reset(bl.sort_temp, capacity, passes, stream);
+        launch_emit_ordered(P, g, keys[0], vals[0], gx, (uint32_t)capacity, bin_header, stream);
+      }
+      GSR_STAGE("emit_ordered", debug, stream);
+      {
+        StageScope ts(ST_SORT, stream);
+        launch_sort_histogram(keys[0], g.counters + 1, capacity, end_bit, st.hist, stream);
+        launch_onesweep(keys, vals, g.counters + 1, capacity, end_bit, st, stream);
+      }
+      GSR_STAGE("radix_sort", debug, stream);
     }
     RenderParams rp{};
     rp.W = width, rp.H = height, rp.grid_x = gx, rp.grid_y = gy;
@@ -298,21 +348,24 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     GSR_STAGE("render", debug, stream);
     return GSR_OK;
   };
-  auto alloc_binning = [&](long long cap) -> int {
-    char* bin_base = binning_alloc(gsr_binning_bytes(cap, width, height), user);
+  auto alloc_binning = [&](long long cap, bool global_path) -> int {
+    char* bin_base = binning_alloc(binning_bytes_for(cap, global_path, width, height), user);
     if (!bin_base) return fail(GSR_ERR_ALLOC, "binning_alloc returned NULL");
-    carve_binning(bin_base, cap, bl);
+    carve_binning(bin_base, cap, bl, global_path, width, height);
     bin_header = reinterpret_cast<unsigned long long*>(bin_base);   // capacity is recorded there by the scatter kernel
     return GSR_OK;
   };
 
-  long long guess = (P > 0 && !debug && !g_timer.enabled) ? capacity_guess(P, width, height) : 0;
-  bool speculated = false;
+  long long guess = 0, guess_longest = 0;
+  if (P > 0 && !debug && !g_timer.enabled) capacity_guess(P, width, height, guess, guess_longest);
+  bool speculated = false, spec_global = guess_longest > LOCAL_SORT_MAX;
   if (guess > 0) {
-    if (int rc = alloc_binning(guess)) return rc;
-    if (int rc = run_tail(guess)) return rc;
+    if (guess >= (1ll << 30)) return fail(GSR_ERR_UNSUPPORTED, "more than 2^30 instances");
+    if (int rc = alloc_binning(guess, spec_global)) return rc;
+    if (int rc = run_tail(guess, spec_global)) return rc;
     speculated = true;
   }
+  long long longest = 0;
   if (P > 0) {
     // poll the pinned word the copy engine writes (cheaper than a driver-level wait), with the event as a safety net
     {
@@ -328,8 +381,10 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
       }
       if (*v == 0xffffffffu) GSR_CUDA(cudaEventSynchronize(box->ready));
     }
-    R = (long long)*box->value;
-    remember_count(P, width, height, R);
+    R = (long long)box->value[0];
+    longest = (long long)box->value[4];
+    remember_count(P, width, height, R, longest);
+    if (R >= (1ll << 30)) return fail(GSR_ERR_UNSUPPORTED, "more than 2^30 instances (%lld)", R);
   }
   if (!speculated || R > guess) {
     if (speculated) {
@@ -338,8 +393,9 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
       launch_reset_cursors(T, im.ranges, im.tile_cursor, stream);
       if (n_touched) GSR_CUDA(cudaMemsetAsync(n_touched, 0, sizeof(int) * (size_t)P, stream));
     }
-    if (int rc = alloc_binning(R)) return rc;
-    if (int rc = run_tail(R)) return rc;
+    const bool global_path = longest > LOCAL_SORT_MAX;
+    if (int rc = alloc_binning(R, global_path)) return rc;
+    if (int rc = run_tail(R, global_path)) return rc;
   }
   stage_collect(stream);
   return R;

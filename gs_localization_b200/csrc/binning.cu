@@ -224,10 +224,15 @@ void launch_reset_cursors(int T, const uint2* ranges, uint32_t* cursor, cudaStre
 
 // ------------------------------------------------------------------ instances -> tile buckets
 // One CTA per preprocess slot segment.  Also zeroes the backward accumulator rows of its slots.
+// ORDERED = false: bucket mode (atomic cursor per tile, composite depth|slot).
+// ORDERED = true : the reference's layout for the global radix sort — instance j of the CTA goes to
+//                  block_off[b] + j (Gaussian order, rows-then-columns), key = tile << 32 | depth bits, value = slot.
+template <bool ORDERED>
 __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict__ block_vis, const uint2* __restrict__ rects,
                                                       const float* __restrict__ depths, uint32_t* __restrict__ cursor,
                                                       uint64_t* __restrict__ comp, float* __restrict__ grad_acc,
-                                                      uint32_t grid_x, uint32_t capacity, unsigned long long* header) {
+                                                      uint32_t grid_x, uint32_t capacity, unsigned long long* header,
+                                                      const uint32_t* __restrict__ block_off, uint32_t* __restrict__ vals) {
   __shared__ uint32_t s_end[256];     // CTA-local inclusive prefix of tile counts
   __shared__ uint2 s_rect[256];
   __shared__ uint32_t s_depth[256];
@@ -267,17 +272,59 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict
     const uint32_t minx = rc.x & 0xffffu, w = (rc.x >> 16) - minx, miny = rc.y & 0xffffu;
     const uint32_t row = within / w, col = within - row * w;
     const uint32_t tile = (miny + row) * grid_x + (minx + col);
-    const uint32_t pos = atomicAdd(cursor + tile, 1u);
-    if (pos < capacity) comp[pos] = ((uint64_t)s_depth[lo] << 32) | (first + lo);
+    if (ORDERED) {
+      const uint32_t pos = __ldg(block_off + blockIdx.x) + j;
+      if (pos < capacity) {
+        comp[pos] = ((uint64_t)tile << 32) | s_depth[lo];
+        vals[pos] = first + lo;
+      }
+    } else {
+      const uint32_t pos = atomicAdd(cursor + tile, 1u);
+      if (pos < capacity) comp[pos] = ((uint64_t)s_depth[lo] << 32) | (first + lo);
+    }
   }
+}
+
+// exclusive scan, in place, of the per-CTA instance counts (one CTA; n = ceil(P/256) values)
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(const uint32_t* __restrict__ a, uint32_t* __restrict__ out, uint32_t n) {
+  __shared__ uint32_t s_warp[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t chunk = (n + 1023) / 1024;
+  const uint32_t i0 = min(n, tid * chunk), i1 = min(n, i0 + chunk);
+  uint32_t sum = 0;
+  for (uint32_t i = i0; i < i1; i++) sum += a[i];
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = s_warp[lane];
+    uint32_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= (uint32_t)o) wi += v; }
+    s_warp[lane] = wi - w;
+  }
+  __syncthreads();
+  uint32_t run = s_warp[warp] + incl - sum;
+  for (uint32_t i = i0; i < i1; i++) { const uint32_t c = a[i]; out[i] = run; run += c; }
 }
 
 void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* comp, uint32_t grid_x, uint32_t capacity,
                     unsigned long long* header, cudaStream_t stream) {
   if (P <= 0) return;
-  scatter_kernel<<<num_pre_blocks(P), 256, 0, stream>>>(g.block_vis, g.rect, g.depths, cursor, comp, g.grad_acc, grid_x, capacity,
-                                                       header);
+  scatter_kernel<false><<<num_pre_blocks(P), 256, 0, stream>>>(g.block_vis, g.rect, g.depths, cursor, comp, g.grad_acc, grid_x,
+                                                              capacity, header, nullptr, nullptr);
   count_launch();
+}
+
+void launch_emit_ordered(int P, const GeometryView& g, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t capacity,
+                         unsigned long long* header, cudaStream_t stream) {
+  if (P <= 0) return;
+  scan_blocks_kernel<<<1, 1024, 0, stream>>>(g.block_tiles, g.block_off, (uint32_t)num_pre_blocks(P));
+  scatter_kernel<true><<<num_pre_blocks(P), 256, 0, stream>>>(g.block_vis, g.rect, g.depths, nullptr, keys, g.grad_acc, grid_x,
+                                                             capacity, header, g.block_off, vals);
+  count_launch(2);
 }
 
 // ------------------------------------------------------------------ tile-local sort (kernel)

@@ -38,6 +38,8 @@ struct GeometryView {           // replaces GeometryState (reference rasterizer_
   uint8_t* clamped;             // [slots] bit c set <=> channel c was clamped at 0
   uint32_t* gid;                // [slots] Gaussian id held by the slot
   uint32_t* block_vis;          // [ceil(P/256)] visible Gaussians of each preprocess CTA
+  uint32_t* block_tiles;        // [ceil(P/256)+1] instances of each CTA
+  uint32_t* block_off;          // [ceil(P/256)+1] their exclusive prefix sum (ordered-emission path only)
   uint32_t* counters;           // [32] 1: num_rendered, 4: largest tile list
   float* grad_acc;              // [12 slots] backward accumulators, zero between uses
 };
@@ -51,8 +53,12 @@ struct ImageView {              // replaces ImageState (reference rasterizer_imp
 };
 
 struct BinningView {            // replaces BinningState (reference rasterizer_impl.h:54-64)
-  uint64_t* comp;               // [R] depth bits << 32 | slot, bucketed by tile, then sorted per tile
-  uint32_t* point_list;         // [R] sorted slots
+  uint32_t* point_list;         // [cap] sorted slots (same offset in both layouts: the backward needs nothing else)
+  uint64_t* comp;               // tile-local path: [cap] depth bits << 32 | slot, bucketed by tile
+  // global radix-sort path (tile lists too long for shared memory): ping-pong key/value arrays + sort temp
+  uint64_t* keys[2];
+  uint32_t* vals_other;
+  char* sort_temp;
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -77,6 +83,8 @@ inline char* carve_geometry(char* base, int P, GeometryView& g) {
   carve(p, g.clamped, S);
   carve(p, g.gid, S);
   carve(p, g.block_vis, (size_t)num_pre_blocks(P) + 1);
+  carve(p, g.block_tiles, (size_t)num_pre_blocks(P) + 1);
+  carve(p, g.block_off, (size_t)num_pre_blocks(P) + 1);
   carve(p, g.counters, (size_t)32);
   carve(p, g.grad_acc, 12 * S);
   return p;

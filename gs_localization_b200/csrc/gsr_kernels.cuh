@@ -61,6 +61,9 @@ void launch_scan_tiles(int* tile_diff, uint32_t gx, uint32_t gy, uint2* ranges, 
 // (Gaussian, tile) instances -> tile buckets as depth_bits << 32 | slot; also zeroes the slots' backward accumulators
 void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* comp, uint32_t grid_x, uint32_t capacity,
                     unsigned long long* header, cudaStream_t stream);
+// the reference's unsorted (key, value) arrays, in Gaussian order, for the global radix sort path
+void launch_emit_ordered(int P, const GeometryView& g, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t capacity,
+                         unsigned long long* header, cudaStream_t stream);
 void launch_reset_cursors(int T, const uint2* ranges, uint32_t* cursor, cudaStream_t stream);
 // per-tile sort of the buckets on the composite key; writes the sorted slots to point_list
 void launch_tile_sort(int num_tiles, const uint2* ranges, uint64_t* comp, uint32_t* point_list, uint32_t capacity,

@@ -135,6 +135,7 @@ __device__ __forceinline__ float3 color_from_sh(int deg, float3 pos, float3 camp
 template <bool ALIGNED>
 __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_fwd_kernel(const PreprocessParams p) {
   __shared__ uint32_t s_warp_vis[PRE_THREADS / 32];
+  __shared__ uint32_t s_warp_tiles[PRE_THREADS / 32];
   __shared__ __align__(16) float s_means[PRE_THREADS * 3];
   __shared__ float s_cam[16 + 16 + 4];
   __shared__ uint16_t s_vis_tid[PRE_THREADS];
@@ -233,17 +234,19 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_fwd_kernel(const Pr
   const bool vis = tiles != 0;
   const uint32_t vis_mask = __ballot_sync(0xffffffffu, vis);
   const uint32_t vis_rank_in_warp = __popc(vis_mask & ((1u << lane) - 1u));
-  if (lane == 0) s_warp_vis[warp] = __popc(vis_mask);
+  const uint32_t warp_tiles = __reduce_add_sync(0xffffffffu, tiles);
+  if (lane == 0) s_warp_vis[warp] = __popc(vis_mask), s_warp_tiles[warp] = warp_tiles;
   __syncthreads();
-  uint32_t warp_off = 0, nvis = 0;
+  uint32_t warp_off = 0, nvis = 0, ntiles = 0;
 #pragma unroll
   for (int w = 0; w < PRE_THREADS / 32; w++) {
     const uint32_t c = s_warp_vis[w];
     if (w < (int)warp) warp_off += c;
     nvis += c;
+    ntiles += s_warp_tiles[w];
   }
   const uint32_t vis_base = (uint32_t)base;     // first slot of this CTA
-  if (tid == 0) p.geom.block_vis[block] = nvis;
+  if (tid == 0) p.geom.block_vis[block] = nvis, p.geom.block_tiles[block] = ntiles;
   if (vis) {
     const uint32_t lr = warp_off + vis_rank_in_warp;   // rank inside the CTA
     const uint32_t k = vis_base + lr;

@@ -24,6 +24,8 @@ SCENES = {
     "ragged": dict(P=3000, W=75, H=53, deg=2, f=70.0, sigma0=0.1),      # W,H not multiples of 16
     "deg1": dict(P=4000, W=128, H=96, deg=1, f=100.0, sigma0=0.08),
     "mid": dict(P=60_000, W=320, H=240, deg=3, f=262.5, sigma0=0.04),
+    # tile lists longer than the shared-memory tile sort handles (> 4096): exercises the global onesweep path
+    "dense": dict(P=200_000, W=64, H=48, deg=1, f=50.0, sigma0=0.1),
 }
 
 
@@ -67,6 +69,9 @@ def test_forward_vs_oracle(name):
     assert R == o.R
     st = ours.export_state(P, R, cam.W, cam.H, geom, binning, img)
     g, b = o.geometry(), o.binning()
+    if name == "dense":
+        lens = b["ranges"][:, 1].astype(np.int64) - b["ranges"][:, 0]
+        assert lens.max() > 4096, lens.max()      # really on the global-sort path
     # integer / index work: bit-exact
     assert np.array_equal(radii.cpu().numpy(), g["radii"])
     assert np.array_equal(st["tiles_touched"].cpu().numpy().view(np.uint32), g["tiles_touched"])
@@ -87,7 +92,7 @@ def test_forward_vs_oracle(name):
     assert mism <= 2e-3, mism
 
 
-@pytest.mark.parametrize("name", ["tiny", "C1", "ragged", "mid"])
+@pytest.mark.parametrize("name", ["tiny", "C1", "ragged", "mid", "dense"])
 def test_forward_vs_reference_bit_exact(name):
     if not util.reference_available():
         pytest.skip("oracle/_ref not built (reference sources absent at build time)")
@@ -126,7 +131,7 @@ def _grads_ours(m, cam, bg, wc, wd, wa):
     return dict(zip(names, [r.cpu().numpy() for r in res])), args, (R, radii, geom, binning, img, alpha)
 
 
-@pytest.mark.parametrize("name", ["tiny", "C1", "ragged", "mid"])
+@pytest.mark.parametrize("name", ["tiny", "C1", "ragged", "mid", "dense"])
 def test_backward_vs_oracle_f64(name):
     m, cam = util.scene(**SCENES[name])
     bg = torch.tensor([0.1, 0.3, 0.2])
