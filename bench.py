@@ -333,9 +333,14 @@ def make_roofline(split, ws, cfg):
     }
     dom = max(split, key=lambda k: split[k])
     peak, how = measured_peaks()
+    traffic = None
+    try:   # per-launch DRAM bytes of that kernel from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json"))).get(dom)
+    except Exception:
+        pass
     achieved = bytes_per_stage[dom] / (split[dom] * 1e-3) / 1e9 if split[dom] > 0 else 0.0
     return {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 5), "traffic": None, "peak_source": how,
+            "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": how,
             "algorithmic_bytes_per_launch": int(bytes_per_stage[dom]), "ms_per_launch": round(split[dom], 4),
             "note": "blend kernels re-use each staged splat 256x from shared memory; they are issue/latency bound, "
                     "so a low HBM fraction is expected (DESIGN.md §4)"}
