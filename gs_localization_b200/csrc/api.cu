@@ -250,6 +250,8 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
   GeometryView g{};
   BinningView bl{};
   Mailbox* box = nullptr;
+  SideStream* color_side = nullptr;
+  bool color_joined = false;
   if (P > 0) {
     char* geom_base = geometry_alloc(gsr_geometry_bytes(P), user);
     if (!geom_base) return fail(GSR_ERR_ALLOC, "geometry_alloc returned NULL");
@@ -271,6 +273,17 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     {
       StageScope ts(ST_PREPROCESS, stream);
       launch_preprocess_fwd(pp, stream);
+      // colours on the side stream, concurrent with the binning kernels; joined before the blend
+      color_side = side_stream();
+      if (color_side && !debug && !g_timer.enabled) {
+        GSR_CUDA(cudaEventRecord(color_side->fork, stream));
+        GSR_CUDA(cudaStreamWaitEvent(color_side->stream, color_side->fork, 0));
+        launch_color_fwd(pp, color_side->stream);
+        GSR_CUDA(cudaEventRecord(color_side->join, color_side->stream));
+      } else {
+        color_side = nullptr;
+        launch_color_fwd(pp, stream);
+      }
     }
     GSR_STAGE("preprocess", debug, stream);
     {
@@ -341,6 +354,10 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     rp.bg = background, rp.out_color = out_color, rp.out_depth = out_depth, rp.out_alpha = out_alpha;
     rp.n_contrib = im.n_contrib, rp.n_touched = (P > 0) ? n_touched : nullptr;
     rp.capacity = (uint32_t)capacity;
+    if (color_side && !color_joined) {
+      GSR_CUDA(cudaStreamWaitEvent(stream, color_side->join, 0));
+      color_joined = true;
+    }
     {
       StageScope ts(ST_RENDER, stream);
       launch_render_fwd(rp, stream);

@@ -32,6 +32,8 @@ struct PreprocessParams {
 };
 
 void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream);
+// colours of the visible slots (needs preprocess; only the blend needs it)
+void launch_color_fwd(const PreprocessParams& p, cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
 
 // ---- binning (binning.cu)

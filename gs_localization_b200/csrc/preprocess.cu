@@ -132,50 +132,47 @@ __device__ __forceinline__ float3 color_from_sh(int deg, float3 pos, float3 camp
   return make_float3(fmaxf(r0, 0.f), fmaxf(r1, 0.f), fmaxf(r2, 0.f));
 }
 
-template <bool ALIGNED>
-__global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_fwd_kernel(const PreprocessParams p) {
+__global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_fwd_kernel(const PreprocessParams p) {
   __shared__ uint32_t s_warp_vis[PRE_THREADS / 32];
   __shared__ uint32_t s_warp_tiles[PRE_THREADS / 32];
-  __shared__ __align__(16) float s_means[PRE_THREADS * 3];
-  __shared__ float s_cam[16 + 16 + 4];
-  __shared__ uint16_t s_vis_tid[PRE_THREADS];
-  __shared__ float s_vis_depth[PRE_THREADS];
+  __shared__ float s_cam[16 + 16];
 
   const int tid = threadIdx.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
-  if (tid < 16) s_cam[tid] = p.viewmatrix[tid];
-  else if (tid < 32) s_cam[tid] = p.projmatrix[tid - 16];
-  else if (tid < 35) s_cam[tid] = p.campos[tid - 32];
   const uint32_t block = blockIdx.x;
   const int base = (int)block * PRE_THREADS;
   const int idx = base + tid;
   const int P = p.P;
 
-  // ---- stage the CTA's means with coalesced 128-bit loads
-  {
-    const int nflt = min(PRE_THREADS, P - base) * 3;
-    const float* src = p.means3D + (size_t)base * 3;
-    if (ALIGNED) {
-      const int nv = nflt >> 2;
-      const float4* s4 = reinterpret_cast<const float4*>(src);
-      for (int i = tid; i < nv; i += PRE_THREADS) reinterpret_cast<float4*>(s_means)[i] = __ldg(s4 + i);
-      for (int i = (nv << 2) + tid; i < nflt; i += PRE_THREADS) s_means[i] = __ldg(src + i);
+  // ---- every per-Gaussian input is requested up front so that one DRAM round trip covers them all; the
+  //      camera constants go through shared memory while those loads are in flight
+  float px = 0.f, py = 0.f, pz = 0.f, opacity = 0.f;
+  float3 sc = {0, 0, 0};
+  float4 q = {0, 0, 0, 0};
+  float cov3D[6] = {0, 0, 0, 0, 0, 0};
+  if (idx < P) {
+    px = __ldg(p.means3D + 3 * (size_t)idx), py = __ldg(p.means3D + 3 * (size_t)idx + 1), pz = __ldg(p.means3D + 3 * (size_t)idx + 2);
+    opacity = __ldg(p.opacities + idx);
+    if (p.cov3D_precomp) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) cov3D[k] = __ldg(p.cov3D_precomp + 6 * (size_t)idx + k);
     } else {
-      for (int i = tid; i < nflt; i += PRE_THREADS) s_means[i] = __ldg(src + i);
+      sc = make_float3(__ldg(p.scales + 3 * (size_t)idx), __ldg(p.scales + 3 * (size_t)idx + 1), __ldg(p.scales + 3 * (size_t)idx + 2));
+      q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
     }
   }
+  if (tid < 16) s_cam[tid] = p.viewmatrix[tid];
+  else if (tid < 32) s_cam[tid] = p.projmatrix[tid - 16];
   __syncthreads();
 
   uint32_t tiles = 0;
   int radius = 0;
   float vz = 0.f, pix_x = 0.f, pix_y = 0.f;
   float3 conic = {0, 0, 0};
-  float cov3D[6];
   uint2 rect = {0, 0};
   if (idx < P) {
     const float* vm = s_cam;
     const float* pm = s_cam + 16;
-    const float px = s_means[3 * tid], py = s_means[3 * tid + 1], pz = s_means[3 * tid + 2];
     // in_frustum: p_view.z <= 0.2 culls (NaN culls too)
     vz = __fadd_rn(dot3c(px, vm[2], py, vm[6], pz, vm[10]), vm[14]);
     if (vz > 0.2f) {
@@ -186,15 +183,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_fwd_kernel(const Pr
       const float hw = __fadd_rn(dot3c(px, pm[3], py, pm[7], pz, pm[11]), pm[15]);
       const float p_w = __frcp_rn(__fadd_rn(hw, 0.0000001f));
       const float projx = __fmul_rn(hx, p_w), projy = __fmul_rn(hy, p_w);
-      if (p.cov3D_precomp) {
-#pragma unroll
-        for (int k = 0; k < 6; k++) cov3D[k] = __ldg(p.cov3D_precomp + 6 * (size_t)idx + k);
-      } else {
-        const float3 sc = {__ldg(p.scales + 3 * (size_t)idx), __ldg(p.scales + 3 * (size_t)idx + 1),
-                           __ldg(p.scales + 3 * (size_t)idx + 2)};
-        const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
-        compute_cov3D(sc, p.scale_modifier, q, cov3D);
-      }
+      if (!p.cov3D_precomp) compute_cov3D(sc, p.scale_modifier, q, cov3D);
       const float3 cov = compute_cov2D(vx, vy, vz, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy, cov3D, vm);
       const float det = __fmaf_rn(cov.x, cov.z, -__fmul_rn(cov.y, cov.y));
       if (det != 0.0f) {
@@ -245,21 +234,17 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_fwd_kernel(const Pr
     nvis += c;
     ntiles += s_warp_tiles[w];
   }
-  const uint32_t vis_base = (uint32_t)base;     // first slot of this CTA
   if (tid == 0) p.geom.block_vis[block] = nvis, p.geom.block_tiles[block] = ntiles;
   if (vis) {
-    const uint32_t lr = warp_off + vis_rank_in_warp;   // rank inside the CTA
-    const uint32_t k = vis_base + lr;
-    s_vis_tid[lr] = (uint16_t)tid;
-    s_vis_depth[lr] = vz;
+    const uint32_t k = (uint32_t)base + warp_off + vis_rank_in_warp;   // slot: CTA segment start + rank inside the CTA
     p.geom.depths[k] = vz;
     p.geom.means2D[k] = make_float2(pix_x, pix_y);
-    p.geom.conic_opacity[k] = make_float4(conic.x, conic.y, conic.z, __ldg(p.opacities + idx));
+    p.geom.conic_opacity[k] = make_float4(conic.x, conic.y, conic.z, opacity);
     p.geom.rect[k] = rect;
     p.geom.gid[k] = (uint32_t)idx;
     if (!p.cov3D_precomp) {
 #pragma unroll
-      for (int q = 0; q < 6; q++) p.geom.cov3D[6 * (size_t)k + q] = cov3D[q];
+      for (int i = 0; i < 6; i++) p.geom.cov3D[6 * (size_t)k + i] = cov3D[i];
     }
     // tile coverage: +1/-1 at the rectangle corners of the 2-D difference grid
     const uint32_t minx = rect.x & 0xffffu, maxx = rect.x >> 16, miny = rect.y & 0xffffu, maxy = rect.y >> 16;
@@ -269,33 +254,41 @@ __global__ void __launch_bounds__(PRE_THREADS, 3) preprocess_fwd_kernel(const Pr
     atomicAdd(p.tile_diff + maxy * stride + minx, -1);
     atomicAdd(p.tile_diff + maxy * stride + maxx, 1);
   }
-  __syncthreads();
+}
 
-  // ---- colour for the CTA's visible Gaussians only, on dense lanes
-  for (uint32_t lr = tid; lr < nvis; lr += PRE_THREADS) {
-    const uint32_t t = s_vis_tid[lr];
-    const size_t g = (size_t)base + t;
+void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream) {
+  preprocess_fwd_kernel<<<num_pre_blocks(p.P), PRE_THREADS, 0, stream>>>(p);
+  count_launch();
+}
+
+// Colour of the visible Gaussians (SH -> RGB, reference forward.cu:20-71, or the caller's precomputed colours),
+// one single-warp CTA per slot segment, dense lanes.  Nothing before the blend needs colours, so this kernel
+// runs on a side stream concurrently with the binning kernels (scan_tiles / scatter / tile_sort).
+constexpr int COLOR_THREADS = 32;
+__global__ void __launch_bounds__(COLOR_THREADS) color_fwd_kernel(const PreprocessParams p) {
+  const uint32_t nvis = p.geom.block_vis[blockIdx.x];
+  if (nvis == 0) return;
+  const float3 cp = {__ldg(p.campos), __ldg(p.campos + 1), __ldg(p.campos + 2)};
+  for (uint32_t t = threadIdx.x; t < nvis; t += COLOR_THREADS) {
+    const uint32_t k = blockIdx.x * PRE_THREADS + t;
+    const size_t g = __ldg(p.geom.gid + k);
     float3 rgb;
     uint8_t cm = 0;
     if (p.colors_precomp) {
       rgb = make_float3(__ldg(p.colors_precomp + 3 * g), __ldg(p.colors_precomp + 3 * g + 1), __ldg(p.colors_precomp + 3 * g + 2));
     } else {
-      const float3 cp = {s_cam[32], s_cam[33], s_cam[34]};
-      const float3 pos = {s_means[3 * t], s_means[3 * t + 1], s_means[3 * t + 2]};
+      const float3 pos = {__ldg(p.means3D + 3 * g), __ldg(p.means3D + 3 * g + 1), __ldg(p.means3D + 3 * g + 2)};
       const float* sh = p.shs + g * p.M * 3;
       if (p.sh_vec4) rgb = color_from_sh<true>(p.D, pos, cp, sh, cm);
       else rgb = color_from_sh<false>(p.D, pos, cp, sh, cm);
     }
-    p.geom.rgbd[vis_base + lr] = make_float4(rgb.x, rgb.y, rgb.z, s_vis_depth[lr]);
-    p.geom.clamped[vis_base + lr] = cm;
+    p.geom.rgbd[k] = make_float4(rgb.x, rgb.y, rgb.z, p.geom.depths[k]);
+    p.geom.clamped[k] = cm;
   }
 }
 
-void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream) {
-  const int blocks = num_pre_blocks(p.P);
-  const bool aligned = ((uintptr_t)p.means3D % 16) == 0;
-  if (aligned) preprocess_fwd_kernel<true><<<blocks, PRE_THREADS, 0, stream>>>(p);
-  else preprocess_fwd_kernel<false><<<blocks, PRE_THREADS, 0, stream>>>(p);
+void launch_color_fwd(const PreprocessParams& p, cudaStream_t stream) {
+  color_fwd_kernel<<<num_pre_blocks(p.P), COLOR_THREADS, 0, stream>>>(p);
   count_launch();
 }
 
