@@ -30,6 +30,16 @@ SIGNATURES = {
         C.c_float, C.c_float, C.c_int,
         _P, _P, _P, _P, _P,
         C.c_int, _P]),
+    "gsr_rasterize_forward_async": (C.c_int, [
+        _P, _P, C.c_longlong, C.c_int, _P,
+        C.c_int, C.c_int, C.c_int,
+        _P, C.c_int, C.c_int,
+        _P, _P, _P, _P,
+        _P, C.c_float, _P, _P,
+        _P, _P, _P,
+        C.c_float, C.c_float,
+        _P, _P, _P, _P, _P, _P]),
+    "gsr_read_counters": (C.c_int, [_P, C.c_int, _P, _P]),
     "gsr_rasterize_backward": (C.c_int, [
         C.c_int, C.c_int, C.c_int, C.c_longlong,
         _P, C.c_int, C.c_int,

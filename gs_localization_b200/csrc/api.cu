@@ -288,7 +288,7 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     GSR_STAGE("preprocess", debug, stream);
     {
       StageScope ts(ST_RANGES, stream);
-      launch_scan_tiles(im.tile_diff, gx, gy, im.ranges, im.tile_cursor, im.tile_order, g.counters, stream);
+      launch_scan_tiles(im.tile_diff, gx, gy, im.ranges, im.tile_cursor, im.tile_order, g.counters, 0, stream);
     }
     GSR_STAGE("scan_tiles", debug, stream);
 
@@ -418,6 +418,98 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
   return R;
 }
 
+
+// Sync-free forward for callers that keep their own buffers (the fused pose-refinement loop): no allocation
+// callbacks, no host wait, nothing that cannot be captured into a CUDA graph.  num_rendered stays on the device
+// (read it later with gsr_read_counters); if it exceeds binning_capacity the kernels clamp and counters[3] is set.
+int gsr_rasterize_forward_async(char* geometry_buffer, char* binning_buffer, long long binning_capacity, int global_sort,
+                                char* image_buffer, int P, int D, int M, const float* background, int width, int height,
+                                const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+                                const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+                                const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
+                                float tan_fovy, float* out_color, float* out_depth, float* out_alpha, int* radii, int* n_touched,
+                                void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (P <= 0 || width <= 0 || height <= 0 || binning_capacity <= 0 || binning_capacity >= (1ll << 30))
+    return fail(GSR_ERR_INVALID_ARGUMENT, "bad sizes");
+  if (!geometry_buffer || !binning_buffer || !image_buffer || !background || !means3D || !opacities || !viewmatrix || !projmatrix ||
+      !cam_pos || !out_color || !out_depth || !out_alpha || !radii || (!shs && !colors_precomp) ||
+      (!cov3D_precomp && (!scales || !rotations)))
+    return fail(GSR_ERR_INVALID_ARGUMENT, "null required pointer");
+  const uint32_t gx = (width + TILE_X - 1) / TILE_X, gy = (height + TILE_Y - 1) / TILE_Y;
+  const int T = (int)(gx * gy);
+  GeometryView g;
+  carve_geometry(geometry_buffer, P, g);
+  ImageView im;
+  carve_image(image_buffer, width, height, im);
+  BinningView bl;
+  carve_binning(binning_buffer, binning_capacity, bl, global_sort != 0, width, height);
+  GSR_CUDA(cudaMemsetAsync(g.counters, 0, 32 * sizeof(uint32_t), stream));
+  GSR_CUDA(cudaMemsetAsync(im.tile_diff, 0, sizeof(int) * (size_t)(gx + 1) * (gy + 1), stream));
+  PreprocessParams pp{};
+  pp.P = P, pp.D = D, pp.M = M, pp.W = width, pp.H = height, pp.grid_x = gx, pp.grid_y = gy;
+  pp.means3D = means3D, pp.scales = scales, pp.rotations = rotations, pp.opacities = opacities, pp.shs = shs;
+  pp.cov3D_precomp = cov3D_precomp, pp.colors_precomp = colors_precomp;
+  pp.viewmatrix = viewmatrix, pp.projmatrix = projmatrix, pp.campos = cam_pos;
+  pp.scale_modifier = scale_modifier, pp.tan_fovx = tan_fovx, pp.tan_fovy = tan_fovy;
+  pp.focal_y = height / (2.0f * tan_fovy), pp.focal_x = width / (2.0f * tan_fovx);
+  pp.prefiltered = 0;
+  pp.sh_vec4 = shs && (M % 4 == 0) && ((uintptr_t)shs % 16 == 0);
+  pp.radii = radii, pp.n_touched = n_touched, pp.tile_diff = im.tile_diff, pp.geom = g;
+  launch_preprocess_fwd(pp, stream);
+  SideStream* ss = side_stream();
+  if (ss) {
+    GSR_CUDA(cudaEventRecord(ss->fork, stream));
+    GSR_CUDA(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+    launch_color_fwd(pp, ss->stream);
+    GSR_CUDA(cudaEventRecord(ss->join, ss->stream));
+  } else {
+    launch_color_fwd(pp, stream);
+  }
+  launch_scan_tiles(im.tile_diff, gx, gy, im.ranges, im.tile_cursor, im.tile_order, g.counters, (uint32_t)binning_capacity, stream);
+  unsigned long long* hdr = reinterpret_cast<unsigned long long*>(binning_buffer);
+  if (!global_sort) {
+    launch_scatter(P, g, im.tile_cursor, bl.comp, gx, (uint32_t)binning_capacity, hdr, stream);
+    launch_tile_sort(T, im.ranges, bl.comp, bl.point_list, (uint32_t)binning_capacity, stream);
+  } else {
+    const int end_bit = sort_end_bit(width, height);
+    const int passes = sort_passes(end_bit);
+    uint64_t* keys[2] = {bl.keys[0], bl.keys[1]};
+    uint32_t* vals[2];
+    vals[passes & 1] = bl.point_list;
+    vals[(passes & 1) ^ 1] = bl.vals_other;
+    SortTemp st;
+    carve_sort_temp(bl.sort_temp, binning_capacity, passes, st);
+    sort_temp_reset(bl.sort_temp, binning_capacity, passes, stream);
+    launch_emit_ordered(P, g, keys[0], vals[0], gx, (uint32_t)binning_capacity, hdr, stream);
+    launch_sort_histogram(keys[0], g.counters + 1, binning_capacity, end_bit, st.hist, stream);
+    launch_onesweep(keys, vals, g.counters + 1, binning_capacity, end_bit, st, stream);
+  }
+  RenderParams rp{};
+  rp.W = width, rp.H = height, rp.grid_x = gx, rp.grid_y = gy;
+  rp.ranges = im.ranges, rp.point_list = bl.point_list, rp.tile_order = im.tile_order;
+  rp.means2D = g.means2D, rp.conic_opacity = g.conic_opacity, rp.rgbd = g.rgbd, rp.gid = g.gid;
+  rp.bg = background, rp.out_color = out_color, rp.out_depth = out_depth, rp.out_alpha = out_alpha;
+  rp.n_contrib = im.n_contrib, rp.n_touched = n_touched, rp.capacity = (uint32_t)binning_capacity;
+  if (ss) GSR_CUDA(cudaStreamWaitEvent(stream, ss->join, 0));
+  launch_render_fwd(rp, stream);
+  GSR_STAGE("forward_async", 0, stream);
+  return GSR_OK;
+}
+
+// counters of the last forward run on this geometry buffer: out[0] = num_rendered, out[1] = overflow flag,
+// out[2] = longest tile list.  Synchronises the stream.
+int gsr_read_counters(const char* geometry_buffer, int P, unsigned int* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!geometry_buffer || P <= 0 || !out) return fail(GSR_ERR_INVALID_ARGUMENT, "bad arguments");
+  GeometryView g;
+  carve_geometry(const_cast<char*>(geometry_buffer), P, g);
+  uint32_t h[8];
+  GSR_CUDA(cudaMemcpyAsync(h, g.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  GSR_CUDA(cudaStreamSynchronize(stream));
+  out[0] = h[1], out[1] = h[3], out[2] = h[4];
+  return GSR_OK;
+}
 
 int gsr_rasterize_backward(int P, int D, int M, long long R, const float* background, int width, int height,
                            const float* means3D, const float* shs, const float* colors_precomp, const float* out_alpha,

@@ -88,7 +88,7 @@ template <bool IN_SMEM>
 __global__ void __launch_bounds__(ST_THREADS) scan_tiles_kernel(int* __restrict__ diff_g, uint32_t gx, uint32_t gy,
                                                                 uint2* __restrict__ ranges, uint32_t* __restrict__ cursor,
                                                                 uint32_t* __restrict__ tile_order,
-                                                                uint32_t* __restrict__ counters) {
+                                                                uint32_t* __restrict__ counters, uint32_t capacity) {
   __shared__ int s_grid[IN_SMEM ? ST_SMEM_CELLS : 1];
   __shared__ uint32_t s_part[ST_THREADS];
   __shared__ uint32_t s_max[32];
@@ -153,7 +153,10 @@ __global__ void __launch_bounds__(ST_THREADS) scan_tiles_kernel(int* __restrict_
     for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= (uint32_t)o) wi += n; }
     s_part[lane] = wi - w;                       // exclusive offset of each warp
     const uint32_t m = __reduce_max_sync(0xffffffffu, s_max[lane]);
-    if (lane == 31) counters[1] = wi;            // num_rendered
+    if (lane == 31) {
+      counters[1] = wi;                          // num_rendered
+      if (capacity && wi > capacity) counters[3] = 1;   // sync-free forward: the caller's binning buffer is too small
+    }
     if (lane == 0) counters[4] = m, s_max[0] = m;  // longest tile list
   }
   __syncthreads();
@@ -199,11 +202,11 @@ __global__ void __launch_bounds__(ST_THREADS) scan_tiles_kernel(int* __restrict_
 }
 
 void launch_scan_tiles(int* tile_diff, uint32_t gx, uint32_t gy, uint2* ranges, uint32_t* cursor, uint32_t* tile_order,
-                       uint32_t* counters, cudaStream_t stream) {
+                       uint32_t* counters, uint32_t capacity, cudaStream_t stream) {
   if ((gx + 1) * (gy + 1) <= ST_SMEM_CELLS)
-    scan_tiles_kernel<true><<<1, ST_THREADS, 0, stream>>>(tile_diff, gx, gy, ranges, cursor, tile_order, counters);
+    scan_tiles_kernel<true><<<1, ST_THREADS, 0, stream>>>(tile_diff, gx, gy, ranges, cursor, tile_order, counters, capacity);
   else
-    scan_tiles_kernel<false><<<1, ST_THREADS, 0, stream>>>(tile_diff, gx, gy, ranges, cursor, tile_order, counters);
+    scan_tiles_kernel<false><<<1, ST_THREADS, 0, stream>>>(tile_diff, gx, gy, ranges, cursor, tile_order, counters, capacity);
   count_launch();
 }
 

@@ -59,7 +59,7 @@ void sort_temp_reset(char* base, long long n, int passes, cudaStream_t stream);
 // coverage grid -> per-tile list lengths -> ranges / bucket cursors / num_rendered (counters[1]) / longest list (counters[4])
 // + tile_order: tiles by descending list length (launch order of the blend CTAs)
 void launch_scan_tiles(int* tile_diff, uint32_t gx, uint32_t gy, uint2* ranges, uint32_t* cursor, uint32_t* tile_order,
-                       uint32_t* counters, cudaStream_t stream);
+                       uint32_t* counters, uint32_t capacity, cudaStream_t stream);
 // (Gaussian, tile) instances -> tile buckets as depth_bits << 32 | slot; also zeroes the slots' backward accumulators
 void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* comp, uint32_t grid_x, uint32_t capacity,
                     unsigned long long* header, cudaStream_t stream);

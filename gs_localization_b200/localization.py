@@ -169,3 +169,142 @@ def refine_pose_fused(gmap: syn.GaussianMap, cam: PoseCamera, target: torch.Tens
             break
     cam.w2c = w2c.view(4, 4)
     return cam.w2c, loss
+
+
+class GraphRefiner:
+    """One pose-refinement iteration captured as a CUDA graph and replayed `iters` times per query.
+
+    All scratch (geometry / image / binning buffers, images, gradients, Adam and pose state) is allocated once
+    for a (map, image size) pair; an iteration is the sync-free forward (gsr_rasterize_forward_async), the fused
+    L1 loss+gradient kernel, the pose-only backward and the Adam+SE3 kernel — no host round trip, no allocation,
+    so the launch cost of an iteration is one graph replay.  The binning capacity is taken from a first eager
+    forward (x1.5); if a later pose overflows it the query is re-run through the eager fused loop."""
+
+    def __init__(self, gmap: syn.GaussianMap, cam: PoseCamera, lr: float = 1e-3, lr_rot: float | None = None,
+                 depth_weight: float | None = None):
+        import ctypes as C
+
+        from . import _lib
+        from .diff_gaussian_rasterization import _C
+
+        self.lib, self._lib, self.C = _lib.load(), _lib, C
+        self.gmap, self.dev = gmap, cam.device
+        self.H, self.W, self.tanfovx, self.tanfovy = cam.H, cam.W, cam.tanfovx, cam.tanfovy
+        self.lr, self.lr_rot = float(lr), float(lr if lr_rot is None else lr_rot)
+        self.depth_weight = depth_weight
+        dev, H, W = self.dev, self.H, self.W
+        P = int(gmap.means3D.shape[0])
+        self.P, self.M = P, int(gmap.shs.shape[1])
+        f32 = dict(dtype=torch.float32, device=dev)
+        byte = dict(dtype=torch.uint8, device=dev)
+        # capacity from one eager forward at the starting pose
+        e = torch.Tensor([])
+        bg = torch.zeros(3, **f32)
+        fwd = _C._forward_impl(bg, gmap.means3D, e, gmap.opacities, gmap.scales, gmap.rotations, 1.0, e,
+                               cam.world_view_transform, cam.full_proj_transform, cam.tanfovx, cam.tanfovy, H, W, gmap.shs,
+                               gmap.sh_degree, cam.camera_center, False, False)
+        cnt = (C.c_uint * 3)()
+        _lib.check(self.lib.gsr_read_counters(fwd[5].data_ptr(), P, cnt, torch.cuda.current_stream(dev).cuda_stream), "gsr_read_counters")
+        self.capacity = int(cnt[0] * 1.5) + 65536
+        self.global_sort = int(cnt[2] * 1.5 > 4096)
+        lib = self.lib
+        self.geom = torch.empty(lib.gsr_geometry_bytes(P), **byte)
+        self.img = torch.empty(lib.gsr_image_bytes(W, H), **byte)
+        self.binning = torch.empty(lib.gsr_binning_bytes(self.capacity, W, H), **byte)
+        self.color, self.depth, self.alpha = torch.empty(3, H, W, **f32), torch.empty(1, H, W, **f32), torch.empty(1, H, W, **f32)
+        self.radii = torch.empty(P, dtype=torch.int32, device=dev)
+        self.dL_dpix, self.dL_ddepth, self.zeros1 = torch.empty(3, H, W, **f32), torch.zeros(1, H, W, **f32), torch.zeros(1, H, W, **f32)
+        self.dL_dtau, self.loss = torch.zeros(6, **f32), torch.zeros(1, **f32)
+        self.adam_m, self.adam_v, self.step, self.tau_norm = (torch.zeros(6, **f32), torch.zeros(6, **f32), torch.zeros(1, **f32),
+                                                              torch.zeros(1, **f32))
+        self.w2c, self.view, self.proj, self.campos = (torch.zeros(16, **f32), torch.zeros(16, **f32), torch.zeros(16, **f32),
+                                                       torch.zeros(3, **f32))
+        self.raw = cam.projection_matrix.contiguous().clone()
+        self.bg = bg
+        self.target = torch.zeros(3, H, W, **f32)
+        self.target_depth = torch.zeros(1, H, W, **f32)
+        self.graph = None
+
+    def _iteration(self):
+        lib, chk, g = self.lib, self._lib.check, self.gmap
+        p = lambda t: t.data_ptr()
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        H, W = self.H, self.W
+        chk(lib.gsr_rasterize_forward_async(
+            p(self.geom), p(self.binning), self.capacity, self.global_sort, p(self.img), self.P, g.sh_degree, self.M,
+            p(self.bg), W, H, p(g.means3D), p(g.shs), None, p(g.opacities), p(g.scales), 1.0, p(g.rotations), None,
+            p(self.view), p(self.proj), p(self.campos), self.tanfovx, self.tanfovy,
+            p(self.color), p(self.depth), p(self.alpha), p(self.radii), None, stream), "gsr_rasterize_forward_async")
+        self.loss.zero_()
+        chk(lib.gsr_l1_loss_grad(p(self.color), p(self.target), p(self.dL_dpix), 3 * H * W, 1.0, p(self.loss), stream), "gsr_l1_loss_grad")
+        gD = self.zeros1
+        if self.depth_weight is not None:
+            chk(lib.gsr_l1_loss_grad(p(self.depth), p(self.target_depth), p(self.dL_ddepth), H * W, float(self.depth_weight),
+                                     p(self.loss), stream), "gsr_l1_loss_grad")
+            gD = self.dL_ddepth
+        chk(lib.gsr_rasterize_backward(
+            self.P, g.sh_degree, self.M, self.capacity, p(self.bg), W, H, p(g.means3D), p(g.shs), None, p(self.alpha),
+            p(g.scales), 1.0, p(g.rotations), None, p(self.view), p(self.proj), p(self.raw), p(self.campos),
+            self.tanfovx, self.tanfovy, p(self.radii), p(self.geom), p(self.binning), p(self.img),
+            p(self.dL_dpix), p(gD), p(self.zeros1), None, None, None, None, None, None, None, None, None,
+            p(self.dL_dtau), 0, stream), "gsr_rasterize_backward")
+        chk(lib.gsr_pose_adam_step(p(self.dL_dtau), p(self.adam_m), p(self.adam_v), p(self.step), self.lr, self.lr_rot, p(self.w2c),
+                                   p(self.raw), p(self.view), p(self.proj), p(self.campos), p(self.tau_norm), stream),
+            "gsr_pose_adam_step")
+
+    def _load_query(self, cam: PoseCamera, target, target_depth):
+        self.w2c.copy_(cam.w2c.reshape(-1))
+        self.view.copy_(cam.world_view_transform.reshape(-1))
+        self.proj.copy_(cam.full_proj_transform.reshape(-1))
+        self.campos.copy_(cam.camera_center)
+        self.target.copy_(target)
+        if target_depth is not None:
+            self.target_depth.copy_(target_depth)
+        for t in (self.adam_m, self.adam_v, self.step):
+            t.zero_()
+
+    def _counters(self):
+        cnt = (self.C.c_uint * 3)()
+        self._lib.check(self.lib.gsr_read_counters(self.geom.data_ptr(), self.P, cnt,
+                                                   torch.cuda.current_stream(self.dev).cuda_stream), "gsr_read_counters")
+        return int(cnt[0]), int(cnt[1]), int(cnt[2])
+
+    def _ensure_capacity(self):
+        """One un-captured sync-free forward at the query's starting pose; grow the binning buffer (and drop the
+        captured graph, whose nodes hold the old pointers) if this view needs more than 80 % of the capacity."""
+        p = lambda t: t.data_ptr()
+        g = self.gmap
+        self._lib.check(self.lib.gsr_rasterize_forward_async(
+            p(self.geom), p(self.binning), self.capacity, self.global_sort, p(self.img), self.P, g.sh_degree, self.M,
+            p(self.bg), self.W, self.H, p(g.means3D), p(g.shs), None, p(g.opacities), p(g.scales), 1.0, p(g.rotations), None,
+            p(self.view), p(self.proj), p(self.campos), self.tanfovx, self.tanfovy,
+            p(self.color), p(self.depth), p(self.alpha), p(self.radii), None,
+            torch.cuda.current_stream(self.dev).cuda_stream), "gsr_rasterize_forward_async")
+        R, overflow, longest = self._counters()
+        need_global = int(longest * 1.5 > 4096)
+        if R * 1.25 > self.capacity or need_global > self.global_sort:
+            self.capacity = int(R * 1.5) + 65536
+            self.global_sort = max(self.global_sort, need_global)
+            self.binning = torch.empty(self.lib.gsr_binning_bytes(self.capacity, self.W, self.H), dtype=torch.uint8, device=self.dev)
+            self.graph = None
+
+    def refine(self, cam: PoseCamera, target: torch.Tensor, iters: int = 50, target_depth: torch.Tensor | None = None):
+        """Refine one query; returns (w2c [4,4], loss [1]) like refine_pose_fused."""
+        self._load_query(cam, target, target_depth)
+        self._ensure_capacity()
+        if self.graph is None:
+            self._iteration()                    # warm-up outside capture (lazy CUDA state, side streams)
+            torch.cuda.synchronize(self.dev)
+            self._load_query(cam, target, target_depth)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._iteration()
+            self._load_query(cam, target, target_depth)   # capture does not execute, but keep the state explicit
+        for _ in range(iters):
+            self.graph.replay()
+        if self._counters()[1]:   # some iteration overflowed the binning capacity: redo this query eagerly
+            return refine_pose_fused(self.gmap, cam, target, iters=iters, lr=self.lr, lr_rot=self.lr_rot,
+                                     target_depth=target_depth if self.depth_weight is not None else None,
+                                     depth_weight=self.depth_weight or 0.01)
+        cam.w2c = self.w2c.view(4, 4).clone()
+        return cam.w2c, self.loss.clone()

@@ -88,6 +88,27 @@ GSR_API long long gsr_rasterize_forward(
     int debug, void* stream);
 
 /*
+ * Sync-free forward for callers that own persistent scratch (the fused pose-refinement loop): same kernels
+ * and results as gsr_rasterize_forward, but no allocation callbacks and no host wait, so the whole call can
+ * be captured into a CUDA graph.  geometry_buffer / image_buffer must hold gsr_geometry_bytes(P) /
+ * gsr_image_bytes(W,H); binning_buffer must hold gsr_binning_bytes(binning_capacity, W, H).  global_sort != 0
+ * selects the global radix-sort layout (needed for speed only when tile lists exceed 4096 entries).
+ * num_rendered stays on the device: gsr_read_counters returns {num_rendered, overflow, longest tile list};
+ * overflow != 0 means num_rendered exceeded binning_capacity and the outputs of that forward are invalid.
+ * gsr_rasterize_backward accepts binning_capacity as its num_rendered argument for such a forward.
+ */
+GSR_API int gsr_rasterize_forward_async(
+    char* geometry_buffer, char* binning_buffer, long long binning_capacity, int global_sort, char* image_buffer,
+    int P, int D, int M,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+    const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+    float tan_fovx, float tan_fovy,
+    float* out_color, float* out_depth, float* out_alpha, int* radii, int* n_touched, void* stream);
+GSR_API int gsr_read_counters(const char* geometry_buffer, int P, unsigned int* out3, void* stream);
+
+/*
  * Backward.  Replaces CudaRasterizer::Rasterizer::backward (rasterizer_impl.cu:343-444,
  * declared rasterizer.h:62-88) as called from RasterizeGaussiansBackwardCUDA
  * (rasterize_points.cu:170-203).

@@ -125,3 +125,22 @@ def test_fused_refinement_matches_framework_loop():
     assert abs(float(loss_ref) - float(loss_fused)) <= 1e-4
     e0, e1 = syn.pose_error(start.w2c, gt.w2c), syn.pose_error(w_fused.cpu(), gt.w2c)
     assert e1[0] < 0.5 * e0[0] and e1[1] < 0.5 * e0[1], (e0, e1)
+
+
+def test_graph_refiner_matches_fused_loop():
+    """The CUDA-graph replayed iteration follows the eager fused loop exactly (same kernels, same order)."""
+    cfg = dict(P=20_000, W=160, H=128, deg=2, f=120.0, box=1.0, sigma0=0.06)
+    m = syn.make_map(cfg["P"], cfg["deg"], cfg["sigma0"], 1.0, seed=0).to(DEV)
+    refiner = None
+    for q in (2, 5):                               # two queries through the same captured graph
+        gt = syn.make_camera(cfg, q)
+        target = loc.render_pose(m, loc.PoseCamera(gt, DEV), torch.zeros(3, device=DEV))[0].detach()
+        start = gt.perturbed(syn.initial_perturbation(q, trans_m=0.02, rot_deg=1.0))
+        a, b = loc.PoseCamera(start, DEV), loc.PoseCamera(start, DEV)
+        w_eager, loss_eager = loc.refine_pose_fused(m, a, target, iters=25, lr=1e-3)
+        if refiner is None:
+            refiner = loc.GraphRefiner(m, b, lr=1e-3)
+        w_graph, loss_graph = refiner.refine(b, target, iters=25)
+        dt, dr = syn.pose_error(w_eager.cpu(), w_graph.cpu())
+        assert dt <= 1e-5 and dr <= 1e-3, (q, dt, dr)
+        assert abs(float(loss_eager) - float(loss_graph)) <= 1e-5

@@ -1,0 +1,40 @@
+"""queries/s of the graph-replayed refinement loop on several BASELINE configs (1 GPU)."""
+import os, sys, time, json
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+from gs_localization_b200 import synthetic as syn, localization as loc
+dev = torch.device("cuda:0")
+for name in sys.argv[1:] or ["C1", "C2", "headline", "C3"]:
+    cfg, gmap, m, cams = bench.build_workload(name, 0, dev)
+    iters = cfg["iters"]
+    arm = bench.Arm("ours", dev)
+    bg = torch.zeros(3, device=dev)
+    qs = []
+    for q in range(7):
+        gt = syn.make_camera(cfg, 20_000 + q)
+        v, p_, _, c = gt.matrices(dev)
+        target = arm.c_forward(m, bg, v, p_, c, gt)[1].clone()
+        qs.append((gt, target))
+    res = {"config": name, "iters": iters}
+    for mode in ("graph", "fused_eager", "framework"):
+        cams_q = [loc.PoseCamera(gt.perturbed(syn.initial_perturbation(q, 0.02, 1.0)), dev) for q, (gt, _) in enumerate(qs)]
+        if mode == "graph":
+            refiner = loc.GraphRefiner(m, cams_q[0])
+            run = lambda cam, tgt: refiner.refine(cam, tgt, iters=iters)
+        elif mode == "fused_eager":
+            run = lambda cam, tgt: loc.refine_pose_fused(m, cam, tgt, iters=iters)
+        else:
+            run = lambda cam, tgt: loc.refine_pose(m, cam, tgt, iters=iters)
+        run(cams_q[0], qs[0][1])
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for cam, (gt, tgt) in zip(cams_q[1:], qs[1:]):
+            run(cam, tgt)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        errs = [syn.pose_error(cam.w2c.cpu(), gt.w2c) for cam, (gt, _) in zip(cams_q[1:], qs[1:])]
+        res[mode] = {"queries_per_s": round(6 / dt, 2), "ms_per_iter": round(dt / 6 / iters * 1e3, 4),
+                     "median_err_m": round(sorted(e[0] for e in errs)[3], 5), "median_err_deg": round(sorted(e[1] for e in errs)[3], 4)}
+    print(json.dumps(res), flush=True)
+    del m, gmap
+    torch.cuda.empty_cache()
