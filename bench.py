@@ -218,12 +218,41 @@ def run_gpu_arm(args, rank, world, local_rank):
     rots = m.rotations.clone().requires_grad_(True)
     params = [means, shs, opac, scales, rots]
 
-    def step_e2e(i):
-        q = i % N_POSES
-        view = host_mats[q][0].to(device, non_blocking=True)
-        proj = host_mats[q][1].to(device, non_blocking=True)
-        campos = host_mats[q][2].to(device, non_blocking=True)
-        target = host_targets[q].to(device, non_blocking=True)
+    # inputs of step i+1 are uploaded on a copy stream while step i computes (every step still copies its own
+    # inputs from pinned host memory inside the timed region; the copy just does not sit on the compute stream).
+    # One packed pinned buffer per pose -> one copy per step; view/proj/campos/target are views of the device slot.
+    copy_stream = torch.cuda.Stream(device)
+    n_in = 16 + 16 + 4 + 3 * H * W
+    host_packed = []
+    for q in range(N_POSES):
+        hp = torch.empty(n_in, dtype=torch.float32).pin_memory()
+        hp[0:16] = host_mats[q][0].reshape(-1)
+        hp[16:32] = host_mats[q][1].reshape(-1)
+        hp[32:35] = host_mats[q][2]
+        hp[36:] = host_targets[q].reshape(-1)
+        host_packed.append(hp)
+    dev_slots = [torch.empty(n_in, dtype=torch.float32, device=device) for _ in range(2)]
+    dev_in = [(d[0:16].view(4, 4), d[16:32].view(4, 4), d[32:35], d[36:].view(3, H, W)) for d in dev_slots]
+    copy_done = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def upload(i):
+        q, slot = i % N_POSES, i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])          # the step that last used this slot has finished with it
+            dev_slots[slot].copy_(host_packed[q], non_blocking=True)
+            copy_done[slot].record(copy_stream)
+
+    for ev in consumed:
+        ev.record(torch.cuda.current_stream(device))
+
+    def step_e2e(i, first=False):
+        q, slot = i % N_POSES, i % 2
+        if first:
+            upload(i)
+        upload(i + 1)
+        torch.cuda.current_stream(device).wait_event(copy_done[slot])
+        view, proj, campos, target = dev_in[slot]
         cam = cams[q]
         rs = settings_cls(image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=bg, scale_modifier=1.0,
                           viewmatrix=view, projmatrix=proj, sh_degree=m.sh_degree, campos=campos, prefiltered=False, debug=False)
@@ -234,21 +263,23 @@ def run_gpu_arm(args, rank, world, local_rank):
         loss.backward()
         for p_ in params:
             p_.grad = None
+        consumed[slot].record(torch.cuda.current_stream(device))
         return float(loss.item())   # device -> host read of the step's result
 
-    for i in range(max(3, args.warmup // 2)):
-        step_e2e(i)
+    nw = max(3, args.warmup // 2)
+    for i in range(nw):
+        step_e2e(i, first=(i == 0))
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(nw, nw + args.steps):
         step_e2e(i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         torch.distributed.barrier()
-    h2d = (16 + 16 + 3 + 3 * H * W) * 4
+    h2d = n_in * 4
     d2h = 4
 
     # ---- stage split + roofline of the dominant kernel (ours, rank 0 only; untimed extra passes)
@@ -285,16 +316,30 @@ def run_gpu_arm(args, rank, world, local_rank):
             with torch.no_grad():
                 target = arm.c_forward(m, bg, v, p_, c, gt)[1].clone()
             qs.append((loc.PoseCamera(gt.perturbed(syn.initial_perturbation(gq, trans_m=0.02, rot_deg=1.0)), device), target, gt))
-        refiner = loc.GraphRefiner(m, qs[0][0], lr=1e-3)
-        refiner.refine(qs[0][0], qs[0][1], iters=args.query_iters)     # warm-up query: includes the graph capture
+        # two graph refiners on two streams per GPU: the latency-bound binning kernels of one query overlap the blend
+        # kernels of the other
+        streams = [torch.cuda.Stream(device) for _ in range(2)]
+        refiners = []
+        for s_ in streams:
+            with torch.cuda.stream(s_):
+                r_ = loc.GraphRefiner(m, qs[0][0], lr=1e-3)
+                warm = loc.PoseCamera(qs[0][2].perturbed(syn.initial_perturbation(0, trans_m=0.02, rot_deg=1.0)), device)
+                r_.refine(warm, qs[0][1], iters=args.query_iters)      # warm-up query: includes the graph capture
+                refiners.append(r_)
         torch.cuda.synchronize()
         if world > 1:
             torch.distributed.barrier()
         t0 = time.perf_counter()
         errs = []
-        for cam_q, target, gt in qs[1:]:
-            w2c, _ = refiner.refine(cam_q, target, iters=args.query_iters)
-            errs.append(w2c)
+        todo = list(qs[1:])
+        while todo:
+            batch, todo = todo[:2], todo[2:]
+            for (cam_q, target, gt), r_, s_ in zip(batch, refiners, streams):
+                with torch.cuda.stream(s_):
+                    r_.submit(cam_q, target, args.query_iters)
+            for (cam_q, target, gt), r_, s_ in zip(batch, refiners, streams):
+                with torch.cuda.stream(s_):
+                    errs.append(r_.collect()[0])
         torch.cuda.synchronize()
         queries_s = time.perf_counter() - t0
         if world > 1:
@@ -427,7 +472,7 @@ def main():
             errs = st.get("final_pose_err") or []
             line["localization"] = {
                 "queries_per_s": round(world * args.queries / queries_s, 3), "iters_per_query": args.query_iters,
-                "queries": world * args.queries, "workload": f"{args.workload} map, pose-only refinement from a 2 cm / 1 deg initial error (one CUDA graph per iteration: sync-free forward, "
+                "queries": world * args.queries, "workload": f"{args.workload} map, pose-only refinement from a 2 cm / 1 deg initial error (2 queries in flight per GPU, one CUDA graph per iteration: sync-free forward, "
                             "L1 loss+grad kernel, pose-only backward, Adam+SE3 kernel)",
                 "median_final_err_m_deg": [round(sorted(e[0] for e in errs)[len(errs) // 2], 5),
                                            round(sorted(e[1] for e in errs)[len(errs) // 2], 4)] if errs else None}

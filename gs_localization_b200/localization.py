@@ -290,6 +290,23 @@ class GraphRefiner:
 
     def refine(self, cam: PoseCamera, target: torch.Tensor, iters: int = 50, target_depth: torch.Tensor | None = None):
         """Refine one query; returns (w2c [4,4], loss [1]) like refine_pose_fused."""
+        self.submit(cam, target, iters, target_depth)
+        return self.collect()
+
+    def collect(self):
+        """Wait for the query submitted last and return (w2c, loss)."""
+        cam, target, iters, target_depth = self._pending
+        if self._counters()[1]:   # some iteration overflowed the binning capacity: redo this query eagerly
+            return refine_pose_fused(self.gmap, cam, target, iters=iters, lr=self.lr, lr_rot=self.lr_rot,
+                                     target_depth=target_depth if self.depth_weight is not None else None,
+                                     depth_weight=self.depth_weight or 0.01)
+        cam.w2c = self.w2c.view(4, 4).clone()
+        return cam.w2c, self.loss.clone()
+
+    def submit(self, cam: PoseCamera, target: torch.Tensor, iters: int = 50, target_depth: torch.Tensor | None = None):
+        """Queue one query on the current stream without waiting for it (several refiners on different streams keep
+        the GPU busy: the latency-bound binning kernels of one query overlap the blend kernels of another)."""
+        self._pending = (cam, target, iters, target_depth)
         self._load_query(cam, target, target_depth)
         self._ensure_capacity()
         if self.graph is None:
@@ -302,9 +319,3 @@ class GraphRefiner:
             self._load_query(cam, target, target_depth)   # capture does not execute, but keep the state explicit
         for _ in range(iters):
             self.graph.replay()
-        if self._counters()[1]:   # some iteration overflowed the binning capacity: redo this query eagerly
-            return refine_pose_fused(self.gmap, cam, target, iters=iters, lr=self.lr, lr_rot=self.lr_rot,
-                                     target_depth=target_depth if self.depth_weight is not None else None,
-                                     depth_weight=self.depth_weight or 0.01)
-        cam.w2c = self.w2c.view(4, 4).clone()
-        return cam.w2c, self.loss.clone()

@@ -35,6 +35,31 @@ for name in sys.argv[1:] or ["C1", "C2", "headline", "C3"]:
         errs = [syn.pose_error(cam.w2c.cpu(), gt.w2c) for cam, (gt, _) in zip(cams_q[1:], qs[1:])]
         res[mode] = {"queries_per_s": round(6 / dt, 2), "ms_per_iter": round(dt / 6 / iters * 1e3, 4),
                      "median_err_m": round(sorted(e[0] for e in errs)[3], 5), "median_err_deg": round(sorted(e[1] for e in errs)[3], 4)}
+    # two refiners on two streams: independent queries overlap on the GPU
+    for nstreams in (2, 3):
+        cams_q = [loc.PoseCamera(gt.perturbed(syn.initial_perturbation(q, 0.02, 1.0)), dev) for q, (gt, _) in enumerate(qs)]
+        streams = [torch.cuda.Stream(dev) for _ in range(nstreams)]
+        refs = []
+        for s_ in streams:
+            with torch.cuda.stream(s_):
+                r_ = loc.GraphRefiner(m, cams_q[0])
+                r_.refine(loc.PoseCamera(qs[0][0].perturbed(syn.initial_perturbation(0, 0.02, 1.0)), dev), qs[0][1], iters=iters)
+                refs.append(r_)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        todo = list(zip(cams_q[1:], qs[1:]))
+        while todo:
+            batch, todo = todo[:nstreams], todo[nstreams:]
+            for (cam, (gt, tgt)), r_, s_ in zip(batch, refs, streams):
+                with torch.cuda.stream(s_):
+                    r_.submit(cam, tgt, iters)
+            for (cam, _), r_, s_ in zip(batch, refs, streams):
+                with torch.cuda.stream(s_):
+                    r_.collect()
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        errs = [syn.pose_error(cam.w2c.cpu(), gt.w2c) for cam, (gt, _) in zip(cams_q[1:], qs[1:])]
+        res[f"graph_x{nstreams}"] = {"queries_per_s": round(6 / dt, 2), "ms_per_iter": round(dt / 6 / iters * 1e3, 4),
+                                     "median_err_m": round(sorted(e[0] for e in errs)[3], 5)}
+        del refs
     print(json.dumps(res), flush=True)
     del m, gmap
     torch.cuda.empty_cache()
