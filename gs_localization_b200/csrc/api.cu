@@ -126,11 +126,11 @@ struct SideStream {
   cudaEvent_t fork = nullptr, join = nullptr;
 };
 SideStream* side_stream() {
-  static std::mutex mu;
-  static SideStream per_device[64];
+  // per host thread and device: the autograd engine runs backward on its own thread, and two threads must never
+  // re-record each other's fork/join events
+  thread_local SideStream per_device[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  std::lock_guard<std::mutex> lk(mu);
   SideStream& s = per_device[dev];
   if (!s.stream) {
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;

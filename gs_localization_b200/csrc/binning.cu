@@ -682,10 +682,14 @@ int launch_onesweep(uint64_t* keys[2], uint32_t* vals[2], const uint32_t* n_ptr,
                     cudaStream_t stream) {
   const int passes = sort_passes(end_bit);
   if (n <= 0 || passes == 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
-    attr_set = true;
+  {
+    static bool attr_set[64] = {};   // per device: the attribute belongs to the device's copy of the kernel
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   sort_scan_hist_kernel<<<passes, SORT_RADIX, 0, stream>>>(t.hist);
   count_launch();

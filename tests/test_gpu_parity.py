@@ -288,3 +288,20 @@ def _grads_from(args, fwd):
     torch.cuda.synchronize()
     names = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations"]
     return dict(zip(names, [r.cpu().numpy() for r in res])), args, fwd
+
+
+def test_backward_with_masked_upstream_gradients():
+    """LoGS' tracking loss masks most pixels (tools/descent_utils.py:85-123): pixels with all-zero upstream
+    gradients are skipped by the backward; the result must equal the unmasked computation of the same loss."""
+    m, cam = util.scene(**SCENES["mid"])
+    bg = torch.tensor([0.1, 0.3, 0.2])
+    rng = np.random.default_rng(3)
+    H, W = cam.H, cam.W
+    mask = (rng.random((1, H, W)) < 0.15).astype(np.float32)
+    wc = rng.standard_normal((3, H, W)).astype(np.float32) * mask
+    wd = (0.3 * rng.standard_normal((1, H, W))).astype(np.float32) * mask
+    wa = np.zeros((1, H, W), np.float32)
+    got, _, _ = _grads_ours(m, cam, bg, wc, wd, wa)
+    want = run_oracle(m, cam, bg, "f64").backward(wc, wd, wa)
+    for k in ("dL_dmeans2D", "dL_dopacity", "dL_dmeans3D", "dL_dsh", "dL_dscales", "dL_drotations"):
+        assert util.rel_err(got[k], want[k]) <= GRAD_REL_TOL, k
