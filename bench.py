@@ -113,8 +113,9 @@ class ClockSampler:
 def build_workload(name, rank, device):
     cfg = syn.CONFIGS[name]
     gmap = syn.make_map(cfg["P"], cfg["deg"], cfg["sigma0"], cfg["box"], seed=0)
-    cams = [syn.make_camera(cfg, rank * N_POSES + q).perturbed(syn.initial_perturbation(rank * N_POSES + q))
-            for q in range(N_POSES)]
+    # every rank works through the same N_POSES query poses against its own replica of the map: per-GPU work is
+    # identical, which is what "weak scaling" means (`rank` only offsets the pose-refinement queries further down)
+    cams = [syn.make_camera(cfg, q).perturbed(syn.initial_perturbation(q)) for q in range(N_POSES)]
     dmap = gmap.to(device) if device is not None else gmap
     return cfg, gmap, dmap, cams
 
@@ -170,7 +171,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     targets = []
     with torch.no_grad():
         for q in range(N_POSES):
-            gt = syn.make_camera(cfg, rank * N_POSES + q)
+            gt = syn.make_camera(cfg, q)
             v, p, _, c = gt.matrices(device)
             targets.append(arm.c_forward(m, bg, v, p, c, gt)[1].clone())
 
@@ -310,7 +311,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         from gs_localization_b200 import localization as loc
         qs = []
         for q in range(args.queries + 1):   # first one is a warm-up
-            gq = rank * args.queries + q
+            gq = q          # same queries on every rank (fixed per-GPU work); a deployment would hand each rank its own
             gt = syn.make_camera(cfg, 10_000 + gq)
             v, p_, _, c = gt.matrices(device)
             with torch.no_grad():
@@ -419,7 +420,8 @@ def cpu_oracle_timing(workload, budget_s=20.0):
     times.sort()
     med = times[len(times) // 2]
     return {"value": round(1.0 / med, 4), "unit": "iterations/s", "cores": num_threads(), "kind": "port",
-            "sample": f"{len(times)} full fwd+bwd iterations of the {workload} workload (median), OpenMP oracle/gsr_oracle.cpp"}
+            "sample": f"{len(times)} full fwd+bwd iterations of the {workload} workload (median), OpenMP oracle/gsr_oracle.cpp",
+            "pairs_last_pose": o.counters()}
 
 
 def main():
@@ -484,6 +486,19 @@ def main():
             line["workload_stats"] = st["workload_stats"]
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_oracle_timing(args.workload)
+            pairs = line["cpu_baseline"].pop("pairs_last_pose", None)
+            if pairs and st["split"]:
+                # secondary roofline of the two blend kernels: contributing (pixel, splat) pairs against the
+                # FP32 non-tensor peak, 148 SMs x 128 lanes x 2 FLOP x max clock; ~34 FLOP/pair forward, ~90 backward
+                kc = pairs["pairs_contributing"]
+                peak_tf = 148 * 128 * 2 * 1.965e9 / 1e12
+                fl = {"render": 34.0, "render_backward": 90.0}
+                line["blend_compute"] = {k: {"pairs_per_s": round(kc / (st["split"][k] * 1e-3), 0),
+                                             "tflops": round(kc * fl[k] / (st["split"][k] * 1e-3) / 1e12, 2),
+                                             "frac_of_fp32_peak": round(kc * fl[k] / (st["split"][k] * 1e-3) / 1e12 / peak_tf, 4)}
+                                         for k in fl}
+                line["blend_compute"]["pairs_contributing"] = kc
+                line["blend_compute"]["fp32_peak_tflops"] = round(peak_tf, 1)
         print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
