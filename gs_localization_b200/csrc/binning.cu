@@ -32,14 +32,12 @@ namespace gsr {
 size_t sort_temp_bytes(long long n, int passes) {
   size_t b = 0;
   b += align_up(sizeof(uint32_t) * SORT_MAX_PASSES * SORT_RADIX, 128);
-  b += align_up(sizeof(uint32_t) * 32, 128);
   b += align_up(sizeof(uint32_t) * (size_t)passes * sort_num_tiles(n) * SORT_RADIX, 128);
   return b + 128;
 }
 void carve_sort_temp(char* base, long long n, int passes, SortTemp& t) {
   char* p = base;
   carve(p, t.hist, (size_t)SORT_MAX_PASSES * SORT_RADIX);
-  carve(p, t.tickets, (size_t)32);
   carve(p, t.status, (size_t)passes * sort_num_tiles(n) * SORT_RADIX);
 }
 void sort_temp_reset(char* base, long long n, int passes, cudaStream_t stream) {
@@ -559,7 +557,6 @@ struct __align__(16) SortSmem {
   uint32_t local_start[SORT_RADIX];
   uint32_t adj[SORT_RADIX];
   uint32_t warp_tot[SORT_RADIX / 32];
-  uint32_t tile;
 };
 
 __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout,

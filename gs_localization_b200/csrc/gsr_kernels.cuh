@@ -46,14 +46,13 @@ constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
 
 struct SortTemp {
   uint32_t* hist;     // [SORT_MAX_PASSES][256]  digit counts -> exclusive bases
-  uint32_t* tickets;  // [SORT_MAX_PASSES]       dynamic tile ids
   uint32_t* status;   // [passes][ntiles][256]   decoupled look-back words
 };
 inline int sort_passes(int end_bit) { return (end_bit + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS; }
 inline size_t sort_num_tiles(long long n) { return (size_t)((n + SORT_TILE - 1) / SORT_TILE); }
 size_t sort_temp_bytes(long long n, int passes);
 void carve_sort_temp(char* base, long long n, int passes, SortTemp& t);
-// zero hist/tickets/status (one memset)
+// zero hist/status (one memset)
 void sort_temp_reset(char* base, long long n, int passes, cudaStream_t stream);
 
 // coverage grid -> per-tile list lengths -> ranges / bucket cursors / num_rendered (counters[1]) / longest list (counters[4])

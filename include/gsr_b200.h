@@ -73,8 +73,11 @@ GSR_API size_t gsr_binning_bytes(long long num_rendered, int width, int height);
  *   n_touched[P] (int32, may be NULL): pose-variant extra output
  *
  * Returns num_rendered (>= 0) — the number of (Gaussian, tile) instances — or a negative
- * error code.  Like the reference it synchronises `stream` once to learn num_rendered
- * (rasterizer_impl.cu:282) before sizing the binning buffer.
+ * error code.  Like the reference it waits once for num_rendered to reach the host
+ * (rasterizer_impl.cu:282).  With no history for this (P, W, H) it does so before sizing the binning
+ * buffer, exactly like the reference; afterwards it launches the rest of the forward speculatively into
+ * a buffer sized from recent calls (binning_alloc is then called with that larger size, and once more
+ * with the exact size in the rare case the guess was too small), so the GPU does not idle during the wait.
  */
 GSR_API long long gsr_rasterize_forward(
     gsr_alloc_fn geometry_alloc, gsr_alloc_fn binning_alloc, gsr_alloc_fn image_alloc, void* user,
