@@ -700,6 +700,15 @@ int gsr_l1_loss_grad(const float* image, const float* target, float* dL_dimage, 
   return GSR_OK;
 }
 
+int gsr_l1_ssim_loss_grad(const float* image, const float* target, int channels, int height, int width, float lambda_dssim,
+                          float* loss_accum, float* dL_dimage, float* scratch, void* stream_) {
+  if (channels <= 0 || height <= 0 || width <= 0 || !image || !target || !loss_accum || !dL_dimage || !scratch)
+    return fail(GSR_ERR_INVALID_ARGUMENT, "bad arguments");
+  launch_l1_ssim_loss_grad(image, target, channels, height, width, lambda_dssim, loss_accum, dL_dimage, scratch, (cudaStream_t)stream_);
+  GSR_STAGE("l1_ssim_loss_grad", 0, (cudaStream_t)stream_);
+  return GSR_OK;
+}
+
 int gsr_pose_adam_step(const float* dL_dtau, float* adam_m, float* adam_v, float* step_count, float lr_trans, float lr_rot,
                        float* w2c, const float* projmatrix_raw, float* viewmatrix, float* projmatrix, float* campos,
                        float* tau_norm, void* stream_) {

@@ -152,4 +152,8 @@ void launch_pose_adam_step(const float* dL_dtau, float* adam_m, float* adam_v, f
                            float* w2c, const float* raw, float* viewmatrix, float* projmatrix, float* campos, float* tau_norm,
                            cudaStream_t stream);
 
+// ---- photometric loss of map training (losses.cu); scratch holds 3*C*H*W + 2 floats
+void launch_l1_ssim_loss_grad(const float* img1, const float* img2, int C, int H, int W, float lambda, float* loss, float* dL_dimg1,
+                              float* scratch, cudaStream_t stream);
+
 }  // namespace gsr

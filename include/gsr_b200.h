@@ -188,6 +188,13 @@ GSR_API int gsr_stage_times(double* total_ms, unsigned long long* calls, int n);
  */
 GSR_API int gsr_l1_loss_grad(const float* image, const float* target, float* dL_dimage, long long n, float weight,
                              float* loss_accum, void* stream);
+/* Photometric loss of LoGS map training and its gradient in two passes over the image
+ * (gs_localization/gs/7scenes_gs_full_dslam.py:165-166; gaussian_splatting/utils/loss_utils.py:17-64):
+ *   *loss_accum += (1-lambda) * mean|image - target| + lambda * (1 - mean SSIM(image, target))
+ *   dL_dimage[C,H,W] = its gradient w.r.t. image (what the rasterizer's backward takes as dL_dpix).
+ * 11x11 Gaussian window (sigma 1.5), zero padding, per channel.  scratch: 3*C*H*W + 2 floats. */
+GSR_API int gsr_l1_ssim_loss_grad(const float* image, const float* target, int channels, int height, int width,
+                                  float lambda_dssim, float* loss_accum, float* dL_dimage, float* scratch, void* stream);
 GSR_API int gsr_pose_adam_step(const float* dL_dtau, float* adam_m, float* adam_v, float* step_count, float lr_trans,
                                float lr_rot, float* w2c, const float* projmatrix_raw, float* viewmatrix, float* projmatrix,
                                float* campos, float* tau_norm, void* stream);

@@ -1,0 +1,45 @@
+"""TEST INFRASTRUCTURE ONLY — numpy float64 restatement of the reference's photometric loss and its gradient.
+
+Follows gaussian_splatting/utils/loss_utils.py: l1_loss (17-18), gaussian (23-25), create_window (27-31),
+_ssim (41-63: zero-padded grouped conv2d with the 11x11 window, C1 = 0.01^2, C2 = 0.03^2, mean), combined as
+gs_localization/gs/7scenes_gs_full_dslam.py:165-166.  Pinned against tests/golden/ref_loss.npz, produced by
+importing the reference module itself (tests/golden/make_loss_golden.py).  Never imported by the product path."""
+import numpy as np
+
+
+def window_1d(size=11, sigma=1.5):
+    g = np.exp(-((np.arange(size) - size // 2) ** 2) / (2.0 * sigma ** 2))
+    return g / g.sum()
+
+
+def _filter(img, w):
+    """zero-padded separable correlation of a [C,H,W] array with the outer product w w^T"""
+    r = len(w) // 2
+    C, H, W = img.shape
+    p = np.zeros((C, H + 2 * r, W + 2 * r))
+    p[:, r:r + H, r:r + W] = img
+    h = sum(w[k] * p[:, :, k:k + W] for k in range(len(w)))
+    return sum(w[k] * h[:, k:k + H, :] for k in range(len(w)))
+
+
+def l1_ssim_loss_grad(img, gt, lam=0.2):
+    """returns (loss, l1, ssim, dloss/dimg) in float64"""
+    x, y = np.asarray(img, np.float64), np.asarray(gt, np.float64)
+    w = window_1d()
+    n = x.size
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    mu1, mu2 = _filter(x, w), _filter(y, w)
+    e11, e22, e12 = _filter(x * x, w), _filter(y * y, w), _filter(x * y, w)
+    s1, s2, s12 = e11 - mu1 ** 2, e22 - mu2 ** 2, e12 - mu1 * mu2
+    A1, A2, B1, B2 = 2 * mu1 * mu2 + C1, 2 * s12 + C2, mu1 ** 2 + mu2 ** 2 + C1, s1 + s2 + C2
+    ssim_map = A1 * A2 / (B1 * B2)
+    l1, ssim = np.abs(x - y).mean(), ssim_map.mean()
+    loss = (1 - lam) * l1 + lam * (1 - ssim)
+    # chain rule through the five filtered moments (the window is symmetric, so the adjoint filter is the filter)
+    g = -lam / n
+    d_mu1 = 2 * mu2 * (A2 - A1) / (B1 * B2) - ssim_map * (2 * mu1 / B1 - 2 * mu1 / B2)
+    d_e11 = -ssim_map / B2
+    d_e12 = 2 * A1 / (B1 * B2)
+    grad = _filter(g * d_mu1, w) + 2 * x * _filter(g * d_e11, w) + y * _filter(g * d_e12, w)
+    grad += (1 - lam) / n * np.sign(x - y)
+    return loss, l1, ssim, grad
