@@ -709,6 +709,27 @@ int gsr_l1_ssim_loss_grad(const float* image, const float* target, int channels,
   return GSR_OK;
 }
 
+int gsr_tracking_loss_grad(const float* image, const float* depth, const float* opacity, const float* gt_image, const float* gt_depth,
+                           const float* grad_mask, const float* exposure, int height, int width, float opacity_threshold,
+                           float depth_weight, float* loss_accum, float* dL_dimage, float* dL_ddepth, float* dL_dexposure,
+                           void* stream_) {
+  if (height <= 0 || width <= 0 || !image || !opacity || !gt_image || !loss_accum || !dL_dimage)
+    return fail(GSR_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (gt_depth && (!depth || !dL_ddepth)) return fail(GSR_ERR_INVALID_ARGUMENT, "gt_depth needs depth and dL_ddepth");
+  launch_tracking_loss_grad(image, depth, opacity, gt_image, gt_depth, grad_mask, exposure, height * width, opacity_threshold,
+                            depth_weight, dL_dimage, dL_ddepth, loss_accum, dL_dexposure, (cudaStream_t)stream_);
+  GSR_STAGE("tracking_loss_grad", 0, (cudaStream_t)stream_);
+  return GSR_OK;
+}
+
+int gsr_exposure_adam_step(float* exposure, float* dL_dexposure, float* adam_m, float* adam_v, float* step_count, float lr,
+                           void* stream_) {
+  if (!exposure || !dL_dexposure || !adam_m || !adam_v || !step_count) return fail(GSR_ERR_INVALID_ARGUMENT, "null pointer");
+  launch_exposure_adam_step(exposure, dL_dexposure, adam_m, adam_v, step_count, lr, (cudaStream_t)stream_);
+  GSR_STAGE("exposure_adam_step", 0, (cudaStream_t)stream_);
+  return GSR_OK;
+}
+
 int gsr_pose_adam_step(const float* dL_dtau, float* adam_m, float* adam_v, float* step_count, float lr_trans, float lr_rot,
                        float* w2c, const float* projmatrix_raw, float* viewmatrix, float* projmatrix, float* campos,
                        float* tau_norm, void* stream_) {

@@ -148,6 +148,11 @@ void launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream);
 // ---- pose-refinement glue (pose_step.cu)
 void launch_l1_loss_grad(const float* image, const float* target, float* dL_dimage, size_t n, float weight, float* loss_out,
                          cudaStream_t stream);
+void launch_tracking_loss_grad(const float* image, const float* depth, const float* opacity, const float* gt_image, const float* gt_depth,
+                               const float* grad_mask, const float* exposure, int npix, float opacity_threshold, float depth_weight,
+                               float* dL_dimage, float* dL_ddepth, float* loss_out, float* dL_dexposure, cudaStream_t stream);
+void launch_exposure_adam_step(float* exposure, float* dL_dexposure, float* adam_m, float* adam_v, float* step_count, float lr,
+                               cudaStream_t stream);
 void launch_pose_adam_step(const float* dL_dtau, float* adam_m, float* adam_v, float* step_count, float lr_trans, float lr_rot,
                            float* w2c, const float* raw, float* viewmatrix, float* projmatrix, float* campos, float* tau_norm,
                            cudaStream_t stream);

@@ -44,6 +44,100 @@ void launch_l1_loss_grad(const float* image, const float* target, float* dL_dima
   count_launch();
 }
 
+// Full tracking loss of LoGS (tools/descent_utils.py:85-123) and its gradient in one pass over the pixels:
+//   image_ab = exp(a) * image + b                                     (:86)
+//   L_rgb    = mean_{3HW} om * |image_ab * gm - gt * gm|              (:104-106)   om = opacity > threshold
+//   L_depth  = mean_{HW} |depth * dm - gt_depth * dm|,  dm = (gt_depth > 0.01) * om * gm      (:116-123)
+//   L        = L_rgb + depth_weight * L_depth       (depth_weight = 1 - alpha; 0 / no gt_depth = monocular)
+// The masks are thresholds, so no gradient reaches opacity.  One thread per pixel, all three channels.
+__global__ void __launch_bounds__(256) tracking_loss_grad_kernel(const float* __restrict__ image, const float* __restrict__ depth,
+                                                                 const float* __restrict__ opacity, const float* __restrict__ gt_image,
+                                                                 const float* __restrict__ gt_depth, const float* __restrict__ grad_mask,
+                                                                 const float* __restrict__ exposure, int npix, float opacity_threshold,
+                                                                 float depth_weight, float* __restrict__ dL_dimage,
+                                                                 float* __restrict__ dL_ddepth, float* __restrict__ loss_out,
+                                                                 float* __restrict__ dL_dexposure) {
+  __shared__ float s_part[3][8];
+  const float ea = exposure ? expf(exposure[0]) : 1.f, eb = exposure ? exposure[1] : 0.f;
+  const float s_rgb = 1.f / (3.f * (float)npix), s_d = depth_weight / (float)npix;
+  float acc = 0.f, acc_a = 0.f, acc_b = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+    const float gm = grad_mask ? __ldg(grad_mask + i) : 1.f;
+    const float om = opacity[i] > opacity_threshold ? 1.f : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const float I = image[(size_t)c * npix + i];
+      const float d = (ea * I + eb) * gm - __ldg(gt_image + (size_t)c * npix + i) * gm;
+      const float sg = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * om * gm;
+      acc += om * fabsf(d) * s_rgb;
+      dL_dimage[(size_t)c * npix + i] = sg * ea * s_rgb;
+      acc_a += sg * ea * I;
+      acc_b += sg;
+    }
+    if (dL_ddepth) {
+      float g = 0.f;
+      if (gt_depth) {
+        const float gd = __ldg(gt_depth + i);
+        const float dm = (gd > 0.01f ? 1.f : 0.f) * om * gm;
+        const float d = depth[i] * dm - gd * dm;
+        acc += fabsf(d) * s_d;
+        g = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * dm * s_d;
+      }
+      dL_ddepth[i] = g;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    acc_a += __shfl_xor_sync(0xffffffffu, acc_a, o);
+    acc_b += __shfl_xor_sync(0xffffffffu, acc_b, o);
+  }
+  if ((threadIdx.x & 31) == 0) s_part[0][threadIdx.x >> 5] = acc, s_part[1][threadIdx.x >> 5] = acc_a, s_part[2][threadIdx.x >> 5] = acc_b;
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int w = 0; w < 8; w++) t += s_part[threadIdx.x][w];
+    if (threadIdx.x == 0) atomicAdd(loss_out, t);
+    else if (dL_dexposure) atomicAdd(dL_dexposure + (threadIdx.x - 1), t * s_rgb);
+  }
+}
+
+void launch_tracking_loss_grad(const float* image, const float* depth, const float* opacity, const float* gt_image, const float* gt_depth,
+                               const float* grad_mask, const float* exposure, int npix, float opacity_threshold, float depth_weight,
+                               float* dL_dimage, float* dL_ddepth, float* loss_out, float* dL_dexposure, cudaStream_t stream) {
+  if (npix <= 0) return;
+  const int blocks = std::min((npix + 255) / 256, 148 * 4);
+  tracking_loss_grad_kernel<<<blocks, 256, 0, stream>>>(image, depth, opacity, gt_image, gt_depth, grad_mask, exposure, npix,
+                                                        opacity_threshold, depth_weight, dL_dimage, dL_ddepth, loss_out, dL_dexposure);
+  count_launch();
+}
+
+// torch.optim.Adam on the two exposure scalars (7scenes_localize_full_dslam.py:48-61: lr 1e-3 each); consumes and
+// clears their gradient accumulators so that the next iteration's loss kernel can add into them.
+__global__ void exposure_adam_step_kernel(float* __restrict__ exposure, float* __restrict__ dL_dexposure, float* __restrict__ adam_m,
+                                          float* __restrict__ adam_v, float* __restrict__ step_count, float lr) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  const float t = step_count[0] + 1.0f;
+  step_count[0] = t;
+  const float bc1 = 1.0f - powf(b1, t), bc2 = 1.0f - powf(b2, t);
+  for (int i = 0; i < 2; i++) {
+    const float g = dL_dexposure[i];
+    dL_dexposure[i] = 0.f;
+    const float m = b1 * adam_m[i] + (1.0f - b1) * g;
+    const float v = b2 * adam_v[i] + (1.0f - b2) * g * g;
+    adam_m[i] = m;
+    adam_v[i] = v;
+    exposure[i] -= (lr / bc1) * (m / (sqrtf(v) / sqrtf(bc2) + eps));
+  }
+}
+
+void launch_exposure_adam_step(float* exposure, float* dL_dexposure, float* adam_m, float* adam_v, float* step_count, float lr,
+                               cudaStream_t stream) {
+  exposure_adam_step_kernel<<<1, 32, 0, stream>>>(exposure, dL_dexposure, adam_m, adam_v, step_count, lr);
+  count_launch();
+}
+
 // state: m[6], v[6], step (as float), then w2c[16] row-major, raw projection (transposed storage) [16]
 __global__ void pose_adam_step_kernel(const float* __restrict__ dL_dtau, float* __restrict__ adam_m, float* __restrict__ adam_v,
                                       float* __restrict__ step_count, float lr_trans, float lr_rot, float* __restrict__ w2c,

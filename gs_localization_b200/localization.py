@@ -57,6 +57,16 @@ class PoseCamera:
                                                         cam.H).t().contiguous().float().to(self.device)
         self.cam_rot_delta = torch.nn.Parameter(torch.zeros(3, device=self.device))
         self.cam_trans_delta = torch.nn.Parameter(torch.zeros(3, device=self.device))
+        # tools/camera_utils.py:66-91: the query image, its depth, gradient mask and exposure pair
+        self.exposure_a = torch.nn.Parameter(torch.tensor([0.0], device=self.device))
+        self.exposure_b = torch.nn.Parameter(torch.tensor([0.0], device=self.device))
+        self.original_image, self.depth, self.grad_mask = None, None, None
+
+    def compute_grad_mask(self, config):
+        """tools/camera_utils.py:164-192."""
+        from . import tracking
+        self.grad_mask = tracking.compute_grad_mask(self.original_image, config["Training"]["edge_threshold"],
+                                                    config["Dataset"]["type"])
 
     # tools/camera_utils.py:144-158
     @property
@@ -115,9 +125,48 @@ def refine_pose(gmap: syn.GaussianMap, cam: PoseCamera, target: torch.Tensor, it
     return cam.w2c, loss
 
 
+def gradient_decent(gmap: syn.GaussianMap, viewpoint: PoseCamera, config, iters: int = 50, lr: float = 1e-3,
+                    converged_threshold: float | None = 1e-4):
+    """The reference loop as written (7scenes_localize_full_dslam.py:29-93): Adam over rotation, translation and the two
+    exposure scalars, the full tracking loss (fused kernel behind autograd), update_pose, early break on convergence."""
+    from . import tracking
+    bg = torch.zeros(3, device=viewpoint.device)
+    opt = torch.optim.Adam([{"params": [viewpoint.cam_rot_delta], "lr": lr}, {"params": [viewpoint.cam_trans_delta], "lr": lr},
+                            {"params": [viewpoint.exposure_a], "lr": lr}, {"params": [viewpoint.exposure_b], "lr": lr}])
+    loss = None
+    for _ in range(iters):
+        image, radii, depth, opacity, n_touched = render_pose(gmap, viewpoint, bg)
+        opt.zero_grad()
+        loss = tracking.get_loss_tracking(config, image, depth, opacity, viewpoint)
+        loss.backward()
+        with torch.no_grad():
+            opt.step()
+            converged = viewpoint.update_pose(converged_threshold if converged_threshold is not None else -1.0)
+        if converged:
+            break
+    return viewpoint.w2c, loss
+
+
+class TrackingLoss:
+    """Options of LoGS' full tracking loss (tools/descent_utils.py:85-123) for the fused loops: opacity threshold,
+    RGB-D weight alpha (depth term weighs 1 - alpha; `monocular` drops it), and Adam on the exposure pair
+    (7scenes_localize_full_dslam.py:48-61).  The per-query gradient mask comes from tracking.compute_grad_mask."""
+
+    def __init__(self, opacity_threshold: float = 0.5, alpha: float = 0.98, monocular: bool = False, exposure_lr: float = 1e-3,
+                 optimise_exposure: bool = True):
+        self.opacity_threshold, self.alpha, self.monocular = float(opacity_threshold), float(alpha), bool(monocular)
+        self.exposure_lr, self.optimise_exposure = float(exposure_lr), bool(optimise_exposure)
+
+    @staticmethod
+    def from_config(config) -> "TrackingLoss":
+        tr = config["Training"]
+        return TrackingLoss(tr["opacity_threshold"], tr["alpha"] if "alpha" in tr else 0.98, tr["monocular"])
+
+
 def refine_pose_fused(gmap: syn.GaussianMap, cam: PoseCamera, target: torch.Tensor, iters: int = 50, lr: float = 1e-3,
                       lr_rot: float | None = None, target_depth: torch.Tensor | None = None, depth_weight: float = 0.01,
-                      converge_threshold: float | None = None):
+                      converge_threshold: float | None = None, tracking: "TrackingLoss | None" = None,
+                      grad_mask: torch.Tensor | None = None, exposure: torch.Tensor | None = None):
     """Same loop as `refine_pose`, without framework ops on the per-iteration path: the rasterizer's C ABI
     forward, a fused L1 loss+gradient kernel, the pose-only backward (SE(3) chain rule fused, no per-Gaussian
     gradients written) and one single-thread kernel doing Adam + SE3_exp + the new view constants.  The only
@@ -148,14 +197,26 @@ def refine_pose_fused(gmap: syn.GaussianMap, cam: PoseCamera, target: torch.Tens
     p = lambda t: t.data_ptr()
     lr_rot = lr if lr_rot is None else lr_rot
     target = target.contiguous()
+    if tracking is not None:
+        gm = None if grad_mask is None else grad_mask.to(**f32).contiguous()
+        exposure = torch.zeros(2, **f32) if exposure is None else exposure
+        dE, exp_m, exp_v, exp_step = torch.zeros(2, **f32), torch.zeros(2, **f32), torch.zeros(2, **f32), torch.zeros(1, **f32)
+        gt_d = None if (tracking.monocular or target_depth is None) else target_depth.contiguous()
     for it in range(iters):
         fwd = _C._forward_impl(bg, gmap.means3D, e, gmap.opacities, gmap.scales, gmap.rotations, 1.0, e, view.view(4, 4),
                                proj.view(4, 4), cam.tanfovx, cam.tanfovy, H, W, gmap.shs, gmap.sh_degree, campos, False, False)
         R, color, depth, alpha, radii, geom, binning, img, _ = fwd
         loss.zero_()
-        _lib.check(lib.gsr_l1_loss_grad(p(color), p(target), p(dL_dpix), 3 * H * W, 1.0, p(loss), stream), "gsr_l1_loss_grad")
         gD = zeros_a
-        if target_depth is not None:
+        if tracking is not None:
+            _lib.check(lib.gsr_tracking_loss_grad(p(color), p(depth), p(alpha), p(target), 0 if gt_d is None else p(gt_d),
+                                                  0 if gm is None else p(gm), p(exposure), H, W, tracking.opacity_threshold,
+                                                  1.0 - tracking.alpha, p(loss), p(dL_dpix), p(dL_ddepth), p(dE), stream),
+                       "gsr_tracking_loss_grad")
+            gD = dL_ddepth
+        else:
+            _lib.check(lib.gsr_l1_loss_grad(p(color), p(target), p(dL_dpix), 3 * H * W, 1.0, p(loss), stream), "gsr_l1_loss_grad")
+        if tracking is None and target_depth is not None:
             _lib.check(lib.gsr_l1_loss_grad(p(depth), p(target_depth), p(dL_ddepth), H * W, depth_weight, p(loss), stream),
                        "gsr_l1_loss_grad")
             gD = dL_ddepth
@@ -165,6 +226,11 @@ def refine_pose_fused(gmap: syn.GaussianMap, cam: PoseCamera, target: torch.Tens
                                        want_pose=True, needs=needs)
         _lib.check(lib.gsr_pose_adam_step(p(dL_dtau), p(adam_m), p(adam_v), p(step), float(lr), float(lr_rot), p(w2c), p(raw),
                                           p(view), p(proj), p(campos), p(tau_norm), stream), "gsr_pose_adam_step")
+        if tracking is not None and tracking.optimise_exposure:
+            _lib.check(lib.gsr_exposure_adam_step(p(exposure), p(dE), p(exp_m), p(exp_v), p(exp_step), tracking.exposure_lr, stream),
+                       "gsr_exposure_adam_step")
+        elif tracking is not None:
+            dE.zero_()
         if converge_threshold is not None and float(tau_norm) < converge_threshold:   # the reference's early break (host sync)
             break
     cam.w2c = w2c.view(4, 4)
@@ -181,7 +247,7 @@ class GraphRefiner:
     forward (x1.5); if a later pose overflows it the query is re-run through the eager fused loop."""
 
     def __init__(self, gmap: syn.GaussianMap, cam: PoseCamera, lr: float = 1e-3, lr_rot: float | None = None,
-                 depth_weight: float | None = None):
+                 depth_weight: float | None = None, tracking: "TrackingLoss | None" = None):
         import ctypes as C
 
         from . import _lib
@@ -191,7 +257,7 @@ class GraphRefiner:
         self.gmap, self.dev = gmap, cam.device
         self.H, self.W, self.tanfovx, self.tanfovy = cam.H, cam.W, cam.tanfovx, cam.tanfovy
         self.lr, self.lr_rot = float(lr), float(lr if lr_rot is None else lr_rot)
-        self.depth_weight = depth_weight
+        self.depth_weight, self.tracking = depth_weight, tracking
         dev, H, W = self.dev, self.H, self.W
         P = int(gmap.means3D.shape[0])
         self.P, self.M = P, int(gmap.shs.shape[1])
@@ -223,6 +289,9 @@ class GraphRefiner:
         self.bg = bg
         self.target = torch.zeros(3, H, W, **f32)
         self.target_depth = torch.zeros(1, H, W, **f32)
+        self.grad_mask = torch.ones(1, H, W, **f32)
+        self.exposure, self.dL_dexposure = torch.zeros(2, **f32), torch.zeros(2, **f32)
+        self.exp_m, self.exp_v, self.exp_step = torch.zeros(2, **f32), torch.zeros(2, **f32), torch.zeros(1, **f32)
         self.graph = None
 
     def _iteration(self):
@@ -236,9 +305,17 @@ class GraphRefiner:
             p(self.view), p(self.proj), p(self.campos), self.tanfovx, self.tanfovy,
             p(self.color), p(self.depth), p(self.alpha), p(self.radii), None, stream), "gsr_rasterize_forward_async")
         self.loss.zero_()
-        chk(lib.gsr_l1_loss_grad(p(self.color), p(self.target), p(self.dL_dpix), 3 * H * W, 1.0, p(self.loss), stream), "gsr_l1_loss_grad")
         gD = self.zeros1
-        if self.depth_weight is not None:
+        tr = self.tracking
+        if tr is not None:
+            chk(lib.gsr_tracking_loss_grad(p(self.color), p(self.depth), p(self.alpha), p(self.target),
+                                           0 if tr.monocular else p(self.target_depth), p(self.grad_mask), p(self.exposure), H, W,
+                                           tr.opacity_threshold, 1.0 - tr.alpha, p(self.loss), p(self.dL_dpix), p(self.dL_ddepth),
+                                           p(self.dL_dexposure), stream), "gsr_tracking_loss_grad")
+            gD = self.dL_ddepth
+        else:
+            chk(lib.gsr_l1_loss_grad(p(self.color), p(self.target), p(self.dL_dpix), 3 * H * W, 1.0, p(self.loss), stream), "gsr_l1_loss_grad")
+        if tr is None and self.depth_weight is not None:
             chk(lib.gsr_l1_loss_grad(p(self.depth), p(self.target_depth), p(self.dL_ddepth), H * W, float(self.depth_weight),
                                      p(self.loss), stream), "gsr_l1_loss_grad")
             gD = self.dL_ddepth
@@ -251,8 +328,14 @@ class GraphRefiner:
         chk(lib.gsr_pose_adam_step(p(self.dL_dtau), p(self.adam_m), p(self.adam_v), p(self.step), self.lr, self.lr_rot, p(self.w2c),
                                    p(self.raw), p(self.view), p(self.proj), p(self.campos), p(self.tau_norm), stream),
             "gsr_pose_adam_step")
+        if tr is not None:
+            if tr.optimise_exposure:
+                chk(lib.gsr_exposure_adam_step(p(self.exposure), p(self.dL_dexposure), p(self.exp_m), p(self.exp_v), p(self.exp_step),
+                                               tr.exposure_lr, stream), "gsr_exposure_adam_step")
+            else:
+                self.dL_dexposure.zero_()
 
-    def _load_query(self, cam: PoseCamera, target, target_depth):
+    def _load_query(self, cam: PoseCamera, target, target_depth, grad_mask=None):
         self.w2c.copy_(cam.w2c.reshape(-1))
         self.view.copy_(cam.world_view_transform.reshape(-1))
         self.proj.copy_(cam.full_proj_transform.reshape(-1))
@@ -260,7 +343,11 @@ class GraphRefiner:
         self.target.copy_(target)
         if target_depth is not None:
             self.target_depth.copy_(target_depth)
-        for t in (self.adam_m, self.adam_v, self.step):
+        if grad_mask is not None:
+            self.grad_mask.copy_(grad_mask.reshape(1, self.H, self.W))
+        else:
+            self.grad_mask.fill_(1.0)
+        for t in (self.adam_m, self.adam_v, self.step, self.exposure, self.dL_dexposure, self.exp_m, self.exp_v, self.exp_step):
             t.zero_()
 
     def _counters(self):
@@ -288,34 +375,38 @@ class GraphRefiner:
             self.binning = torch.empty(self.lib.gsr_binning_bytes(self.capacity, self.W, self.H), dtype=torch.uint8, device=self.dev)
             self.graph = None
 
-    def refine(self, cam: PoseCamera, target: torch.Tensor, iters: int = 50, target_depth: torch.Tensor | None = None):
+    def refine(self, cam: PoseCamera, target: torch.Tensor, iters: int = 50, target_depth: torch.Tensor | None = None,
+               grad_mask: torch.Tensor | None = None):
         """Refine one query; returns (w2c [4,4], loss [1]) like refine_pose_fused."""
-        self.submit(cam, target, iters, target_depth)
+        self.submit(cam, target, iters, target_depth, grad_mask)
         return self.collect()
 
     def collect(self):
         """Wait for the query submitted last and return (w2c, loss)."""
-        cam, target, iters, target_depth = self._pending
+        cam, target, iters, target_depth, grad_mask = self._pending
         if self._counters()[1]:   # some iteration overflowed the binning capacity: redo this query eagerly
+            self.exposure.zero_()
             return refine_pose_fused(self.gmap, cam, target, iters=iters, lr=self.lr, lr_rot=self.lr_rot,
-                                     target_depth=target_depth if self.depth_weight is not None else None,
-                                     depth_weight=self.depth_weight or 0.01)
+                                     target_depth=target_depth if (self.depth_weight is not None or self.tracking is not None) else None,
+                                     depth_weight=self.depth_weight or 0.01, tracking=self.tracking, grad_mask=grad_mask,
+                                     exposure=self.exposure)
         cam.w2c = self.w2c.view(4, 4).clone()
         return cam.w2c, self.loss.clone()
 
-    def submit(self, cam: PoseCamera, target: torch.Tensor, iters: int = 50, target_depth: torch.Tensor | None = None):
+    def submit(self, cam: PoseCamera, target: torch.Tensor, iters: int = 50, target_depth: torch.Tensor | None = None,
+               grad_mask: torch.Tensor | None = None):
         """Queue one query on the current stream without waiting for it (several refiners on different streams keep
         the GPU busy: the latency-bound binning kernels of one query overlap the blend kernels of another)."""
-        self._pending = (cam, target, iters, target_depth)
-        self._load_query(cam, target, target_depth)
+        self._pending = (cam, target, iters, target_depth, grad_mask)
+        self._load_query(cam, target, target_depth, grad_mask)
         self._ensure_capacity()
         if self.graph is None:
             self._iteration()                    # warm-up outside capture (lazy CUDA state, side streams)
             torch.cuda.synchronize(self.dev)
-            self._load_query(cam, target, target_depth)
+            self._load_query(cam, target, target_depth, grad_mask)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._iteration()
-            self._load_query(cam, target, target_depth)   # capture does not execute, but keep the state explicit
+            self._load_query(cam, target, target_depth, grad_mask)   # capture does not execute, but keep the state explicit
         for _ in range(iters):
             self.graph.replay()

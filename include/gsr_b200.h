@@ -195,6 +195,20 @@ GSR_API int gsr_l1_loss_grad(const float* image, const float* target, float* dL_
  * 11x11 Gaussian window (sigma 1.5), zero padding, per channel.  scratch: 3*C*H*W + 2 floats. */
 GSR_API int gsr_l1_ssim_loss_grad(const float* image, const float* target, int channels, int height, int width,
                                   float lambda_dssim, float* loss_accum, float* dL_dimage, float* scratch, void* stream);
+/* Full tracking loss of LoGS and its gradient in one pass (tools/descent_utils.py:85-123):
+ *   image_ab = exp(exposure[0]) * image + exposure[1]
+ *   L = mean_{3HW} om * |image_ab*gm - gt_image*gm| + depth_weight * mean_{HW} |depth*dm - gt_depth*dm|
+ *   om = opacity > opacity_threshold, gm = grad_mask (float 0/1, NULL = ones), dm = (gt_depth > 0.01) * om * gm.
+ * depth_weight = 1 - config.Training.alpha; gt_depth NULL = monocular.  exposure NULL = (0, 0).
+ * *loss_accum += L; dL_dimage[3,H,W] and dL_ddepth[H,W] (if non-NULL) are written; dL_dexposure[2] (optional) is
+ * accumulated into.  gsr_exposure_adam_step is torch.optim.Adam on the two exposure scalars
+ * (7scenes_localize_full_dslam.py:48-61) and clears dL_dexposure. */
+GSR_API int gsr_tracking_loss_grad(const float* image, const float* depth, const float* opacity, const float* gt_image,
+                                   const float* gt_depth, const float* grad_mask, const float* exposure, int height, int width,
+                                   float opacity_threshold, float depth_weight, float* loss_accum, float* dL_dimage,
+                                   float* dL_ddepth, float* dL_dexposure, void* stream);
+GSR_API int gsr_exposure_adam_step(float* exposure, float* dL_dexposure, float* adam_m, float* adam_v, float* step_count,
+                                   float lr, void* stream);
 GSR_API int gsr_pose_adam_step(const float* dL_dtau, float* adam_m, float* adam_v, float* step_count, float lr_trans,
                                float lr_rot, float* w2c, const float* projmatrix_raw, float* viewmatrix, float* projmatrix,
                                float* campos, float* tau_norm, void* stream);

@@ -43,3 +43,30 @@ def l1_ssim_loss_grad(img, gt, lam=0.2):
     grad = _filter(g * d_mu1, w) + 2 * x * _filter(g * d_e11, w) + y * _filter(g * d_e12, w)
     grad += (1 - lam) / n * np.sign(x - y)
     return loss, l1, ssim, grad
+
+
+def tracking_loss_grad(image, depth, opacity, gt_image, gt_depth, grad_mask, exposure=(0.0, 0.0), opacity_threshold=0.5,
+                       depth_weight=0.02):
+    """get_loss_tracking of gs_localization/pipelines/tools/descent_utils.py:85-123 and its gradient, float64.
+    image, gt_image [3,H,W]; depth, opacity [1,H,W]; gt_depth [H,W] or None (monocular); grad_mask [1,H,W] or None.
+    Returns (loss, dL/dimage, dL/ddepth, dL/d(exposure_a, exposure_b)).  Pinned against tests/golden/ref_tracking.npz."""
+    I, G = np.asarray(image, np.float64), np.asarray(gt_image, np.float64)
+    H, W = I.shape[1:]
+    gm = np.ones((1, H, W)) if grad_mask is None else np.asarray(grad_mask, np.float64).reshape(1, H, W)
+    om = (np.asarray(opacity, np.float32).reshape(1, H, W) > np.float32(opacity_threshold)).astype(np.float64)
+    a, b = float(exposure[0]), float(exposure[1])
+    ea = np.exp(a)
+    d = (ea * I + b) * gm - G * gm
+    loss = (om * np.abs(d)).mean()
+    sg = np.sign(d) * om * gm / d.size
+    dI = sg * ea
+    da, db = (sg * ea * I).sum(), sg.sum()
+    dD = np.zeros((1, H, W))
+    if gt_depth is not None:
+        gd = np.asarray(gt_depth, np.float64).reshape(1, H, W)
+        D = np.asarray(depth, np.float64).reshape(1, H, W)
+        dm = (np.asarray(gt_depth, np.float32).reshape(1, H, W) > np.float32(0.01)) * om * gm
+        dd = D * dm - gd * dm
+        loss += depth_weight * np.abs(dd).mean()
+        dD = depth_weight * np.sign(dd) * dm / dd.size
+    return loss, dI, dD, np.array([da, db])

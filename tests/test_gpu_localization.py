@@ -144,3 +144,41 @@ def test_graph_refiner_matches_fused_loop():
         dt, dr = syn.pose_error(w_eager.cpu(), w_graph.cpu())
         assert dt <= 1e-5 and dr <= 1e-3, (q, dt, dr)
         assert abs(float(loss_eager) - float(loss_graph)) <= 1e-5
+
+
+def test_full_tracking_loss_loops_agree():
+    """Full LoGS tracking loss (exposure pair, opacity / gradient masks, RGB-D term): the reference-shaped loop
+    (torch.optim.Adam + autograd around the fused loss kernel), the eager fused loop and the graph-replayed loop
+    follow the same trajectory, and the exposure pair moves toward the gain/offset baked into the query image."""
+    cfg = dict(P=20_000, W=160, H=128, deg=2, f=120.0, box=1.0, sigma0=0.06)
+    config = {"Training": {"monocular": False, "opacity_threshold": 0.5, "alpha": 0.9, "edge_threshold": 1.1},
+              "Dataset": {"type": "tum"}}
+    m = syn.make_map(cfg["P"], cfg["deg"], cfg["sigma0"], 1.0, seed=0).to(DEV)
+    gt = syn.make_camera(cfg, 3)
+    img, _, dep, _, _ = loc.render_pose(m, loc.PoseCamera(gt, DEV), torch.zeros(3, device=DEV))
+    target = (1.03 * img.detach() + 0.01).contiguous()
+    target_depth = dep.detach().clone()
+    target_depth[:, :20] = 0.0                                     # invalid depth rows
+    start = gt.perturbed(syn.initial_perturbation(3, trans_m=0.02, rot_deg=1.0))
+    cams = [loc.PoseCamera(start, DEV) for _ in range(3)]
+    for c in cams:
+        c.original_image, c.depth = target, target_depth[0]
+        c.compute_grad_mask(config)
+    assert 0.2 < cams[0].grad_mask.float().mean() < 0.8
+    iters = 30
+    w_ref, loss_ref = loc.gradient_decent(m, cams[0], config, iters=iters, converged_threshold=None)
+    tl = loc.TrackingLoss.from_config(config)
+    exposure = torch.zeros(2, device=DEV)
+    w_fused, loss_fused = loc.refine_pose_fused(m, cams[1], target, iters=iters, target_depth=target_depth, tracking=tl,
+                                                grad_mask=cams[1].grad_mask, exposure=exposure)
+    refiner = loc.GraphRefiner(m, cams[2], tracking=tl)
+    w_graph, loss_graph = refiner.refine(cams[2], target, iters=iters, target_depth=target_depth, grad_mask=cams[2].grad_mask)
+    for w in (w_fused, w_graph):
+        dt, dr = syn.pose_error(w_ref.cpu(), w.cpu())
+        assert dt <= 1e-4 and dr <= 0.005, (dt, dr)
+    assert abs(float(loss_ref) - float(loss_fused)) <= 1e-4 and abs(float(loss_fused) - float(loss_graph)) <= 1e-5
+    ea = torch.cat([cams[0].exposure_a.detach(), cams[0].exposure_b.detach()])
+    assert torch.allclose(ea, exposure, atol=2e-4) and torch.allclose(exposure, refiner.exposure, atol=1e-5)
+    assert float(exposure[0]) > 0.005                              # gain moved toward log(1.03)
+    e0, e1 = syn.pose_error(start.w2c, gt.w2c), syn.pose_error(w_graph.cpu(), gt.w2c)
+    assert e1[0] < e0[0] and e1[1] < e0[1], (e0, e1)

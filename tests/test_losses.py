@@ -86,3 +86,83 @@ def test_loss_autograd_wrapper_feeds_rasterizer():
     want_loss, _, _, want = loss_oracle.l1_ssim_loss_grad(x.detach().cpu().numpy(), y.cpu().numpy(), 0.2)
     assert abs(loss.item() - want_loss) < 2e-5
     assert np.abs(x.grad.cpu().numpy() - 2.0 * want).max() <= 1e-4 * np.abs(2.0 * want).max()
+
+
+# ------------------------------------------------------------------- tracking loss (descent_utils.py:85-123)
+TGOLD = os.path.join(os.path.dirname(__file__), "golden", "ref_tracking.npz")
+TCASES = ["rgbd", "mono", "rgbd_default"]
+
+
+def _tracking_inputs(g, case):
+    mono = bool(g[f"{case}_mono"])
+    return dict(image=g[f"{case}_image"], depth=g[f"{case}_depth"], opacity=g[f"{case}_opacity"], gt_image=g[f"{case}_gt"],
+                gt_depth=None if mono else g[f"{case}_gt_depth"], grad_mask=g[f"{case}_grad_mask"], exposure=g[f"{case}_exposure"],
+                opacity_threshold=0.5, depth_weight=float(g[f"{case}_depth_weight"]))
+
+
+def _check_tracking(got, g, case):
+    loss, dI, dD, dE = got
+    assert abs(loss - g[f"{case}_loss"]) < 1e-6
+    assert np.abs(dI - g[f"{case}_dimage"]).max() <= 1e-5 * np.abs(g[f"{case}_dimage"]).max()
+    assert np.abs(np.reshape(dD, g[f"{case}_ddepth"].shape) - g[f"{case}_ddepth"]).max() <= 1e-5 * max(np.abs(g[f"{case}_ddepth"]).max(), 1e-9)
+    assert np.abs(dE - g[f"{case}_dexposure"]).max() <= 1e-4 * np.abs(g[f"{case}_dexposure"]).max() + 1e-7
+
+
+@pytest.mark.parametrize("case", TCASES)
+def test_tracking_oracle_matches_reference_golden(case):
+    g = np.load(TGOLD)
+    _check_tracking(loss_oracle.tracking_loss_grad(**_tracking_inputs(g, case)), g, case)
+
+
+def _cuda_tracking(image, depth, opacity, gt_image, gt_depth, grad_mask, exposure, opacity_threshold, depth_weight):
+    import torch
+    from gs_localization_b200 import _lib
+    lib = _lib.load()
+    dev = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a, np.float32)).cuda()
+    I, D, O, G, GD, GM, E = map(dev, (image, depth, opacity, gt_image, gt_depth, grad_mask, exposure))
+    H, W = I.shape[1:]
+    loss, dI, dD, dE = torch.zeros(1, device="cuda"), torch.full_like(I, float("nan")), torch.full_like(D, float("nan")), torch.zeros(2, device="cuda")
+    p = lambda t: 0 if t is None else t.data_ptr()
+    _lib.check(lib.gsr_tracking_loss_grad(p(I), p(D), p(O), p(G), p(GD), p(GM), p(E), H, W, opacity_threshold, depth_weight,
+                                          p(loss), p(dI), p(dD), p(dE), torch.cuda.current_stream().cuda_stream), "tracking")
+    torch.cuda.synchronize()
+    return loss.item(), dI.cpu().numpy(), dD.cpu().numpy(), dE.cpu().numpy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", TCASES)
+def test_cuda_tracking_loss_matches_reference_golden(case):
+    g = np.load(TGOLD)
+    _check_tracking(_cuda_tracking(**_tracking_inputs(g, case)), g, case)
+
+
+@pytest.mark.gpu
+def test_cuda_tracking_loss_full_size_and_defaults():
+    rng = np.random.default_rng(2)
+    H, W = 480, 640
+    gt = rng.random((3, H, W)).astype(np.float32)
+    img = np.clip(gt + 0.1 * rng.standard_normal(gt.shape), 0, 1).astype(np.float32)
+    gd = (rng.random((H, W)) * 4).astype(np.float32)
+    dep = (gd[None] + 0.1 * rng.standard_normal((1, H, W))).astype(np.float32)
+    opa = rng.random((1, H, W)).astype(np.float32)
+    for kw in (dict(gt_depth=gd, grad_mask=(rng.random((1, H, W)) > 0.5), exposure=np.float32([0.1, 0.05])),
+               dict(gt_depth=None, grad_mask=None, exposure=None)):
+        want = loss_oracle.tracking_loss_grad(img, dep, opa, gt, kw["gt_depth"], kw["grad_mask"],
+                                              (0.0, 0.0) if kw["exposure"] is None else kw["exposure"], 0.5, 0.02)
+        got = _cuda_tracking(img, dep, opa, gt, kw["gt_depth"], kw["grad_mask"], kw["exposure"], 0.5, 0.02)
+        assert abs(got[0] - want[0]) < 1e-5
+        assert np.abs(got[1] - want[1]).max() <= 1e-5 * np.abs(want[1]).max()
+        assert np.abs(got[2] - want[2]).max() <= 1e-5 * max(np.abs(want[2]).max(), 1e-9)
+        if kw["exposure"] is not None:
+            assert np.abs(got[3] - want[3]).max() <= 1e-3 * np.abs(want[3]).max()   # float32 sums of 9.2e5 signed terms
+
+
+def test_grad_mask_matches_reference_golden():
+    import torch
+    from gs_localization_b200 import tracking
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_grad_mask.npz"))
+    img = torch.from_numpy(g["img"])
+    gv, gh = tracking.image_gradient(img)
+    assert np.abs(gv.numpy() - g["grad_v"]).max() < 1e-6 and np.abs(gh.numpy() - g["grad_h"]).max() < 1e-6
+    assert np.array_equal(tracking.compute_grad_mask(img, 1.1, "tum").numpy(), g["tum"])
+    assert np.array_equal(tracking.compute_grad_mask(img, 4, "replica").numpy(), g["replica"])
