@@ -709,6 +709,15 @@ int gsr_l1_ssim_loss_grad(const float* image, const float* target, int channels,
   return GSR_OK;
 }
 
+int gsr_depth_loss_grad(const float* depth, const float* pseudo_depth, const float* gt_depth, long long n, float inv_numerator,
+                        float pearson_weight, float l1_weight, float* loss_accum, float* dL_ddepth, double* scratch, void* stream_) {
+  if (n <= 0 || n >= (1ll << 31) || !depth || !loss_accum || !dL_ddepth || !scratch) return fail(GSR_ERR_INVALID_ARGUMENT, "bad arguments");
+  launch_depth_loss_grad(depth, pseudo_depth, gt_depth, (int)n, inv_numerator, pearson_weight, l1_weight, loss_accum, dL_ddepth,
+                         scratch, (cudaStream_t)stream_);
+  GSR_STAGE("depth_loss_grad", 0, (cudaStream_t)stream_);
+  return GSR_OK;
+}
+
 int gsr_tracking_loss_grad(const float* image, const float* depth, const float* opacity, const float* gt_image, const float* gt_depth,
                            const float* grad_mask, const float* exposure, int height, int width, float opacity_threshold,
                            float depth_weight, float* loss_accum, float* dL_dimage, float* dL_ddepth, float* dL_dexposure,

@@ -8,6 +8,8 @@
 // shared memory, the SSIM map, the loss sums and the three derivative maps (d ssim / d mu1, d E[xx], d E[xy],
 // pre-multiplied by dL/d ssim); pass 2 filters those maps with the same (symmetric) window and adds the L1 term,
 // yielding dL/dx directly — which is exactly the dL_dpix the rasterizer's backward consumes.
+#include <algorithm>
+
 #include "gsr_kernels.cuh"
 
 namespace gsr {
@@ -158,6 +160,94 @@ void launch_l1_ssim_loss_grad(const float* img1, const float* img2, int C, int H
   ssim_bwd_kernel<<<grid, block, 0, stream>>>(img1, img2, W, H, C, win, (1.f - lambda) / n, maps, dL_dimg1);
   ssim_finish_kernel<<<1, 32, 0, stream>>>(sums, n, lambda, loss);
   count_launch(3);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Depth terms of the map-training loss (gs_localization/gs/7scenes_gs_full_dslam.py:168-184):
+//   pseudo = min(1 - r(-m, d), 1 - r(k / (m + 200), d))      r = Pearson correlation over all pixels, m = monocular
+//                                                            (MiDaS) depth, d = rendered depth, k = 1000 (1 in train.py)
+//   L = w_p * pseudo + w_l1 * mean|d * mask - gt * mask|,    mask = gt > 0
+// r comes from torchmetrics.functional.pearson_corrcoef (third-party, not vendored, version unpinned): restated
+// here from its definition r = S_ad / sqrt(S_aa S_dd) with centred sums accumulated in double.
+// Pass 1 reduces the nine raw sums, pass 2 recomputes the two coefficients per thread and writes dL/dd.
+__global__ void __launch_bounds__(256) depth_loss_sums_kernel(const float* __restrict__ depth, const float* __restrict__ pseudo,
+                                                              const float* __restrict__ gt, int n, float k, double* __restrict__ sums) {
+  // 0:Sd 1:Sdd 2:Sa 3:Saa 4:Sad 5:Sb 6:Sbb 7:Sbd 8:S|l1|
+  double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double d = depth[i];
+    if (pseudo) {
+      const float m = __ldg(pseudo + i);
+      const double a = -(double)m, b = (double)(k / (m + 200.f));
+      acc[0] += d; acc[1] += d * d; acc[2] += a; acc[3] += a * a; acc[4] += a * d; acc[5] += b; acc[6] += b * b; acc[7] += b * d;
+    }
+    if (gt) {
+      const float g = __ldg(gt + i);
+      if (g > 0.f) acc[8] += fabs(d - (double)g);
+    }
+  }
+  __shared__ double s_part[9][8];
+#pragma unroll
+  for (int q = 0; q < 9; q++) {
+    double v = acc[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_part[q][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double t = 0;
+    for (int w = 0; w < 8; w++) t += s_part[threadIdx.x][w];
+    atomicAdd(sums + threadIdx.x, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) depth_loss_grad_kernel(const float* __restrict__ depth, const float* __restrict__ pseudo,
+                                                              const float* __restrict__ gt, int n, float k, float w_pearson, float w_l1,
+                                                              const double* __restrict__ sums, float* __restrict__ dL_ddepth,
+                                                              float* __restrict__ loss) {
+  const double N = (double)n;
+  double mean_d = 0, mean_x = 0, c_x = 0, c_d = 0;   // selected regressor x: dL/dd_i = c_x (x_i - mean_x) + c_d (d_i - mean_d)
+  int pick = 0;
+  double pseudo_loss = 0;
+  if (pseudo) {
+    mean_d = sums[0] / N;
+    const double Sdd = sums[1] - sums[0] * mean_d;
+    const double Saa = sums[3] - sums[2] * sums[2] / N, Sad = sums[4] - sums[2] * mean_d;
+    const double Sbb = sums[6] - sums[5] * sums[5] / N, Sbd = sums[7] - sums[5] * mean_d;
+    const double ra = Sad / sqrt(Saa * Sdd), rb = Sbd / sqrt(Sbb * Sdd);
+    pick = (1.0 - rb) < (1.0 - ra);                   // python min(): the second only if strictly smaller
+    const double r = pick ? rb : ra, Sxx = pick ? Sbb : Saa;
+    mean_x = (pick ? sums[5] : sums[2]) / N;
+    pseudo_loss = 1.0 - r;
+    c_x = -(double)w_pearson / sqrt(Sxx * Sdd);
+    c_d = (double)w_pearson * r / Sdd;
+  }
+  const float g_l1 = w_l1 / (float)n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float d = depth[i];
+    double g = 0;
+    if (pseudo) {
+      const float m = __ldg(pseudo + i);
+      const double x = pick ? (double)(k / (m + 200.f)) : -(double)m;
+      g = c_x * (x - mean_x) + c_d * ((double)d - mean_d);
+    }
+    if (gt) {
+      const float t = __ldg(gt + i);
+      if (t > 0.f) g += d > t ? g_l1 : (d < t ? -g_l1 : 0.f);
+    }
+    dL_ddepth[i] = (float)g;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) loss[0] += (float)((double)w_pearson * pseudo_loss + (gt ? (double)w_l1 * sums[8] / N : 0.0));
+}
+
+void launch_depth_loss_grad(const float* depth, const float* pseudo, const float* gt, int n, float k, float w_pearson, float w_l1,
+                            float* loss, float* dL_ddepth, double* scratch, cudaStream_t stream) {
+  cudaMemsetAsync(scratch, 0, 9 * sizeof(double), stream);
+  const int blocks = std::min((n + 255) / 256, 148 * 4);
+  depth_loss_sums_kernel<<<blocks, 256, 0, stream>>>(depth, pseudo, gt, n, k, scratch);
+  depth_loss_grad_kernel<<<blocks, 256, 0, stream>>>(depth, pseudo, gt, n, k, w_pearson, w_l1, scratch, dL_ddepth, loss);
+  count_launch(2);
 }
 
 }  // namespace gsr

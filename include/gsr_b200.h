@@ -195,6 +195,16 @@ GSR_API int gsr_l1_loss_grad(const float* image, const float* target, float* dL_
  * 11x11 Gaussian window (sigma 1.5), zero padding, per channel.  scratch: 3*C*H*W + 2 floats. */
 GSR_API int gsr_l1_ssim_loss_grad(const float* image, const float* target, int channels, int height, int width,
                                   float lambda_dssim, float* loss_accum, float* dL_dimage, float* scratch, void* stream);
+/* Depth terms of the map-training loss (gs_localization/gs/7scenes_gs_full_dslam.py:168-184) and their gradient:
+ *   *loss_accum += pearson_weight * min(1 - r(-m, d), 1 - r(inv_numerator / (m + 200), d))
+ *                + l1_weight * mean|d*mask - gt*mask|,  mask = gt_depth > 0
+ * d = depth[n] (rendered), m = pseudo_depth[n] (monocular estimate; NULL drops the term), gt_depth[n] (NULL drops
+ * the L1 term); r = Pearson correlation (torchmetrics.functional.pearson_corrcoef in the reference; restated from
+ * its definition, centred sums in double).  Reference weights: 0.01, inv_numerator 1000, 0.05.
+ * dL_ddepth[n] is written.  scratch: 9 doubles. */
+GSR_API int gsr_depth_loss_grad(const float* depth, const float* pseudo_depth, const float* gt_depth, long long n,
+                                float inv_numerator, float pearson_weight, float l1_weight, float* loss_accum,
+                                float* dL_ddepth, double* scratch, void* stream);
 /* Full tracking loss of LoGS and its gradient in one pass (tools/descent_utils.py:85-123):
  *   image_ab = exp(exposure[0]) * image + exposure[1]
  *   L = mean_{3HW} om * |image_ab*gm - gt_image*gm| + depth_weight * mean_{HW} |depth*dm - gt_depth*dm|

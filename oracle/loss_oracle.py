@@ -70,3 +70,35 @@ def tracking_loss_grad(image, depth, opacity, gt_image, gt_depth, grad_mask, exp
         loss += depth_weight * np.abs(dd).mean()
         dD = depth_weight * np.sign(dd) * dm / dd.size
     return loss, dI, dD, np.array([da, db])
+
+
+def depth_loss_grad(depth, pseudo, gt, inv_numerator=1000.0, w_pearson=0.01, w_l1=0.05):
+    """Depth terms of the map-training loss (gs_localization/gs/7scenes_gs_full_dslam.py:168-184), float64:
+    w_p * min(1 - r(-m, d), 1 - r(k/(m+200), d)) + w_l1 * mean|d*mask - gt*mask|, mask = gt > 0.
+    r is torchmetrics' pearson_corrcoef in the reference — a third-party dependency that is neither vendored nor
+    version-pinned there and is absent from this image: PARITY UNPINNED against it; restated from the definition of
+    the Pearson coefficient and checked against np.corrcoef and torch autograd in tests/test_losses.py."""
+    d = np.asarray(depth, np.float64).ravel()
+    n = d.size
+    loss, grad = 0.0, np.zeros(n)
+    if pseudo is not None:
+        m32 = np.asarray(pseudo, np.float32).ravel()
+        cands = [-m32.astype(np.float64), (np.float32(inv_numerator) / (m32 + np.float32(200.0))).astype(np.float64)]
+        dc = d - d.mean()
+        Sdd = (dc * dc).sum()
+        best = None
+        for x in cands:
+            xc = x - x.mean()
+            r = (xc * dc).sum() / np.sqrt((xc * xc).sum() * Sdd)
+            if best is None or (1 - r) < best[0]:
+                best = (1 - r, r, xc)
+        l, r, xc = best
+        loss += w_pearson * l
+        grad += -w_pearson * (xc / np.sqrt((xc * xc).sum() * Sdd) - r * dc / Sdd)
+    if gt is not None:
+        g = np.asarray(gt, np.float64).ravel()
+        mask = np.asarray(gt, np.float32).ravel() > 0
+        diff = (d - g) * mask
+        loss += w_l1 * np.abs(diff).mean()
+        grad += w_l1 * np.sign(diff) / n
+    return loss, grad.reshape(np.shape(depth))

@@ -166,3 +166,50 @@ def test_grad_mask_matches_reference_golden():
     assert np.abs(gv.numpy() - g["grad_v"]).max() < 1e-6 and np.abs(gh.numpy() - g["grad_h"]).max() < 1e-6
     assert np.array_equal(tracking.compute_grad_mask(img, 1.1, "tum").numpy(), g["tum"])
     assert np.array_equal(tracking.compute_grad_mask(img, 4, "replica").numpy(), g["replica"])
+
+
+# ----------------------------------------------------------- depth terms of the training loss (7scenes_gs_full_dslam.py:168-184)
+def _depth_case(seed, n=(48, 64)):
+    rng = np.random.default_rng(seed)
+    gt = (1.0 + 3.0 * rng.random(n)).astype(np.float32)
+    gt[rng.random(n) < 0.15] = 0.0
+    true = np.where(gt > 0, gt, 2.0)
+    pseudo = (800.0 / true + 20.0 * rng.standard_normal(n)).astype(np.float32)      # MiDaS-like inverse depth
+    depth = (true + 0.2 * rng.standard_normal(n)).astype(np.float32)
+    return depth, pseudo, gt
+
+
+def test_depth_loss_oracle_vs_corrcoef_and_autograd():
+    import torch
+    depth, pseudo, gt = _depth_case(0)
+    loss, grad = loss_oracle.depth_loss_grad(depth, pseudo, gt)
+    d64 = depth.astype(np.float64).ravel()
+    r1 = np.corrcoef(-pseudo.astype(np.float64).ravel(), d64)[0, 1]
+    r2 = np.corrcoef((np.float32(1000) / (pseudo + np.float32(200))).astype(np.float64).ravel(), d64)[0, 1]
+    l1 = np.abs((d64 - gt.ravel()) * (gt.ravel() > 0)).mean()
+    assert abs(loss - (0.01 * min(1 - r1, 1 - r2) + 0.05 * l1)) < 1e-12
+    # autograd of the same expression written with torch.corrcoef
+    d = torch.from_numpy(d64).requires_grad_(True)
+    m = torch.from_numpy(pseudo.astype(np.float64).ravel())
+    g = torch.from_numpy(gt.astype(np.float64).ravel())
+    cands = [1 - torch.corrcoef(torch.stack([-m, d]))[0, 1],
+             1 - torch.corrcoef(torch.stack([torch.from_numpy((np.float32(1000) / (pseudo + np.float32(200))).astype(np.float64).ravel()), d]))[0, 1]]
+    mask = (g > 0).double()
+    L = 0.01 * min(cands) + 0.05 * (d * mask - g * mask).abs().mean()
+    L.backward()
+    assert abs(L.item() - loss) < 1e-12
+    assert np.abs(d.grad.numpy() - grad.ravel()).max() <= 1e-9 * np.abs(grad).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_pseudo,use_gt,n", [(True, True, (480, 640)), (True, False, (33, 7)), (False, True, (5, 5)), (True, True, (840, 1297))])
+def test_cuda_depth_loss_matches_oracle(use_pseudo, use_gt, n):
+    import torch
+    from gs_localization_b200 import losses
+    depth, pseudo, gt = _depth_case(3, n)
+    want_loss, want = loss_oracle.depth_loss_grad(depth, pseudo if use_pseudo else None, gt if use_gt else None)
+    d = torch.from_numpy(depth).cuda().requires_grad_(True)
+    L = losses.depth_loss(d, torch.from_numpy(pseudo).cuda() if use_pseudo else None, torch.from_numpy(gt).cuda() if use_gt else None)
+    L.backward()
+    assert abs(L.item() - want_loss) < 1e-6
+    assert np.abs(d.grad.cpu().numpy() - want).max() <= 1e-4 * np.abs(want).max()
