@@ -709,6 +709,17 @@ int gsr_l1_ssim_loss_grad(const float* image, const float* target, int channels,
   return GSR_OK;
 }
 
+size_t gsr_knn_workspace_bytes(long long n_points) { return n_points > 0 ? knn_workspace_bytes(n_points) : 0; }
+
+int gsr_dist2_knn3(const float* points, long long n_points, float* mean_dists, char* workspace, void* stream_) {
+  if (n_points < 0 || n_points >= (1ll << 30)) return fail(GSR_ERR_INVALID_ARGUMENT, "n_points must be in [0, 2^30)");
+  if (n_points == 0) return GSR_OK;
+  if (!points || !mean_dists || !workspace) return fail(GSR_ERR_INVALID_ARGUMENT, "null pointer");
+  launch_dist2_knn3(points, n_points, mean_dists, workspace, (cudaStream_t)stream_);
+  GSR_STAGE("dist2_knn3", 0, (cudaStream_t)stream_);
+  return GSR_OK;
+}
+
 int gsr_depth_loss_grad(const float* depth, const float* pseudo_depth, const float* gt_depth, long long n, float inv_numerator,
                         float pearson_weight, float l1_weight, float* loss_accum, float* dL_ddepth, double* scratch, void* stream_) {
   if (n <= 0 || n >= (1ll << 31) || !depth || !loss_accum || !dL_ddepth || !scratch) return fail(GSR_ERR_INVALID_ARGUMENT, "bad arguments");

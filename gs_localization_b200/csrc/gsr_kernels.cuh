@@ -161,6 +161,10 @@ void launch_pose_adam_step(const float* dL_dtau, float* adam_m, float* adam_v, f
 void launch_l1_ssim_loss_grad(const float* img1, const float* img2, int C, int H, int W, float lambda, float* loss, float* dL_dimg1,
                               float* scratch, cudaStream_t stream);
 
+// ---- simple-knn (knn.cu)
+size_t knn_workspace_bytes(long long P);
+int launch_dist2_knn3(const float* points, long long P, float* mean_dists, char* workspace, cudaStream_t stream);
+
 // depth terms of the map-training loss; scratch holds 9 doubles
 void launch_depth_loss_grad(const float* depth, const float* pseudo, const float* gt, int n, float k, float w_pearson, float w_l1,
                             float* loss, float* dL_ddepth, double* scratch, cudaStream_t stream);

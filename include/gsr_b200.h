@@ -195,6 +195,12 @@ GSR_API int gsr_l1_loss_grad(const float* image, const float* target, float* dL_
  * 11x11 Gaussian window (sigma 1.5), zero padding, per channel.  scratch: 3*C*H*W + 2 floats. */
 GSR_API int gsr_l1_ssim_loss_grad(const float* image, const float* target, int channels, int height, int width,
                                   float lambda_dssim, float* loss_accum, float* dL_dimage, float* scratch, void* stream);
+/* distCUDA2 of simple-knn (gaussian_splatting/submodules/simple-knn/spatial.cu:15-26, simple_knn.cu:185-221):
+ * mean_dists[i] = mean of the squared distances from points[i] to its three nearest other points (exact search;
+ * FLT_MAX stands in for missing neighbours when n_points < 4, as in the reference).  points: [n,3] float32.
+ * workspace: gsr_knn_workspace_bytes(n) bytes of device memory. */
+GSR_API size_t gsr_knn_workspace_bytes(long long n_points);
+GSR_API int gsr_dist2_knn3(const float* points, long long n_points, float* mean_dists, char* workspace, void* stream);
 /* Depth terms of the map-training loss (gs_localization/gs/7scenes_gs_full_dslam.py:168-184) and their gradient:
  *   *loss_accum += pearson_weight * min(1 - r(-m, d), 1 - r(inv_numerator / (m + 200), d))
  *                + l1_weight * mean|d*mask - gt*mask|,  mask = gt_depth > 0

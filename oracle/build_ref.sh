@@ -23,10 +23,42 @@ OUT="$HERE/_ref"
 PKG="$OUT/diff_gaussian_rasterization"
 OBJ="$OUT/obj"
 
+KNN="${GSR_REFERENCE_ROOT:-/root/reference}/gaussian_splatting/submodules/simple-knn"
+KPKG="$OUT/simple_knn"
+
+# simple-knn (distCUDA2: mean squared distance to the 3 nearest neighbours, used by create_from_pcd):
+# three translation units (its setup.py), plus -include cfloat for FLT_MAX on a modern toolchain.
+build_knn() {
+  [ -d "$KNN" ] || return 0
+  if [ -f "$KPKG/_C.so" ] && [ "$KPKG/_C.so" -nt "$KNN/simple_knn.cu" ] && [ "${1:-}" != "--force" ]; then
+    echo "build_ref.sh: $KPKG/_C.so up to date"; return 0
+  fi
+  mkdir -p "$KPKG" "$OBJ/knn"
+  local PY=python TORCH_DIR PYINC
+  TORCH_DIR="$($PY -c 'import os, torch; print(os.path.dirname(torch.__file__))')"
+  PYINC="$($PY -c 'import sysconfig; print(sysconfig.get_paths()["include"])')"
+  local FLAGS=(-std=c++17 -O3 --expt-relaxed-constexpr -Xcompiler -fPIC -include cstdint -include cfloat
+               -gencode arch=compute_100a,code=sm_100a -lineinfo
+               -DTORCH_EXTENSION_NAME=_C -DTORCH_API_INCLUDE_EXTENSION_H -D_GLIBCXX_USE_CXX11_ABI=1 -I"$KNN"
+               -isystem "$TORCH_DIR/include" -isystem "$TORCH_DIR/include/torch/csrc/api/include" -isystem "$PYINC" -w)
+  nvcc "${FLAGS[@]}" -c "$KNN/simple_knn.cu" -o "$OBJ/knn/simple_knn.o" &
+  nvcc "${FLAGS[@]}" -c "$KNN/spatial.cu" -o "$OBJ/knn/spatial.o" &
+  nvcc "${FLAGS[@]}" -x cu -c "$KNN/ext.cpp" -o "$OBJ/knn/ext.o" &
+  wait
+  nvcc -shared -o "$KPKG/_C.so" "$OBJ/knn/simple_knn.o" "$OBJ/knn/spatial.o" "$OBJ/knn/ext.o" \
+       -L"$TORCH_DIR/lib" -lc10 -lc10_cuda -ltorch_cpu -ltorch_cuda -ltorch -ltorch_python \
+       -Xlinker -rpath -Xlinker "$TORCH_DIR/lib"
+  : > "$KPKG/__init__.py"
+  cuobjdump -sass "$OBJ/knn/simple_knn.o" > "$OUT/simple_knn.sass" 2>/dev/null || true
+  echo "build_ref.sh: built $KPKG/_C.so"
+}
+
 if [ ! -d "$REF" ]; then
   echo "build_ref.sh: reference sources not present at $REF — keeping any prebuilt oracle/_ref" >&2
   exit 0
 fi
+mkdir -p "$OUT/obj"
+build_knn "${1:-}"
 if [ -f "$PKG/_C.so" ] && [ "$PKG/_C.so" -nt "$REF/cuda_rasterizer/backward.cu" ] && [ "${1:-}" != "--force" ]; then
   echo "build_ref.sh: $PKG/_C.so up to date"
   exit 0
