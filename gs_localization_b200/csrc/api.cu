@@ -709,6 +709,42 @@ int gsr_l1_ssim_loss_grad(const float* image, const float* target, int channels,
   return GSR_OK;
 }
 
+int gsr_map_adam_step(int P, int M, int do_stats, int do_adam, const int* steps, const float* lrs, float beta1, float beta2, float eps,
+                      float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                      float* opacity_act, float* scaling_act, float* rotation_act, const float* dL_dmeans2D, const int* radii,
+                      float* max_radii2D, float* xyz_gradient_accum, float* denom, void* stream_) {
+  if (P < 0 || M < 1) return fail(GSR_ERR_INVALID_ARGUMENT, "bad P/M");
+  if (P == 0) return GSR_OK;
+  MapStepParams s{};
+  s.P = P, s.M = M, s.do_stats = do_stats, s.do_adam = do_adam;
+  if (do_stats && (!dL_dmeans2D || !radii || !max_radii2D || !xyz_gradient_accum || !denom))
+    return fail(GSR_ERR_INVALID_ARGUMENT, "statistics need dL_dmeans2D, radii, max_radii2D, xyz_gradient_accum, denom");
+  s.g_means2D = dL_dmeans2D, s.radii = radii, s.max_radii2D = max_radii2D, s.xyz_gradient_accum = xyz_gradient_accum, s.denom = denom;
+  if (do_adam) {
+    if (!steps || !lrs || !params || !grads || !exp_avg || !exp_avg_sq) return fail(GSR_ERR_INVALID_ARGUMENT, "adam needs steps, lrs and the tensor tables");
+    for (int i = 0; i < 6; i++)
+      if (lrs[i] >= 0.f && steps[i] < 1) return fail(GSR_ERR_INVALID_ARGUMENT, "steps[%d] must be >= 1", i);
+    float lr[6];
+    for (int i = 0; i < 6; i++) lr[i] = lrs[i];
+    // order: xyz, f_dc+f_rest (one tensor), opacity, scaling, rotation
+    for (int t = 0; t < 5; t++) {
+      const bool used = t == 1 ? (lr[1] >= 0.f || lr[2] >= 0.f) : lr[t == 0 ? 0 : t + 1] >= 0.f;
+      if (used && (!params[t] || !grads[t] || !exp_avg[t] || !exp_avg_sq[t])) return fail(GSR_ERR_INVALID_ARGUMENT, "null tensor in group %d", t);
+    }
+    if ((lr[3] >= 0.f && !opacity_act) || (lr[4] >= 0.f && !scaling_act) || (lr[5] >= 0.f && !rotation_act))
+      return fail(GSR_ERR_INVALID_ARGUMENT, "activation outputs missing");
+    s.xyz = params[0], s.features = params[1], s.opacity = params[2], s.scaling = params[3], s.rotation = params[4];
+    s.g_xyz = grads[0], s.g_features = grads[1], s.g_opacity = grads[2], s.g_scaling = grads[3], s.g_rotation = grads[4];
+    s.m_xyz = exp_avg[0], s.m_features = exp_avg[1], s.m_opacity = exp_avg[2], s.m_scaling = exp_avg[3], s.m_rotation = exp_avg[4];
+    s.v_xyz = exp_avg_sq[0], s.v_features = exp_avg_sq[1], s.v_opacity = exp_avg_sq[2], s.v_scaling = exp_avg_sq[3], s.v_rotation = exp_avg_sq[4];
+    s.lr_xyz = lr[0], s.lr_f_dc = lr[1], s.lr_f_rest = lr[2], s.lr_opacity = lr[3], s.lr_scaling = lr[4], s.lr_rotation = lr[5];
+    s.opacity_act = opacity_act, s.scaling_act = scaling_act, s.rotation_act = rotation_act;
+  }
+  launch_map_step(s, beta1, beta2, eps, steps, (cudaStream_t)stream_);
+  GSR_STAGE("map_adam_step", 0, (cudaStream_t)stream_);
+  return GSR_OK;
+}
+
 size_t gsr_knn_workspace_bytes(long long n_points) { return n_points > 0 ? knn_workspace_bytes(n_points) : 0; }
 
 int gsr_dist2_knn3(const float* points, long long n_points, float* mean_dists, char* workspace, void* stream_) {

@@ -161,6 +161,26 @@ void launch_pose_adam_step(const float* dL_dtau, float* adam_m, float* adam_v, f
 void launch_l1_ssim_loss_grad(const float* img1, const float* img2, int C, int H, int W, float lambda, float* loss, float* dL_dimg1,
                               float* scratch, cudaStream_t stream);
 
+// ---- optimiser side of a map-training iteration (map_step.cu); a negative learning rate skips that group
+struct MapStepParams {
+  int P, M;
+  int do_stats, do_adam;
+  // raw parameters, updated in place; features is [P,M,3] (f_dc = coefficient 0, f_rest = the others)
+  float *xyz, *features, *opacity, *scaling, *rotation;
+  // gradients w.r.t. what the rasterizer consumed (activated opacity / scales / rotations)
+  const float *g_xyz, *g_features, *g_opacity, *g_scaling, *g_rotation;
+  float *m_xyz, *m_features, *m_opacity, *m_scaling, *m_rotation;
+  float *v_xyz, *v_features, *v_opacity, *v_scaling, *v_rotation;
+  float lr_xyz, lr_f_dc, lr_f_rest, lr_opacity, lr_scaling, lr_rotation;
+  // refreshed activations for the next render
+  float *opacity_act, *scaling_act, *rotation_act;
+  // densification statistics
+  const float* g_means2D;
+  const int* radii;
+  float *max_radii2D, *xyz_gradient_accum, *denom;
+};
+void launch_map_step(const MapStepParams& s, float beta1, float beta2, float eps, const int* steps, cudaStream_t stream);
+
 // ---- simple-knn (knn.cu)
 size_t knn_workspace_bytes(long long P);
 int launch_dist2_knn3(const float* points, long long P, float* mean_dists, char* workspace, cudaStream_t stream);

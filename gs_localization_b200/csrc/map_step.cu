@@ -1,0 +1,154 @@
+// Optimiser side of a LoGS map-training iteration, fused (gs_localization/gs/7scenes_gs_full_dslam.py:225-242 with
+// gaussian_splatting/scene/gaussian_model.py:44-58,96-115,152-168,405-407):
+//
+//   * chain rule through the parameter activations (sigmoid opacity, exp scaling, normalised rotation), which the
+//     reference leaves to autograd as ~10 element-wise kernels over P-sized tensors;
+//   * torch.optim.Adam (betas 0.9/0.999, eps 1e-15, one learning rate per parameter group) on all six groups;
+//   * re-activation of the updated parameters into the buffers the rasterizer reads next iteration;
+//   * the densification statistics (max_radii2D, xyz_gradient_accum, denom over the visible set).
+//
+// Two launches: one thread per Gaussian for the 11 geometric scalars + statistics, one float4 per thread for the
+// SH features, whose DC and higher-order coefficients live in ONE [P,M,3] tensor (no torch.cat per render, no split
+// of its gradient) with the group's learning rate chosen per coefficient.  HBM-bound: 7 passes over 59 floats per
+// Gaussian (read p, g, m, v; write p, m, v) — 1.65 KB per Gaussian at SH degree 3.
+#include <algorithm>
+#include <cmath>
+
+#include "gsr_kernels.cuh"
+
+namespace gsr {
+
+struct AdamScalars {
+  float w1;           // 1 - beta1   (exp_avg.lerp_(grad, 1 - beta1))
+  float b2, w2;       // beta2, 1 - beta2
+  float eps;
+  // per group (xyz, f_dc, f_rest, opacity, scaling, rotation): torch keeps one step counter per parameter, and a group
+  // whose parameter was just replaced (reset_opacity) misses a step
+  float inv_bc1[6];   // 1 / (1 - beta1^t)
+  float bc2_sqrt[6];  // sqrt(1 - beta2^t)
+};
+
+__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, float lr, const AdamScalars& a, int group) {
+  m = m + a.w1 * (g - m);
+  v = v * a.b2 + a.w2 * g * g;
+  const float denom = sqrtf(v) / a.bc2_sqrt[group] + a.eps;
+  return p - (lr * a.inv_bc1[group]) * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) map_geometry_step_kernel(MapStepParams s, AdamScalars a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.P) return;
+  if (s.do_stats) {
+    const int r = s.radii[i];
+    if (r > 0) {
+      s.max_radii2D[i] = fmaxf(s.max_radii2D[i], (float)r);
+      const float gx = s.g_means2D[3 * (size_t)i], gy = s.g_means2D[3 * (size_t)i + 1];
+      s.xyz_gradient_accum[i] += sqrtf(gx * gx + gy * gy);
+      s.denom[i] += 1.f;
+    }
+  }
+  if (!s.do_adam) return;
+  if (s.lr_xyz >= 0.f) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const size_t e = 3 * (size_t)i + c;
+      float m = s.m_xyz[e], v = s.v_xyz[e];
+      s.xyz[e] = adam_update(s.xyz[e], s.g_xyz[e], m, v, s.lr_xyz, a, 0);
+      s.m_xyz[e] = m, s.v_xyz[e] = v;
+    }
+  }
+  if (s.lr_opacity >= 0.f) {
+    const float raw = s.opacity[i];
+    const float sig = 1.f / (1.f + expf(-raw));
+    float m = s.m_opacity[i], v = s.v_opacity[i];
+    const float nraw = adam_update(raw, s.g_opacity[i] * sig * (1.f - sig), m, v, s.lr_opacity, a, 3);
+    s.opacity[i] = nraw, s.m_opacity[i] = m, s.v_opacity[i] = v;
+    s.opacity_act[i] = 1.f / (1.f + expf(-nraw));
+  }
+  if (s.lr_scaling >= 0.f) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const size_t e = 3 * (size_t)i + c;
+      const float raw = s.scaling[e];
+      float m = s.m_scaling[e], v = s.v_scaling[e];
+      const float nraw = adam_update(raw, s.g_scaling[e] * expf(raw), m, v, s.lr_scaling, a, 4);
+      s.scaling[e] = nraw, s.m_scaling[e] = m, s.v_scaling[e] = v;
+      s.scaling_act[e] = expf(nraw);
+    }
+  }
+  if (s.lr_rotation >= 0.f) {
+    const float4 q = reinterpret_cast<const float4*>(s.rotation)[i];
+    const float4 g = reinterpret_cast<const float4*>(s.g_rotation)[i];
+    float4 m = reinterpret_cast<float4*>(s.m_rotation)[i], v = reinterpret_cast<float4*>(s.v_rotation)[i];
+    // backward of F.normalize (eps 1e-12): (g - n (n.g)) / max(|q|, eps)
+    const float len = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+    const float4 n = make_float4(q.x / len, q.y / len, q.z / len, q.w / len);
+    const float ng = n.x * g.x + n.y * g.y + n.z * g.z + n.w * g.w;
+    float4 nq;
+    nq.x = adam_update(q.x, (g.x - n.x * ng) / len, m.x, v.x, s.lr_rotation, a, 5);
+    nq.y = adam_update(q.y, (g.y - n.y * ng) / len, m.y, v.y, s.lr_rotation, a, 5);
+    nq.z = adam_update(q.z, (g.z - n.z * ng) / len, m.z, v.z, s.lr_rotation, a, 5);
+    nq.w = adam_update(q.w, (g.w - n.w * ng) / len, m.w, v.w, s.lr_rotation, a, 5);
+    reinterpret_cast<float4*>(s.rotation)[i] = nq;
+    reinterpret_cast<float4*>(s.m_rotation)[i] = m;
+    reinterpret_cast<float4*>(s.v_rotation)[i] = v;
+    const float nl = fmaxf(sqrtf(nq.x * nq.x + nq.y * nq.y + nq.z * nq.z + nq.w * nq.w), 1e-12f);
+    reinterpret_cast<float4*>(s.rotation_act)[i] = make_float4(nq.x / nl, nq.y / nl, nq.z / nl, nq.w / nl);
+  }
+}
+
+// SH features [P,M,3]: coefficient 0 is the f_dc group, 1..M-1 the f_rest group
+__global__ void __launch_bounds__(256) map_features_step_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                                                                float4* __restrict__ v, size_t n, int floats_per_gaussian, float lr_dc,
+                                                                float lr_rest, AdamScalars a) {
+  const size_t n4 = n >> 2;
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {   // tail when P*M*3 is not a multiple of 4 (SH degree 0 or 2)
+    const size_t e = 4 * n4 + threadIdx.x;
+    const float lr = (int)(e % (size_t)floats_per_gaussian) < 3 ? lr_dc : lr_rest;
+    float* ps = reinterpret_cast<float*>(p);
+    float* ms = reinterpret_cast<float*>(m);
+    float* vs = reinterpret_cast<float*>(v);
+    if (lr >= 0.f) ps[e] = adam_update(ps[e], reinterpret_cast<const float*>(g)[e], ms[e], vs[e], lr, a, (int)(e % (size_t)floats_per_gaussian) < 3 ? 1 : 2);
+  }
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (size_t)gridDim.x * blockDim.x) {
+    const int within = (int)((4 * t) % (size_t)floats_per_gaussian);
+    float4 pp = p[t], mm = m[t], vv = v[t];
+    const float4 gg = g[t];
+    float* pa = &pp.x;
+    float* ma = &mm.x;
+    float* va = &vv.x;
+    const float* ga = &gg.x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const bool dc = ((within + k) % floats_per_gaussian) < 3;
+      const float lr = dc ? lr_dc : lr_rest;
+      if (lr >= 0.f) pa[k] = adam_update(pa[k], ga[k], ma[k], va[k], lr, a, dc ? 1 : 2);
+    }
+    p[t] = pp, m[t] = mm, v[t] = vv;
+  }
+}
+
+void launch_map_step(const MapStepParams& s, float beta1, float beta2, float eps, const int* steps, cudaStream_t stream) {
+  if (s.P <= 0) return;
+  AdamScalars a;
+  a.w1 = (float)(1.0 - (double)beta1);
+  a.b2 = beta2;
+  a.w2 = (float)(1.0 - (double)beta2);
+  a.eps = eps;
+  for (int g = 0; g < 6; g++) {
+    const double t = (double)(steps ? std::max(steps[g], 1) : 1);
+    a.inv_bc1[g] = (float)(1.0 / (1.0 - pow((double)beta1, t)));
+    a.bc2_sqrt[g] = (float)sqrt(1.0 - pow((double)beta2, t));
+  }
+  map_geometry_step_kernel<<<(s.P + 255) / 256, 256, 0, stream>>>(s, a);
+  count_launch();
+  if (s.do_adam && s.features && (s.lr_f_dc >= 0.f || s.lr_f_rest >= 0.f)) {
+    const size_t n = (size_t)s.P * s.M * 3;
+    const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)148 * 16);
+    map_features_step_kernel<<<blocks, 256, 0, stream>>>((float4*)s.features, (const float4*)s.g_features, (float4*)s.m_features,
+                                                         (float4*)s.v_features, n, s.M * 3, s.lr_f_dc, s.lr_f_rest, a);
+    count_launch();
+  }
+}
+
+}  // namespace gsr

@@ -195,6 +195,24 @@ GSR_API int gsr_l1_loss_grad(const float* image, const float* target, float* dL_
  * 11x11 Gaussian window (sigma 1.5), zero padding, per channel.  scratch: 3*C*H*W + 2 floats. */
 GSR_API int gsr_l1_ssim_loss_grad(const float* image, const float* target, int channels, int height, int width,
                                   float lambda_dssim, float* loss_accum, float* dL_dimage, float* scratch, void* stream);
+/* Optimiser side of one map-training iteration, fused (gs_localization/gs/7scenes_gs_full_dslam.py:225-242;
+ * gaussian_splatting/scene/gaussian_model.py:44-58 activations, :152-168 Adam groups, :405-407 statistics):
+ *   do_stats: over the visible set (radii > 0): max_radii2D = max(., radii); xyz_gradient_accum += |dL_dmeans2D.xy|;
+ *             denom += 1.
+ *   do_adam : torch.optim.Adam, step numbers steps[6] (>= 1, one per group like torch's per-parameter counters), on the five tensors
+ *             params[] = { xyz [P,3], features [P,M,3], opacity [P] (logit), scaling [P,3] (log), rotation [P,4] }
+ *             with grads[] taken w.r.t. what the rasterizer consumed (activated opacity / scales / rotations; the
+ *             chain rule through sigmoid / exp / normalize is applied here), state exp_avg[] / exp_avg_sq[], and
+ *             lrs[6] = { xyz, f_dc, f_rest, opacity, scaling, rotation } (f_dc = SH coefficient 0 of `features`,
+ *             f_rest the others).  A negative learning rate leaves that group untouched (the reference skips groups
+ *             whose parameter was just replaced, e.g. after reset_opacity).  The activated copies
+ *             opacity_act [P], scaling_act [P,3], rotation_act [P,4] are refreshed for the next render.
+ * All tables hold device pointers; the tables themselves are host arrays. */
+GSR_API int gsr_map_adam_step(int P, int M, int do_stats, int do_adam, const int* steps, const float* lrs, float beta1, float beta2,
+                              float eps, float* const* params, const float* const* grads, float* const* exp_avg,
+                              float* const* exp_avg_sq, float* opacity_act, float* scaling_act, float* rotation_act,
+                              const float* dL_dmeans2D, const int* radii, float* max_radii2D, float* xyz_gradient_accum,
+                              float* denom, void* stream);
 /* distCUDA2 of simple-knn (gaussian_splatting/submodules/simple-knn/spatial.cu:15-26, simple_knn.cu:185-221):
  * mean_dists[i] = mean of the squared distances from points[i] to its three nearest other points (exact search;
  * FLT_MAX stands in for missing neighbours when n_points < 4, as in the reference).  points: [n,3] float32.
