@@ -264,8 +264,19 @@ def run_gpu_arm(args, rank, world, local_rank):
         for p_ in params:
             p_.grad = None
         consumed[slot].record(torch.cuda.current_stream(device))
-        return float(loss.item())   # device -> host read of the step's result
+        # device -> host read of the step's result: asynchronous copy into pinned memory, consumed one step later
+        # (the usual logging pattern of a training loop) so that the host can queue step i+1 behind step i
+        loss_host[slot].copy_(loss.detach(), non_blocking=True)
+        loss_ready[slot].record(torch.cuda.current_stream(device))
+        got = None
+        if not first:
+            loss_ready[1 - slot].synchronize()
+            got = float(loss_host[1 - slot])
+        return got
 
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    losses_read = 0
     nw = max(3, args.warmup // 2)
     for i in range(nw):
         step_e2e(i, first=(i == 0))
@@ -274,9 +285,12 @@ def run_gpu_arm(args, rank, world, local_rank):
         torch.distributed.barrier()
     t0 = time.perf_counter()
     for i in range(nw, nw + args.steps):
-        step_e2e(i)
+        losses_read += step_e2e(i) is not None
+    loss_ready[(nw + args.steps - 1) % 2].synchronize()       # the last step's loss
+    last_loss = float(loss_host[(nw + args.steps - 1) % 2])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    assert losses_read == args.steps and last_loss == last_loss
     clocks = sampler.stop()   # sampled across both timed regions (device-resident and end-to-end)
     if world > 1:
         torch.distributed.barrier()

@@ -68,5 +68,34 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+BINDING_SRC = os.path.join(HERE, "binding", "torch_binding.cpp")
+BINDING = os.path.join(HERE, "_gsr_torch.so")
+
+
+def build_binding(force: bool = False) -> str:
+    """The compiled torch-facing glue (binding/torch_binding.cpp -> _gsr_torch.so): host C++ only, linked against
+    libgsr_b200.so (found next to it through $ORIGIN) and the torch libraries of the running interpreter."""
+    build(force=False)
+    deps = [BINDING_SRC, os.path.join(HERE, "..", "include", "gsr_b200.h"), __file__]
+    if not force and os.path.exists(BINDING) and all(os.path.getmtime(d) <= os.path.getmtime(BINDING) for d in deps):
+        return BINDING
+    import sysconfig
+
+    import torch
+    tdir = os.path.dirname(torch.__file__)
+    cxx = FLAGS[-1]
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-w",
+           "-DTORCH_EXTENSION_NAME=_gsr_torch", "-DTORCH_API_INCLUDE_EXTENSION_H",
+           f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           "-isystem", os.path.join(tdir, "include"), "-isystem", os.path.join(tdir, "include", "torch", "csrc", "api", "include"),
+           "-isystem", sysconfig.get_paths()["include"], "-isystem", "/usr/local/cuda/include",
+           BINDING_SRC, "-o", BINDING, "-L" + HERE, "-l:libgsr_b200.so", "-L" + os.path.join(tdir, "lib"),
+           "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python",
+           "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + os.path.join(tdir, "lib")]
+    subprocess.check_call(cmd)
+    return BINDING
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_binding(force="--force" in sys.argv))

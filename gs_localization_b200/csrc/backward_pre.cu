@@ -16,6 +16,8 @@
 // thread forms its 6-vector contribution to dL/d(rho, theta) for the left perturbation
 // T_w2c <- exp(tau) T_w2c (gs_localization/pipelines/tools/pose_utils.py:90-122), the CTA
 // reduces it with shuffles and issues 6 atomics.
+#include <algorithm>
+
 #include "gsr_kernels.cuh"
 
 namespace gsr {

@@ -16,6 +16,22 @@ from .. import _lib
 
 NUM_CHANNELS = 3
 
+# Two equivalent bindings over the same C ABI: the compiled one (binding/torch_binding.cpp -> _gsr_torch.so, the
+# counterpart of the reference's rasterize_points.cu glue; ~3x less host time per call) and the ctypes one below.
+# GSR_BINDING=ctypes|compiled forces one; by default the compiled module is used when it has been built.
+import os as _os
+
+_B = None
+if _os.environ.get("GSR_BINDING", "compiled") != "ctypes":
+    try:
+        _lib.load()                      # resolves libgsr_b200.so first (and fails loudly if it is missing)
+        from .. import _gsr_torch as _B  # noqa: F401
+    except ImportError:
+        if _os.environ.get("GSR_BINDING") == "compiled":
+            raise
+        _B = None
+_NEED_BITS = dict(means3D=0, means2D=1, sh=2, colors=3, opacity=4, scales=5, rotations=6, cov3D=7)
+
 
 def _ptr(t: torch.Tensor):
     """Device pointer of a contiguous float/int tensor; None for the reference's empty placeholders."""
@@ -76,6 +92,13 @@ def _make_alloc(name):
 _ALLOC_GEOM, _ALLOC_BINNING, _ALLOC_IMG = _make_alloc("geom"), _make_alloc("binning"), _make_alloc("img")
 
 
+_EMPTY = torch.Tensor([])
+
+
+def _t(x):
+    return _EMPTY if x is None else x
+
+
 def _require_cuda(means3D):
     if not means3D.is_cuda:
         raise RuntimeError("gs_localization_b200: tensors must be CUDA tensors (no CPU fallback exists)")
@@ -87,6 +110,13 @@ def _forward_impl(background, means3D, colors, opacity, scales, rotations, scale
     if means3D.ndimension() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:57-59
     _require_cuda(means3D)
+    if _B is not None:
+        try:
+            return _B.forward(background, means3D, _t(colors), opacity, _t(scales), _t(rotations), float(scale_modifier),
+                              _t(cov3D_precomp), viewmatrix, projmatrix, float(tan_fovx), float(tan_fovy), int(image_height),
+                              int(image_width), _t(sh), int(degree), campos, bool(prefiltered), bool(debug), bool(want_n_touched))
+        except RuntimeError as ex:
+            raise _lib.GsrError(str(ex)) from None
     lib = _lib.load()
     dev = means3D.device
     P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
@@ -138,6 +168,21 @@ def _backward_impl(background, means3D, radii, colors, scales, rotations, scale_
                    geomBuffer, R, binningBuffer, imageBuffer, alpha, debug, projmatrix_raw=None, want_pose=False,
                    needs=None):
     _require_cuda(means3D)
+    if _B is not None:
+        mask = 0xff
+        if needs:
+            mask = 0
+            for k, bit in _NEED_BITS.items():
+                if needs.get(k, True):
+                    mask |= 1 << bit
+        try:
+            res = _B.backward(background, means3D, radii, _t(colors), _t(scales), _t(rotations), float(scale_modifier),
+                              _t(cov3D_precomp), viewmatrix, projmatrix, float(tan_fovx), float(tan_fovy), dL_dout_color,
+                              dL_dout_depth, dL_dout_alpha, _t(sh), int(degree), campos, geomBuffer, int(R), binningBuffer,
+                              imageBuffer, alpha, bool(debug), _t(projmatrix_raw), bool(want_pose), mask)
+        except RuntimeError as ex:
+            raise _lib.GsrError(str(ex)) from None
+        return res[:8], res[8]
     lib = _lib.load()
     dev = means3D.device
     P = int(means3D.size(0))
@@ -192,6 +237,8 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
 def mark_visible(means3D, viewmatrix, projmatrix):
     """markVisible (rasterize_points.cu:208-227): bool[P], True where view-space z > 0.2."""
     _require_cuda(means3D)
+    if _B is not None:
+        return _B.mark_visible(means3D, viewmatrix, projmatrix)
     lib = _lib.load()
     dev = means3D.device
     P = int(means3D.size(0))

@@ -114,3 +114,22 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.GsrError, match="no CPU / PyTorch fallback"):
         _lib.load()
+
+
+def test_compiled_binding_loads_and_matches_abi():
+    """binding/torch_binding.cpp: the compiled `_C` glue links the same C-ABI library (no compute without a GPU)."""
+    from gs_localization_b200 import _lib, build
+    build.build_binding()
+    lib = _lib.load()
+    from gs_localization_b200 import _gsr_torch
+    assert _gsr_torch.abi_version() == lib.gsr_abi_version()
+    for name in ("forward", "backward", "mark_visible"):
+        assert callable(getattr(_gsr_torch, name))
+    import gs_localization_b200.diff_gaussian_rasterization._C as C
+    assert C._B is _gsr_torch
+    import pytest
+    import torch
+    with pytest.raises(RuntimeError):                      # CPU tensors: loud failure, not a fallback
+        C.rasterize_gaussians(torch.zeros(3), torch.zeros(4, 3), torch.Tensor([]), torch.zeros(4, 1), torch.zeros(4, 3),
+                              torch.zeros(4, 4), 1.0, torch.Tensor([]), torch.eye(4), torch.eye(4), 1.0, 1.0, 8, 8,
+                              torch.zeros(4, 1, 3), 0, torch.zeros(3), False, False)
