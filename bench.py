@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline", choices=list(syn.CONFIGS))
-    ap.add_argument("--queries", type=int, default=6, help="pose-refinement queries per rank for the queries/s figure (ours only)")
+    ap.add_argument("--queries", type=int, default=12, help="pose-refinement queries per rank for the queries/s figure (ours only)")
     ap.add_argument("--query-iters", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-split", action="store_true")

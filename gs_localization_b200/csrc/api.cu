@@ -69,6 +69,14 @@ char* carve_binning(char* base, long long cap, BinningView& b, bool global_path 
     p += sort_temp_bytes(cap, sort_passes(sort_end_bit(W, H)));
     b.comp = nullptr;
   }
+  b.units = nullptr, b.ckpt = nullptr, b.units_off = b.ckpt_off = 0;
+  if (W > 0 && H > 0) {
+    const size_t tiles = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+    const size_t nu = max_units(cap, tiles);
+    carve(p, b.units, nu);
+    carve(p, b.ckpt, nu * CKPT_FLOATS);
+    b.units_off = (size_t)((char*)b.units - base), b.ckpt_off = (size_t)((char*)b.ckpt - base);
+  }
   return p;
 }
 constexpr long long LOCAL_SORT_MAX = 4096;   // longest tile list the shared-memory tile sort handles (binning.cu TS_SMEM_KEYS)
@@ -162,6 +170,14 @@ struct CountHistory {
   long long R[16] = {}, longest[16] = {};
 };
 thread_local CountHistory t_hist[4];
+// Capacities are rounded up to 1/8-octave steps so that successive forwards ask the caller's allocator for a small
+// set of sizes (a caching allocator then reuses its blocks instead of growing the buffer a few percent at a time).
+long long round_capacity(long long c) {
+  if (c <= 4096) return 4096;
+  long long step = 1;
+  while ((step << 4) <= c) step <<= 1;   // step = 2^(floor(log2 c) - 3)
+  return (c + step - 1) / step * step;
+}
 void capacity_guess(int P, int W, int H, long long& cap, long long& longest) {
   static const bool disabled = getenv("GSR_NO_SPECULATION") != nullptr;   // A/B switch for measurements
   cap = longest = 0;
@@ -170,7 +186,7 @@ void capacity_guess(int P, int W, int H, long long& cap, long long& longest) {
     if (h.P == P && h.W == W && h.H == H && h.n > 0) {
       long long m = 0, l = 0;
       for (int i = 0; i < h.n; i++) m = std::max(m, h.R[i]), l = std::max(l, h.longest[i]);
-      cap = m + m / 4 + 4096;
+      cap = round_capacity(m + m / 4 + 4096);
       longest = l + l / 4;
       return;
     }
@@ -309,12 +325,12 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
   // previous call with the same (P, W, H); the host then waits for num_rendered while the GPU keeps
   // working.  If the guess was too small (kernels clamp to the capacity, nothing overruns) the tail is
   // simply re-run with the exact size.  First call / no history: the reference's order.
-  unsigned long long* bin_header = nullptr;
+  BinHeader* bin_header = nullptr;
   auto run_tail = [&](long long capacity, bool global_path) -> int {
     if (capacity > 0 && !global_path) {
       {
         StageScope ts(ST_DUPLICATE, stream);
-        launch_scatter(P, g, im.tile_cursor, bl.comp, gx, (uint32_t)capacity, bin_header, stream);
+        launch_scatter(P, g, im.tile_cursor, bl.comp, gx, BinHeader{(unsigned long long)capacity, bl.units_off, bl.ckpt_off}, bin_header, stream);
       }
       GSR_STAGE("scatter", debug, stream);
       {
@@ -337,7 +353,7 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
       {
         StageScope ts(ST_DUPLICATE, stream);
         sort_temp_reset(bl.sort_temp, capacity, passes, stream);
-        launch_emit_ordered(P, g, keys[0], vals[0], gx, (uint32_t)capacity, bin_header, stream);
+        launch_emit_ordered(P, g, keys[0], vals[0], gx, BinHeader{(unsigned long long)capacity, bl.units_off, bl.ckpt_off}, bin_header, stream);
       }
       GSR_STAGE("emit_ordered", debug, stream);
       {
@@ -354,6 +370,7 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     rp.bg = background, rp.out_color = out_color, rp.out_depth = out_depth, rp.out_alpha = out_alpha;
     rp.n_contrib = im.n_contrib, rp.n_touched = (P > 0) ? n_touched : nullptr;
     rp.capacity = (uint32_t)capacity;
+    rp.final_cd = im.final_cd, rp.units = bl.units, rp.ckpt = bl.ckpt, rp.unit_count = (P > 0) ? g.counters + 5 : nullptr;
     if (color_side && !color_joined) {
       GSR_CUDA(cudaStreamWaitEvent(stream, color_side->join, 0));
       color_joined = true;
@@ -369,7 +386,7 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     char* bin_base = binning_alloc(binning_bytes_for(cap, global_path, width, height), user);
     if (!bin_base) return fail(GSR_ERR_ALLOC, "binning_alloc returned NULL");
     carve_binning(bin_base, cap, bl, global_path, width, height);
-    bin_header = reinterpret_cast<unsigned long long*>(bin_base);   // capacity is recorded there by the scatter kernel
+    bin_header = reinterpret_cast<BinHeader*>(bin_base);   // capacity and the unit/checkpoint offsets are recorded there by the scatter kernel
     return GSR_OK;
   };
 
@@ -411,8 +428,9 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
       if (n_touched) GSR_CUDA(cudaMemsetAsync(n_touched, 0, sizeof(int) * (size_t)P, stream));
     }
     const bool global_path = longest > LOCAL_SORT_MAX;
-    if (int rc = alloc_binning(R, global_path)) return rc;
-    if (int rc = run_tail(R, global_path)) return rc;
+    const long long cap = R > 0 ? round_capacity(R) : 0;
+    if (int rc = alloc_binning(cap, global_path)) return rc;
+    if (int rc = run_tail(cap, global_path)) return rc;
   }
   stage_collect(stream);
   return R;
@@ -467,9 +485,10 @@ int gsr_rasterize_forward_async(char* geometry_buffer, char* binning_buffer, lon
     launch_color_fwd(pp, stream);
   }
   launch_scan_tiles(im.tile_diff, gx, gy, im.ranges, im.tile_cursor, im.tile_order, g.counters, (uint32_t)binning_capacity, stream);
-  unsigned long long* hdr = reinterpret_cast<unsigned long long*>(binning_buffer);
+  BinHeader* hdr = reinterpret_cast<BinHeader*>(binning_buffer);
+  const BinHeader hv{(unsigned long long)binning_capacity, bl.units_off, bl.ckpt_off};
   if (!global_sort) {
-    launch_scatter(P, g, im.tile_cursor, bl.comp, gx, (uint32_t)binning_capacity, hdr, stream);
+    launch_scatter(P, g, im.tile_cursor, bl.comp, gx, hv, hdr, stream);
     launch_tile_sort(T, im.ranges, bl.comp, bl.point_list, (uint32_t)binning_capacity, stream);
   } else {
     const int end_bit = sort_end_bit(width, height);
@@ -481,13 +500,14 @@ int gsr_rasterize_forward_async(char* geometry_buffer, char* binning_buffer, lon
     SortTemp st;
     carve_sort_temp(bl.sort_temp, binning_capacity, passes, st);
     sort_temp_reset(bl.sort_temp, binning_capacity, passes, stream);
-    launch_emit_ordered(P, g, keys[0], vals[0], gx, (uint32_t)binning_capacity, hdr, stream);
+    launch_emit_ordered(P, g, keys[0], vals[0], gx, hv, hdr, stream);
     launch_sort_histogram(keys[0], g.counters + 1, binning_capacity, end_bit, st.hist, stream);
     launch_onesweep(keys, vals, g.counters + 1, binning_capacity, end_bit, st, stream);
   }
   RenderParams rp{};
   rp.W = width, rp.H = height, rp.grid_x = gx, rp.grid_y = gy;
   rp.ranges = im.ranges, rp.point_list = bl.point_list, rp.tile_order = im.tile_order;
+  rp.final_cd = im.final_cd, rp.units = bl.units, rp.ckpt = bl.ckpt, rp.unit_count = g.counters + 5;
   rp.means2D = g.means2D, rp.conic_opacity = g.conic_opacity, rp.rgbd = g.rgbd, rp.gid = g.gid;
   rp.bg = background, rp.out_color = out_color, rp.out_depth = out_depth, rp.out_alpha = out_alpha;
   rp.n_contrib = im.n_contrib, rp.n_touched = n_touched, rp.capacity = (uint32_t)binning_capacity;
@@ -549,7 +569,9 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
   if (R > 0) {
     RenderBwdParams rb{};
     rb.W = width, rb.H = height, rb.grid_x = gx, rb.grid_y = gy;
-    rb.ranges = im.ranges, rb.point_list = bl.point_list, rb.tile_order = im.tile_order;
+    rb.ranges = im.ranges, rb.point_list = bl.point_list;
+    rb.binning_base = binning_buffer, rb.unit_count = g.counters + 5, rb.final_cd = im.final_cd;
+    rb.max_units = (uint32_t)max_units(R, (size_t)gx * gy);
     rb.means2D = g.means2D, rb.conic_opacity = g.conic_opacity, rb.rgbd = g.rgbd;
     rb.bg = background, rb.out_alpha = out_alpha, rb.n_contrib = im.n_contrib;
     rb.dL_dpix = dL_dpix, rb.dL_ddepth = dL_ddepth, rb.dL_dalpha = dL_dalpha, rb.grad_acc = g.grad_acc;

@@ -232,13 +232,17 @@ template <bool ORDERED>
 __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict__ block_vis, const uint2* __restrict__ rects,
                                                       const float* __restrict__ depths, uint32_t* __restrict__ cursor,
                                                       uint64_t* __restrict__ comp, float* __restrict__ grad_acc,
-                                                      uint32_t grid_x, uint32_t capacity, unsigned long long* header,
+                                                      uint32_t grid_x, BinHeader hv, BinHeader* header, uint32_t* unit_count,
                                                       const uint32_t* __restrict__ block_off, uint32_t* __restrict__ vals) {
+  const uint32_t capacity = (uint32_t)hv.capacity;
   __shared__ uint32_t s_end[256];     // CTA-local inclusive prefix of tile counts
   __shared__ uint2 s_rect[256];
   __shared__ uint32_t s_depth[256];
   __shared__ uint32_t s_wsum[8];
-  if (blockIdx.x == 0 && threadIdx.x == 0 && header) *header = capacity;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (header) *header = hv;
+    *unit_count = 0;   // the forward blend appends the backward's work units
+  }
   const uint32_t cnt = block_vis[blockIdx.x];
   if (cnt == 0) return;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -311,20 +315,20 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(const uint32_t* __res
   for (uint32_t i = i0; i < i1; i++) { const uint32_t c = a[i]; out[i] = run; run += c; }
 }
 
-void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* comp, uint32_t grid_x, uint32_t capacity,
-                    unsigned long long* header, cudaStream_t stream) {
+void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* comp, uint32_t grid_x, BinHeader hv,
+                    BinHeader* header, cudaStream_t stream) {
   if (P <= 0) return;
   scatter_kernel<false><<<num_pre_blocks(P), 256, 0, stream>>>(g.block_vis, g.rect, g.depths, cursor, comp, g.grad_acc, grid_x,
-                                                              capacity, header, nullptr, nullptr);
+                                                              hv, header, g.counters + 5, nullptr, nullptr);
   count_launch();
 }
 
-void launch_emit_ordered(int P, const GeometryView& g, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t capacity,
-                         unsigned long long* header, cudaStream_t stream) {
+void launch_emit_ordered(int P, const GeometryView& g, uint64_t* keys, uint32_t* vals, uint32_t grid_x, BinHeader hv,
+                         BinHeader* header, cudaStream_t stream) {
   if (P <= 0) return;
   scan_blocks_kernel<<<1, 1024, 0, stream>>>(g.block_tiles, g.block_off, (uint32_t)num_pre_blocks(P));
   scatter_kernel<true><<<num_pre_blocks(P), 256, 0, stream>>>(g.block_vis, g.rect, g.depths, nullptr, keys, g.grad_acc, grid_x,
-                                                             capacity, header, g.block_off, vals);
+                                                             hv, header, g.counters + 5, g.block_off, vals);
   count_launch(2);
 }
 

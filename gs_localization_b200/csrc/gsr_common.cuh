@@ -50,6 +50,7 @@ struct ImageView {              // replaces ImageState (reference rasterizer_imp
   int* tile_diff;               // [(gy+1)(gx+1)] 2-D difference grid of tile coverage -> per-tile counts
   uint32_t* tile_cursor;        // [T]   bucket write cursors
   uint32_t* tile_order;         // [T]   tiles by descending list length: launch order of the blend CTAs
+  float4* final_cd;             // [N]   forward's final (C0, C1, C2, D) without the background term
 };
 
 struct BinningView {            // replaces BinningState (reference rasterizer_impl.h:54-64)
@@ -59,7 +60,22 @@ struct BinningView {            // replaces BinningState (reference rasterizer_i
   uint64_t* keys[2];
   uint32_t* vals_other;
   char* sort_temp;
+  // backward work units and the forward's per-segment pixel checkpoints (both layouts; offsets are from the buffer base
+  // and are recorded in the header by the scatter kernel, because the backward is not told the capacity)
+  uint2* units;                 // [max_units] (tile, segment)
+  float* ckpt;                  // [max_units][5][256]  T, C0, C1, C2, D of the tile's pixels at the start of a segment
+  size_t units_off, ckpt_off;
 };
+
+// The blend backward runs one CTA per (tile, segment of SEG list entries); the forward leaves the pixel state at every
+// segment boundary so that a segment can be walked back to front without the ones behind it.
+constexpr int SEG = 256;
+constexpr int CKPT_FLOATS = 5 * 256;
+struct BinHeader { unsigned long long capacity, units_off, ckpt_off; };
+inline size_t max_units(long long cap, size_t tiles) { return (size_t)(cap / SEG) + tiles + 2; }
+// slot of tile t's checkpoint for segment r: sum_{i<t} ceil(len_i / SEG) <= floor(start_t / SEG) + t, and consecutive
+// tiles never overlap, so no prefix sum over segment counts is needed
+__host__ __device__ inline uint32_t ckpt_slot(uint32_t range_start, uint32_t tile, uint32_t seg) { return range_start / SEG + tile + seg; }
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -98,6 +114,7 @@ inline char* carve_image(char* base, int W, int H, ImageView& im) {
   carve(p, im.tile_diff, (gx + 1) * (gy + 1));
   carve(p, im.tile_cursor, gx * gy);
   carve(p, im.tile_order, gx * gy);
+  carve(p, im.final_cd, (size_t)W * H);
   return p;
 }
 

@@ -60,11 +60,11 @@ void sort_temp_reset(char* base, long long n, int passes, cudaStream_t stream);
 void launch_scan_tiles(int* tile_diff, uint32_t gx, uint32_t gy, uint2* ranges, uint32_t* cursor, uint32_t* tile_order,
                        uint32_t* counters, uint32_t capacity, cudaStream_t stream);
 // (Gaussian, tile) instances -> tile buckets as depth_bits << 32 | slot; also zeroes the slots' backward accumulators
-void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* comp, uint32_t grid_x, uint32_t capacity,
-                    unsigned long long* header, cudaStream_t stream);
+void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* comp, uint32_t grid_x, BinHeader hv,
+                    BinHeader* header, cudaStream_t stream);
 // the reference's unsorted (key, value) arrays, in Gaussian order, for the global radix sort path
-void launch_emit_ordered(int P, const GeometryView& g, uint64_t* keys, uint32_t* vals, uint32_t grid_x, uint32_t capacity,
-                         unsigned long long* header, cudaStream_t stream);
+void launch_emit_ordered(int P, const GeometryView& g, uint64_t* keys, uint32_t* vals, uint32_t grid_x, BinHeader hv,
+                         BinHeader* header, cudaStream_t stream);
 void launch_reset_cursors(int T, const uint2* ranges, uint32_t* cursor, cudaStream_t stream);
 // per-tile sort of the buckets on the composite key; writes the sorted slots to point_list
 void launch_tile_sort(int num_tiles, const uint2* ranges, uint64_t* comp, uint32_t* point_list, uint32_t capacity,
@@ -94,6 +94,10 @@ struct RenderParams {
   uint32_t* n_contrib;
   int* n_touched;            // may be null
   uint32_t capacity;         // entries of point_list that exist (speculative launch: ranges may exceed it)
+  float4* final_cd;          // [N] final (C0, C1, C2, D) for the segment-parallel backward
+  uint2* units;              // backward work units appended here, *unit_count of them
+  float* ckpt;               // pixel state at segment boundaries
+  uint32_t* unit_count;
 };
 void launch_render_fwd(const RenderParams& p, cudaStream_t stream);
 
@@ -101,7 +105,10 @@ struct RenderBwdParams {
   int W, H;
   uint32_t grid_x, grid_y;
   const uint2* ranges;
-  const uint32_t* tile_order;
+  const char* binning_base;     // BinHeader at offset 0: where the units and checkpoints of this forward live
+  const uint32_t* unit_count;
+  const float4* final_cd;
+  uint32_t max_units;           // launch bound: floor(R / SEG) + T + 2
   const uint32_t* point_list;   // sorted visible ranks
   const float2* means2D;
   const float4* conic_opacity;
