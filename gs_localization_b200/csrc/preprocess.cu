@@ -18,6 +18,8 @@
 // ranges and num_rendered all fall out of one tiny prefix-sum kernel over the tile grid
 // (binning.cu).  Arithmetic that decides binning is pinned with IEEE intrinsics to the
 // reference's sm_100a rounding sequence (gsr_common.cuh).
+#include <cstdlib>
+
 #include "gsr_kernels.cuh"
 
 namespace gsr {
@@ -135,22 +137,107 @@ __device__ __forceinline__ float3 color_from_sh(int deg, float3 pos, float3 camp
 __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_fwd_kernel(const PreprocessParams p) {
   __shared__ uint32_t s_warp_vis[PRE_THREADS / 32];
   __shared__ uint32_t s_warp_tiles[PRE_THREADS / 32];
+  __shared__ uint32_t s_warp_near[PRE_THREADS / 32];
+  __shared__ uint8_t s_cand[PRE_THREADS];
   __shared__ float s_cam[16 + 16];
 
   const int tid = threadIdx.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
   const uint32_t block = blockIdx.x;
   const int base = (int)block * PRE_THREADS;
-  const int idx = base + tid;
   const int P = p.P;
 
-  // ---- every per-Gaussian input is requested up front so that one DRAM round trip covers them all; the
-  //      camera constants go through shared memory while those loads are in flight
+  // ---- phase 1, one thread per Gaussian: everything cheap.  The reference culls only on view-space depth
+  //      (auxiliary.h:139-164; its x/y frustum test is commented out), so about half of a room-scale map survives
+  //      the cull and goes through the covariance pipeline only to end with an empty tile rectangle.  Here a
+  //      conservative bound of the screen radius decides first whether the rectangle CAN be non-empty:
+  //        lambda_max(cov2D) <= |W|_F^2 |J|_F^2 s_max^2 |R|_F^2 + 0.3,   radius <= 3 sqrt(lambda_max + sqrt(0.1)) + 1
+  //      (J with the clamped t of forward.cu:86-91, R the reference's unnormalised-quaternion matrix, whose Frobenius
+  //      norm is 1 + 2 (1 - 2|v|^2)^2 + 8 w^2 |v|^2).  A Gaussian whose bounded rectangle misses the image by a
+  //      pixel of margin gets radius 0 exactly as the full computation would give it; NaNs fall through to phase 2.
+  //      All per-Gaussian inputs are requested up front so that one DRAM round trip covers them.
+  bool near = false;
+  {
+    const int idx = base + tid;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    float3 sc = {0, 0, 0};
+    float4 q = {0, 0, 0, 0};
+    if (idx < P) {
+      px = __ldg(p.means3D + 3 * (size_t)idx), py = __ldg(p.means3D + 3 * (size_t)idx + 1), pz = __ldg(p.means3D + 3 * (size_t)idx + 2);
+      if (!p.cov3D_precomp) {
+        sc = make_float3(__ldg(p.scales + 3 * (size_t)idx), __ldg(p.scales + 3 * (size_t)idx + 1), __ldg(p.scales + 3 * (size_t)idx + 2));
+        q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+      }
+    }
+    if (tid < 16) s_cam[tid] = p.viewmatrix[tid];
+    else if (tid < 32) s_cam[tid] = p.projmatrix[tid - 16];
+    __syncthreads();
+    if (idx < P) {
+      const float* vm = s_cam;
+      const float* pm = s_cam + 16;
+      // in_frustum: p_view.z <= 0.2 culls (NaN culls too)
+      const float vz = __fadd_rn(dot3c(px, vm[2], py, vm[6], pz, vm[10]), vm[14]);
+      if (vz > 0.2f) {
+        near = true;
+        if (!p.cov3D_precomp) {
+          const float hx = __fadd_rn(dot3c(px, pm[0], py, pm[4], pz, pm[8]), pm[12]);
+          const float hy = __fadd_rn(dot3c(px, pm[1], py, pm[5], pz, pm[9]), pm[13]);
+          const float hw = __fadd_rn(dot3c(px, pm[3], py, pm[7], pz, pm[11]), pm[15]);
+          const float p_w = 1.0f / (hw + 0.0000001f);
+          const float cx = ((hx * p_w + 1.0f) * (float)p.W - 1.0f) * 0.5f, cy = ((hy * p_w + 1.0f) * (float)p.H - 1.0f) * 0.5f;
+          float w2 = 0.f;
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) w2 += vm[4 * c + r] * vm[4 * c + r];
+          const float limx = 1.3f * p.tan_fovx, limy = 1.3f * p.tan_fovy;
+          const float iz = 1.0f / vz;
+          const float j2 = (p.focal_x * iz) * (p.focal_x * iz) * (1.0f + limx * limx) + (p.focal_y * iz) * (p.focal_y * iz) * (1.0f + limy * limy);
+          const float smax = fmaxf(fmaxf(fabsf(sc.x), fabsf(sc.y)), fabsf(sc.z)) * fabsf(p.scale_modifier);
+          const float v2 = q.y * q.y + q.z * q.z + q.w * q.w;
+          const float r2 = 1.0f + 2.0f * (1.0f - 2.0f * v2) * (1.0f - 2.0f * v2) + 8.0f * q.x * q.x * v2;
+          const float lam = w2 * j2 * smax * smax * r2 * 1.02f + 0.3f + 0.32f;
+          const float rb = 3.0f * sqrtf(lam) * 1.01f + 2.0f;
+          // outside for sure: the whole [c - rb, c + rb + 15] interval maps to tile index <= 0 or >= grid on one axis
+          const bool outside = (cx + rb + 15.0f < 0.0f) || (cx - rb >= 16.0f * (float)p.grid_x) || (cy + rb + 15.0f < 0.0f) ||
+                               (cy - rb >= 16.0f * (float)p.grid_y);
+          near = !outside;   // NaN/Inf anywhere -> comparisons false -> kept
+        }
+      } else if (p.prefiltered) {
+        // reference auxiliary.h:156-160
+        printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+        __trap();
+      }
+      if (!near) p.radii[idx] = 0;
+      if (p.n_touched) p.n_touched[idx] = 0;
+    }
+  }
+  // compact the candidates: phase 2 runs the covariance pipeline on dense warps
+  uint32_t n_cand;
+  {
+    const uint32_t m = __ballot_sync(0xffffffffu, near);
+    if (lane == 0) s_warp_near[warp] = __popc(m);
+    __syncthreads();
+    uint32_t off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < PRE_THREADS / 32; w++) {
+      const uint32_t c = s_warp_near[w];
+      if (w < (int)warp) off += c;
+      tot += c;
+    }
+    if (near) s_cand[off + __popc(m & ((1u << lane) - 1u))] = (uint8_t)tid;
+    n_cand = tot;
+    __syncthreads();
+  }
+
+  // ---- phase 2, thread t < n_cand takes candidate t (ascending Gaussian order is preserved)
+  const bool work = (uint32_t)tid < n_cand;
+  const int idx = work ? base + (int)s_cand[tid] : P;
   float px = 0.f, py = 0.f, pz = 0.f, opacity = 0.f;
   float3 sc = {0, 0, 0};
   float4 q = {0, 0, 0, 0};
   float cov3D[6] = {0, 0, 0, 0, 0, 0};
-  if (idx < P) {
+  if (work) {
     px = __ldg(p.means3D + 3 * (size_t)idx), py = __ldg(p.means3D + 3 * (size_t)idx + 1), pz = __ldg(p.means3D + 3 * (size_t)idx + 2);
     opacity = __ldg(p.opacities + idx);
     if (p.cov3D_precomp) {
@@ -161,21 +248,17 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_fwd_kernel(const Pr
       q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
     }
   }
-  if (tid < 16) s_cam[tid] = p.viewmatrix[tid];
-  else if (tid < 32) s_cam[tid] = p.projmatrix[tid - 16];
-  __syncthreads();
 
   uint32_t tiles = 0;
   int radius = 0;
   float vz = 0.f, pix_x = 0.f, pix_y = 0.f;
   float3 conic = {0, 0, 0};
   uint2 rect = {0, 0};
-  if (idx < P) {
+  if (work) {
     const float* vm = s_cam;
     const float* pm = s_cam + 16;
-    // in_frustum: p_view.z <= 0.2 culls (NaN culls too)
     vz = __fadd_rn(dot3c(px, vm[2], py, vm[6], pz, vm[10]), vm[14]);
-    if (vz > 0.2f) {
+    {
       const float vx = __fadd_rn(dot3c(px, vm[0], py, vm[4], pz, vm[8]), vm[12]);
       const float vy = __fadd_rn(dot3c(px, vm[1], py, vm[5], pz, vm[9]), vm[13]);
       const float hx = __fadd_rn(dot3c(px, pm[0], py, pm[4], pz, pm[8]), pm[12]);
@@ -210,13 +293,8 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_fwd_kernel(const Pr
           rect = make_uint2(minx | (maxx << 16), miny | (maxy << 16));
         }
       }
-    } else if (p.prefiltered) {
-      // reference auxiliary.h:156-160
-      printf("Point is filtered although prefiltered is set. This shouldn't happen!");
-      __trap();
     }
     p.radii[idx] = radius;
-    if (p.n_touched) p.n_touched[idx] = 0;
   }
 
   // ---- pack the visible Gaussians into the CTA's slot segment (ballot ranks keep Gaussian order)
