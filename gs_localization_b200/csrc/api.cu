@@ -770,6 +770,30 @@ int gsr_map_adam_step(int P, int M, int do_stats, int do_adam, const int* steps,
   return GSR_OK;
 }
 
+int gsr_pack_gradient_rows(const long long* row_ids, int n_rows, int padded_rows, int M, float* const* grads, float* table, void* stream_) {
+  if (n_rows < 0 || padded_rows < n_rows || M < 1 || !grads || !table || (n_rows > 0 && !row_ids)) return fail(GSR_ERR_INVALID_ARGUMENT, "bad arguments");
+  GradRowTensors t;
+  for (int i = 0; i < 5; i++) {
+    if (!grads[i]) return fail(GSR_ERR_INVALID_ARGUMENT, "null gradient tensor %d", i);
+    t.g[i] = grads[i];
+  }
+  launch_pack_gradient_rows(row_ids, n_rows, padded_rows, M, t, table, (cudaStream_t)stream_);
+  GSR_STAGE("pack_gradient_rows", 0, (cudaStream_t)stream_);
+  return GSR_OK;
+}
+
+int gsr_add_gradient_rows(const float* table, int padded_rows, int M, float* const* grads, void* stream_) {
+  if (padded_rows < 0 || M < 1 || !grads || !table) return fail(GSR_ERR_INVALID_ARGUMENT, "bad arguments");
+  GradRowTensors t;
+  for (int i = 0; i < 5; i++) {
+    if (!grads[i]) return fail(GSR_ERR_INVALID_ARGUMENT, "null gradient tensor %d", i);
+    t.g[i] = grads[i];
+  }
+  launch_add_gradient_rows(table, padded_rows, M, t, (cudaStream_t)stream_);
+  GSR_STAGE("add_gradient_rows", 0, (cudaStream_t)stream_);
+  return GSR_OK;
+}
+
 size_t gsr_knn_workspace_bytes(long long n_points) { return n_points > 0 ? knn_workspace_bytes(n_points) : 0; }
 
 int gsr_dist2_knn3(const float* points, long long n_points, float* mean_dists, char* workspace, void* stream_) {

@@ -186,6 +186,9 @@ struct MapStepParams {
   const int* radii;
   float *max_radii2D, *xyz_gradient_accum, *denom;
 };
+struct GradRowTensors { float* g[5]; };   // xyz, features, opacity, scaling, rotation gradients
+void launch_pack_gradient_rows(const long long* idx, int k, int K, int M, const GradRowTensors& t, float* table, cudaStream_t stream);
+void launch_add_gradient_rows(const float* table, int K, int M, const GradRowTensors& t, cudaStream_t stream);
 void launch_map_step(const MapStepParams& s, float beta1, float beta2, float eps, const int* steps, cudaStream_t stream);
 
 // ---- simple-knn (knn.cu)

@@ -151,4 +151,61 @@ void launch_map_step(const MapStepParams& s, float beta1, float beta2, float eps
   }
 }
 
+// ---- visible-rows gradient exchange of data-parallel map training (parallel.SparseGradientExchange)
+// table row = [row id as int bits | xyz 3 | features 3M | opacity 1 | scaling 3 | rotation 4]; one warp per row.
+__device__ __forceinline__ void row_column(int c, int M, int& tensor, int& within) {
+  const int f = 3 * M;
+  if (c < 3) tensor = 0, within = c;
+  else if (c < 3 + f) tensor = 1, within = c - 3;
+  else if (c < 4 + f) tensor = 2, within = 0;
+  else if (c < 7 + f) tensor = 3, within = c - 4 - f;
+  else tensor = 4, within = c - 7 - f;
+}
+
+__global__ void __launch_bounds__(256) pack_gradient_rows_kernel(const long long* __restrict__ idx, int k, int K, int M, GradRowTensors t,
+                                                                 float* __restrict__ table) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= K) return;
+  const int F = 11 + 3 * M;
+  float* out = table + (size_t)row * (1 + F);
+  if (row >= k) {
+    if (lane == 0) out[0] = __int_as_float(-1);
+    return;
+  }
+  const long long g = idx[row];
+  if (lane == 0) out[0] = __int_as_float((int)g);
+  const int width[5] = {3, 3 * M, 1, 3, 4};
+  for (int c = lane; c < F; c += 32) {
+    int ten, w;
+    row_column(c, M, ten, w);
+    out[1 + c] = t.g[ten][(size_t)g * width[ten] + w];
+  }
+}
+
+__global__ void __launch_bounds__(256) add_gradient_rows_kernel(const float* __restrict__ table, int K, int M, GradRowTensors t) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= K) return;
+  const int F = 11 + 3 * M;
+  const float* in = table + (size_t)row * (1 + F);
+  const int g = __float_as_int(in[0]);
+  if (g < 0) return;
+  const int width[5] = {3, 3 * M, 1, 3, 4};
+  for (int c = lane; c < F; c += 32) {
+    int ten, w;
+    row_column(c, M, ten, w);
+    t.g[ten][(size_t)g * width[ten] + w] += in[1 + c];   // row ids are unique within one rank's table
+  }
+}
+
+void launch_pack_gradient_rows(const long long* idx, int k, int K, int M, const GradRowTensors& t, float* table, cudaStream_t stream) {
+  if (K <= 0) return;
+  pack_gradient_rows_kernel<<<(K + 7) / 8, 256, 0, stream>>>(idx, k, K, M, t, table);
+  count_launch();
+}
+void launch_add_gradient_rows(const float* table, int K, int M, const GradRowTensors& t, cudaStream_t stream) {
+  if (K <= 0) return;
+  add_gradient_rows_kernel<<<(K + 7) / 8, 256, 0, stream>>>(table, K, M, t);
+  count_launch();
+}
+
 }  // namespace gsr

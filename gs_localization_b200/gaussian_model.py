@@ -281,8 +281,10 @@ class GaussianModel:
         self.denom[update_filter] += 1
 
     # ------------------------------------------------------------------ one training iteration, no autograd
-    def training_step(self, cam, gt_image, bg, opt, iteration: int, pseudo_depth=None, gt_depth=None, extent: float = 1.0):
-        """7scenes_gs_full_dslam.py:128-242 for one view: returns (loss tensor[1], dict of render outputs)."""
+    def compute_gradients(self, cam, gt_image, bg, opt, iteration: int, pseudo_depth=None, gt_depth=None):
+        """Render + loss + backward of one view (7scenes_gs_full_dslam.py:128-190) without touching the parameters.
+        Returns (loss[1], grads, dL_dmeans2D, outputs); grads = (dL_dxyz, dL_dfeatures, dL_dopacity_act, dL_dscaling_act,
+        dL_drotation_act), dense over all Gaussians and exactly zero outside `outputs["radii"] > 0`."""
         lib = _lib.load()
         dev = self.device
         self.update_learning_rate(iteration)
@@ -311,6 +313,13 @@ class GaussianModel:
                                         campos, geom, R, binning, img, alpha, False, needs=needs)
         dL_dmeans2D, _, dL_dopacity, dL_dmeans3D, _, dL_dsh, dL_dscales, dL_drotations = grads
         g = (dL_dmeans3D, dL_dsh, dL_dopacity, dL_dscales, dL_drotations)
+        return loss, g, dL_dmeans2D, dict(render=color, depth=depth, alpha=alpha, radii=radii)
+
+    def apply_gradients(self, g, dL_dmeans2D, radii, opt, iteration: int, extent: float = 1.0):
+        """Statistics, densification / opacity reset on their schedule, and the optimiser step
+        (7scenes_gs_full_dslam.py:225-242).  Under data parallelism `g` is the sum over ranks (identical everywhere, so
+        every rank takes the same densification decisions given the same RNG seed) while dL_dmeans2D / radii stay local
+        unless the caller exchanged them too."""
         info = None
         if iteration < opt.densify_until_iter:
             densify = iteration > opt.densify_from_iter and iteration % opt.densification_interval == 0
@@ -330,4 +339,10 @@ class GaussianModel:
                 self.optimizer_step(g, dL_dmeans2D, radii, stats=True, adam=True)
         else:
             self.optimizer_step(g, adam=True)
-        return loss, dict(render=color, depth=depth, alpha=alpha, radii=radii, densify=info)
+        return info
+
+    def training_step(self, cam, gt_image, bg, opt, iteration: int, pseudo_depth=None, gt_depth=None, extent: float = 1.0):
+        """7scenes_gs_full_dslam.py:128-242 for one view: returns (loss tensor[1], dict of render outputs)."""
+        loss, g, dL_dmeans2D, out = self.compute_gradients(cam, gt_image, bg, opt, iteration, pseudo_depth, gt_depth)
+        out["densify"] = self.apply_gradients(g, dL_dmeans2D, out["radii"], opt, iteration, extent)
+        return loss, out

@@ -213,6 +213,14 @@ GSR_API int gsr_map_adam_step(int P, int M, int do_stats, int do_adam, const int
                               float* const* exp_avg_sq, float* opacity_act, float* scaling_act, float* rotation_act,
                               const float* dL_dmeans2D, const int* radii, float* max_radii2D, float* xyz_gradient_accum,
                               float* denom, void* stream);
+/* Visible-rows gradient exchange of data-parallel map training (the dense all-reduce moves 59 floats
+ * per Gaussian although one view touches a few percent of the map).  gsr_pack_gradient_rows gathers rows row_ids[n_rows]
+ * of the five gradient tensors grads[] = { xyz [P,3], features [P,M,3], opacity [P], scaling [P,3], rotation [P,4] }
+ * into table[padded_rows][1 + 11 + 3M]: column 0 is the row id (int bits; -1 for padding rows).  gsr_add_gradient_rows
+ * adds a (received) table back into dense gradients; ids must be unique within a table.  Host tables of device pointers. */
+GSR_API int gsr_pack_gradient_rows(const long long* row_ids, int n_rows, int padded_rows, int M, float* const* grads,
+                                   float* table, void* stream);
+GSR_API int gsr_add_gradient_rows(const float* table, int padded_rows, int M, float* const* grads, void* stream);
 /* distCUDA2 of simple-knn (gaussian_splatting/submodules/simple-knn/spatial.cu:15-26, simple_knn.cu:185-221):
  * mean_dists[i] = mean of the squared distances from points[i] to its three nearest other points (exact search;
  * FLT_MAX stands in for missing neighbours when n_points < 4, as in the reference).  points: [n,3] float32.

@@ -81,3 +81,27 @@ def test_single_process_defaults():
     assert parallel.shard_queries(5) == [0, 1, 2, 3, 4]
     t = parallel.gather_query_results({1: torch.ones(2)}, 3, 2)
     assert t.shape == (3, 2) and t[1, 0] == 1 and torch.isnan(t[0, 0])
+
+
+def _sparse(rank, world):
+    torch.manual_seed(0)
+    P = 500
+    like = [torch.zeros(P, 3), torch.zeros(P, 4, 3), torch.zeros(P, 1), torch.zeros(P, 3), torch.zeros(P, 4)]
+    g = torch.Generator().manual_seed(100 + rank)
+    vis = torch.rand(P, generator=g) < (0.1 if rank == 0 else 0.3)       # different row counts per rank
+    grads = [torch.randn(t.shape, generator=g) * vis.view(-1, *([1] * (t.dim() - 1))) for t in like]
+    dense = [x.clone() for x in grads]
+    for x in dense:
+        dist.all_reduce(x)
+    ex = parallel.SparseGradientExchange(like, granularity=64)
+    out = ex.exchange(grads, vis)
+    err = max(float((a - b).abs().max()) for a, b in zip(out, dense))
+    return err, ex.last_rows, ex.F
+
+
+def test_sparse_gradient_exchange_equals_dense_allreduce():
+    out = _spawn(_sparse)
+    for r in (0, 1):
+        err, rows, F = out[r]
+        assert err < 1e-6 and F == 3 + 12 + 1 + 3 + 4
+        assert rows % 64 == 0 and 64 <= rows <= 256                       # padded to the larger rank's visible count
