@@ -236,12 +236,20 @@ def run_gpu_arm(args, rank, world, local_rank):
     copy_done = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
+    # the copy is issued with one cudaMemcpyAsync on the copy stream (entering a torch stream context every step costs
+    # more host time than the call it wraps)
+    import ctypes
+    _rt = ctypes.CDLL("libcudart.so.12")
+    _rt.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+    _rt.cudaMemcpyAsync.restype = ctypes.c_int
+
     def upload(i):
         q, slot = i % N_POSES, i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])          # the step that last used this slot has finished with it
-            dev_slots[slot].copy_(host_packed[q], non_blocking=True)
-            copy_done[slot].record(copy_stream)
+        copy_stream.wait_event(consumed[slot])              # the step that last used this slot has finished with it
+        rc = _rt.cudaMemcpyAsync(dev_slots[slot].data_ptr(), host_packed[q].data_ptr(), n_in * 4, 1, copy_stream.cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"cudaMemcpyAsync failed ({rc})")
+        copy_done[slot].record(copy_stream)
 
     for ev in consumed:
         ev.record(torch.cuda.current_stream(device))
