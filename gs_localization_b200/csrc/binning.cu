@@ -95,23 +95,25 @@ __global__ void __launch_bounds__(ST_THREADS) scan_tiles_kernel(int* __restrict_
   constexpr uint32_t nt = ST_THREADS;
   const uint32_t stride = gx + 1;
   const uint32_t cells = stride * (gy + 1);
+  // logical cell i lives at diff_g[i * DIFF_STRIDE]; the shared copy is packed
   int* diff = IN_SMEM ? s_grid : diff_g;
+  constexpr uint32_t DS = IN_SMEM ? 1u : (uint32_t)DIFF_STRIDE;
   if (IN_SMEM) {
-    for (uint32_t i = tid; i < cells; i += nt) s_grid[i] = diff_g[i];
+    for (uint32_t i = tid; i < cells; i += nt) s_grid[i] = diff_g[(size_t)i * DIFF_STRIDE];
   }
   if (tid < ST_BUCKETS) s_bucket[tid] = 0;
   __syncthreads();
   // prefix along rows: one warp per row, shuffle scan over 32-wide pieces
   for (uint32_t y = warp; y <= gy; y += nt / 32) {
     int carry = 0;
-    int* row = diff + y * stride;
+    int* row = diff + (size_t)y * stride * DS;
     for (uint32_t x0 = 0; x0 <= gx; x0 += 32) {
       const uint32_t x = x0 + lane;
-      int v = x <= gx ? row[x] : 0;
+      int v = x <= gx ? row[x * DS] : 0;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= (uint32_t)o) v += n; }
       v += carry;
-      if (x <= gx) row[x] = v;
+      if (x <= gx) row[x * DS] = v;
       carry = __shfl_sync(0xffffffffu, v, 31);
     }
   }
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(ST_THREADS) scan_tiles_kernel(int* __restrict_
   // prefix along columns: one thread per column
   for (uint32_t x = tid; x <= gx; x += nt) {
     int run = 0;
-    for (uint32_t y = 0; y <= gy; y++) { run += diff[y * stride + x]; diff[y * stride + x] = run; }
+    for (uint32_t y = 0; y <= gy; y++) { run += diff[(size_t)(y * stride + x) * DS]; diff[(size_t)(y * stride + x) * DS] = run; }
   }
   __syncthreads();
   // exclusive scan of the T counts in tile order: each thread owns a contiguous chunk
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(ST_THREADS) scan_tiles_kernel(int* __restrict_
   {
     uint32_t ty = t0 / gx, tx = t0 - ty * gx;
     for (uint32_t t = t0; t < t1; t++) {
-      const uint32_t c = (uint32_t)diff[ty * stride + tx];
+      const uint32_t c = (uint32_t)diff[(size_t)(ty * stride + tx) * DS];
       sum += c;
       mx = max(mx, c);
       if (++tx == gx) tx = 0, ty++;
@@ -166,9 +168,9 @@ __global__ void __launch_bounds__(ST_THREADS) scan_tiles_kernel(int* __restrict_
   {
     uint32_t ty = t0 / gx, tx = t0 - ty * gx;
     for (uint32_t t = t0, i = 0; t < t1; t++, i++) {
-      const uint32_t c = (uint32_t)diff[ty * stride + tx];
+      const uint32_t c = (uint32_t)diff[(size_t)(ty * stride + tx) * DS];
       ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);   // untouched tiles stay (0,0) like the reference
-      cursor[t] = run;
+      cursor[(size_t)t * CURSOR_STRIDE] = run;
       run += c;
       if (order_ok) {
         const uint32_t bk = (ST_BUCKETS - 1) - min((uint32_t)(ST_BUCKETS - 1), (uint32_t)(((unsigned long long)c * ST_BUCKETS) / (longest + 1)));
@@ -214,7 +216,7 @@ __global__ void reset_cursors_kernel(int T, const uint2* __restrict__ ranges, co
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
   // empty tiles have range (0,0) but their cursor was the running prefix; they receive no instance, any value works
-  cursor[t] = ranges[t].x;
+  cursor[(size_t)t * CURSOR_STRIDE] = ranges[t].x;
   (void)diff, (void)gx;
 }
 void launch_reset_cursors(int T, const uint2* ranges, uint32_t* cursor, cudaStream_t stream) {
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict
         vals[pos] = first + lo;
       }
     } else {
-      const uint32_t pos = atomicAdd(cursor + tile, 1u);
+      const uint32_t pos = atomicAdd(cursor + (size_t)tile * CURSOR_STRIDE, 1u);
       if (pos < capacity) comp[pos] = ((uint64_t)s_depth[lo] << 32) | (first + lo);
     }
   }

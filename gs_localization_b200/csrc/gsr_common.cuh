@@ -44,11 +44,16 @@ struct GeometryView {           // replaces GeometryState (reference rasterizer_
   float* grad_acc;              // [12 slots] backward accumulators, zero between uses
 };
 
+// Bucket cursors are hammered by one atomic per instance; packed, the T cursors of a frame share ~40 cache lines and
+// the L2 atomic units serialise on them.  One cursor per 32-byte sector spreads them over all slices.
+constexpr int CURSOR_STRIDE = 8;
+constexpr int DIFF_STRIDE = 8;     // same for the cells of the coverage difference grid (4 atomics per visible Gaussian)
+
 struct ImageView {              // replaces ImageState (reference rasterizer_impl.h:46-52)
   uint2* ranges;                // [T]   [start, end) of each tile in the sorted list, (0,0) if empty
   uint32_t* n_contrib;          // [N]
-  int* tile_diff;               // [(gy+1)(gx+1)] 2-D difference grid of tile coverage -> per-tile counts
-  uint32_t* tile_cursor;        // [T]   bucket write cursors
+  int* tile_diff;               // [(gy+1)(gx+1) * DIFF_STRIDE] 2-D difference grid of tile coverage -> per-tile counts
+  uint32_t* tile_cursor;        // [T * CURSOR_STRIDE] bucket write cursors, one per 32-byte sector
   uint32_t* tile_order;         // [T]   tiles by descending list length: launch order of the blend CTAs
   float4* final_cd;             // [N]   forward's final (C0, C1, C2, D) without the background term
 };
@@ -111,8 +116,8 @@ inline char* carve_image(char* base, int W, int H, ImageView& im) {
   const size_t gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
   carve(p, im.ranges, gx * gy);
   carve(p, im.n_contrib, (size_t)W * H);
-  carve(p, im.tile_diff, (gx + 1) * (gy + 1));
-  carve(p, im.tile_cursor, gx * gy);
+  carve(p, im.tile_diff, (gx + 1) * (gy + 1) * DIFF_STRIDE);
+  carve(p, im.tile_cursor, gx * gy * CURSOR_STRIDE);
   carve(p, im.tile_order, gx * gy);
   carve(p, im.final_cd, (size_t)W * H);
   return p;

@@ -327,10 +327,10 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_fwd_kernel(const Pr
     // tile coverage: +1/-1 at the rectangle corners of the 2-D difference grid
     const uint32_t minx = rect.x & 0xffffu, maxx = rect.x >> 16, miny = rect.y & 0xffffu, maxy = rect.y >> 16;
     const uint32_t stride = p.grid_x + 1;
-    atomicAdd(p.tile_diff + miny * stride + minx, 1);
-    atomicAdd(p.tile_diff + miny * stride + maxx, -1);
-    atomicAdd(p.tile_diff + maxy * stride + minx, -1);
-    atomicAdd(p.tile_diff + maxy * stride + maxx, 1);
+    atomicAdd(p.tile_diff + (size_t)(miny * stride + minx) * DIFF_STRIDE, 1);
+    atomicAdd(p.tile_diff + (size_t)(miny * stride + maxx) * DIFF_STRIDE, -1);
+    atomicAdd(p.tile_diff + (size_t)(maxy * stride + minx) * DIFF_STRIDE, -1);
+    atomicAdd(p.tile_diff + (size_t)(maxy * stride + maxx) * DIFF_STRIDE, 1);
   }
 }
 

@@ -26,6 +26,8 @@ SCENES = {
     "mid": dict(P=60_000, W=320, H=240, deg=3, f=262.5, sigma0=0.04),
     # tile lists longer than the shared-memory tile sort handles (> 4096): exercises the global onesweep path
     "dense": dict(P=200_000, W=64, H=48, deg=1, f=50.0, sigma0=0.1),
+    # more than 10240 cells in the coverage grid: scan_tiles works in global memory instead of shared memory
+    "wide": dict(P=4000, W=2064, H=1552, deg=0, f=1500.0, sigma0=0.05),
 }
 
 
@@ -92,7 +94,7 @@ def test_forward_vs_oracle(name):
     assert mism <= 2e-3, mism
 
 
-@pytest.mark.parametrize("name", ["tiny", "C1", "ragged", "mid", "dense"])
+@pytest.mark.parametrize("name", ["tiny", "C1", "ragged", "mid", "dense", "wide"])
 def test_forward_vs_reference_bit_exact(name):
     if not util.reference_available():
         pytest.skip("oracle/_ref not built (reference sources absent at build time)")
