@@ -22,7 +22,8 @@
 
 namespace gsr {
 
-constexpr int BW_THREADS = 32;   // one single-warp CTA per preprocess slot segment, looping over its visible slots
+constexpr int BW_THREADS = 128;  // one warp per preprocess slot segment, looping over its visible slots; four segments per CTA
+                                 // so that the pose gradient leaves as 6 atomics per four segments (they all hit one cache line)
 
 // reference auxiliary.h:107-117
 __device__ __forceinline__ float3 dnormvdv(float3 v, float3 dv) {
@@ -122,16 +123,16 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
   __shared__ float s_tau[BW_THREADS / 32][6];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t nvis = p.geom.block_vis[blockIdx.x];
-  if (nvis == 0) return;
+  const uint32_t seg = blockIdx.x * (BW_THREADS / 32) + warp;
+  const uint32_t nvis = seg < (uint32_t)((p.P + PRE_THREADS - 1) / PRE_THREADS) ? p.geom.block_vis[seg] : 0u;
   const int M = p.M;
   const int row = 3 * M;                 // floats per SH row
   const float* vm = p.viewmatrix;
   const float* proj = p.projmatrix;
   float tau[6] = {0, 0, 0, 0, 0, 0};
 
-  for (uint32_t t_in_seg = tid; t_in_seg < nvis; t_in_seg += BW_THREADS) {
-  const uint32_t k = blockIdx.x * PRE_THREADS + t_in_seg;     // slot
+  for (uint32_t t_in_seg = lane; t_in_seg < nvis; t_in_seg += 32) {
+  const uint32_t k = seg * PRE_THREADS + t_in_seg;     // slot
   const bool visible = true;
   float3 g_mean2D = {0, 0, 0};
   float4 g_conic = {0, 0, 0, 0};
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
 
 void launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream) {
   if (p.P <= 0) return;
-  preprocess_bwd_kernel<<<num_pre_blocks(p.P), BW_THREADS, 0, stream>>>(p);
+  preprocess_bwd_kernel<<<(num_pre_blocks(p.P) + BW_THREADS / 32 - 1) / (BW_THREADS / 32), BW_THREADS, 0, stream>>>(p);
   count_launch();
 }
 
