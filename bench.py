@@ -254,6 +254,8 @@ def run_gpu_arm(args, rank, world, local_rank):
     for ev in consumed:
         ev.record(torch.cuda.current_stream(device))
 
+    rasterizer = raster_cls(None)
+
     def step_e2e(i, first=False):
         q, slot = i % N_POSES, i % 2
         if first:
@@ -265,8 +267,9 @@ def run_gpu_arm(args, rank, world, local_rank):
         rs = settings_cls(image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=bg, scale_modifier=1.0,
                           viewmatrix=view, projmatrix=proj, sh_degree=m.sh_degree, campos=campos, prefiltered=False, debug=False)
         means2D = torch.zeros_like(means, requires_grad=True)
-        color, radii, depth, alpha = raster_cls(rs)(means3D=means, means2D=means2D, opacities=opac, shs=shs, scales=scales,
-                                                    rotations=rots)
+        rasterizer.raster_settings = rs          # one module, new settings per view (the attribute is the reference's own)
+        color, radii, depth, alpha = rasterizer(means3D=means, means2D=means2D, opacities=opac, shs=shs, scales=scales,
+                                                rotations=rots)
         loss = (color - target).abs().mean()
         loss.backward()
         for p_ in params:

@@ -10,6 +10,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -94,10 +95,19 @@ backward(const torch::Tensor& background, const torch::Tensor& means3D, const to
   const int64_t P = means3D.size(0), H = dL_dout_color.size(1), W = dL_dout_color.size(2);
   const int M = sh.defined() && sh.numel() != 0 ? (int)sh.size(1) : 0;
   const auto f32 = torch::TensorOptions().device(dev).dtype(torch::kFloat32);
-  // every row is written by the library (zeros for culled Gaussians): empty, not the reference's nine zeros
+  // Every row is written by the library (zeros for culled Gaussians): empty, not the reference's nine zeros.  The
+  // gradients are carved out of ONE allocation, 128-byte aligned slices in a fixed order, so that the library's dense
+  // zero fill is a single memset over the arena instead of one per tensor.
+  const int64_t widths[8] = {3, 3, 3 * (int64_t)M, 3, 1, 3, 4, 6};   // means3D, means2D, sh, colors, opacity, scales, rotations, cov3D
+  int64_t offs[8], total = 0;
+  for (int b = 0; b < 8; b++) {
+    offs[b] = total;
+    if ((needs >> b) & 1) total += (P * widths[b] + 31) / 32 * 32;
+  }
+  torch::Tensor arena = P > 0 ? torch::empty({std::max<int64_t>(total, 1)}, f32) : torch::zeros({std::max<int64_t>(total, 1)}, f32);
   auto mk = [&](int bit, std::vector<int64_t> shape) -> torch::Tensor {
     if (!((needs >> bit) & 1)) return torch::Tensor();
-    return P > 0 ? torch::empty(shape, f32) : torch::zeros(shape, f32);
+    return arena.narrow(0, offs[bit], P * widths[bit]).view(shape);
   };
   auto dL_dmeans3D = mk(0, {P, 3}), dL_dmeans2D = mk(1, {P, 3}), dL_dsh = mk(2, {P, M, 3}), dL_dcolors = mk(3, {P, 3}),
        dL_dopacity = mk(4, {P, 1}), dL_dscales = mk(5, {P, 3}), dL_drotations = mk(6, {P, 4}), dL_dcov3D = mk(7, {P, 6});
