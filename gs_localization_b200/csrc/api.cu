@@ -558,16 +558,52 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
   BinningView bl;
   carve_binning(binning_buffer, R, bl);
 
-  // Order matters for the host: the blend backward is launched first so that the GPU never waits for this
-  // function's bookkeeping; the fork event is recorded before it so that the fills do not queue behind it.
-  SideStream* ss = side_stream();
-  if (ss) GSR_CUDA(cudaEventRecord(ss->fork, stream));
+  // Dense outputs: zero rows for culled Gaussians (the reference's nine torch::zeros, rasterize_points.cu:158-166).
+  // Outputs that sit next to each other in memory (a caller carving them from one arena; gaps of alignment padding
+  // allowed) are merged.  When the blend backward runs, it writes the zeros itself between its work units — a memset
+  // on a side stream cannot overlap with it, the persistent blend CTAs leave it no SM slots (measured: the fills
+  // cost 45 us of a 0.49 ms step that way).  Otherwise (nothing rendered, unaligned spans) plain memsets.
+  struct Span { char* lo; char* hi; } spans[9];
+  int ns = 0;
+  {
+    const size_t Pz = (size_t)P;
+    struct { float* p; size_t n; } fills[] = {{dL_dmean2D, 3 * Pz}, {dL_dconic, 4 * Pz}, {dL_dopacity, Pz}, {dL_dcolor, 3 * Pz},
+                                             {dL_dmean3D, 3 * Pz}, {dL_dcov3D, 6 * Pz}, {dL_dsh, 3 * (size_t)M * Pz},
+                                             {dL_dscale, 3 * Pz}, {dL_drot, 4 * Pz}};
+    Span raw[9];
+    int nr = 0;
+    for (auto& f : fills)
+      if (f.p && f.n) raw[nr++] = Span{(char*)f.p, (char*)f.p + sizeof(float) * f.n};
+    std::sort(raw, raw + nr, [](const Span& a, const Span& b) { return a.lo < b.lo; });
+    for (int i = 0; i < nr;) {
+      Span m = raw[i];
+      int j = i + 1;
+      while (j < nr && raw[j].lo >= m.hi && raw[j].lo - m.hi <= 256) m.hi = raw[j++].hi;
+      spans[ns++] = m;
+      i = j;
+    }
+  }
+  FillSpans fused{};
+  bool fuse_fill = R > 0 && !getenv("GSR_FILL_MEMSET");
+  for (int i = 0; i < ns && fuse_fill; i++) fuse_fill = ((uintptr_t)spans[i].lo % 16 == 0);
+  if (fuse_fill) {
+    for (int i = 0; i < ns; i++) {
+      const size_t bytes = (size_t)(spans[i].hi - spans[i].lo);
+      fused.base[i] = reinterpret_cast<float4*>(spans[i].lo);
+      fused.n4[i] = bytes / 16;
+      if (bytes % 16) GSR_CUDA(cudaMemsetAsync(spans[i].lo + bytes / 16 * 16, 0, bytes % 16, stream));   // at most 12 bytes
+    }
+    fused.count = ns;
+  } else {
+    for (int i = 0; i < ns; i++) GSR_CUDA(cudaMemsetAsync(spans[i].lo, 0, (size_t)(spans[i].hi - spans[i].lo), stream));
+  }
 
   // the accumulator rows of all visible slots are zero here: the forward's scatter kernel zeroed
   // them and every preprocess-backward leaves them zero again
   StageScope* ts_r = new StageScope(ST_BWD_RENDER, stream);
   if (R > 0) {
     RenderBwdParams rb{};
+    rb.fills = fused;
     rb.W = width, rb.H = height, rb.grid_x = gx, rb.grid_y = gy;
     rb.ranges = im.ranges, rb.point_list = bl.point_list;
     rb.binning_base = binning_buffer, rb.unit_count = g.counters + 5, rb.final_cd = im.final_cd;
@@ -576,35 +612,6 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
     rb.bg = background, rb.out_alpha = out_alpha, rb.n_contrib = im.n_contrib;
     rb.dL_dpix = dL_dpix, rb.dL_ddepth = dL_ddepth, rb.dL_dalpha = dL_dalpha, rb.grad_acc = g.grad_acc;
     launch_render_bwd(rb, stream);
-  }
-
-  // dense outputs: zero rows for culled Gaussians (the reference's nine torch::zeros, rasterize_points.cu:158-166),
-  // filled on a side stream while the blend backward runs
-  {
-    cudaStream_t fill = ss ? ss->stream : stream;
-    if (ss) GSR_CUDA(cudaStreamWaitEvent(fill, ss->fork, 0));
-    const size_t Pz = (size_t)P;
-    struct { float* p; size_t n; } fills[] = {{dL_dmean2D, 3 * Pz}, {dL_dconic, 4 * Pz}, {dL_dopacity, Pz}, {dL_dcolor, 3 * Pz},
-                                             {dL_dmean3D, 3 * Pz}, {dL_dcov3D, 6 * Pz}, {dL_dsh, 3 * (size_t)M * Pz},
-                                             {dL_dscale, 3 * Pz}, {dL_drot, 4 * Pz}};
-    // cudaMemsetAsync, not a fill kernel: a kernel filling 300 MB from the side stream takes SM slots away from the
-    // blend backward and costs more than it saves in launches (measured: 1965 -> 1843 it/s).  Outputs that sit next
-    // to each other in memory (a caller carving them from one arena, gaps of alignment padding allowed) are filled
-    // by one call.
-    struct Span { char* lo; char* hi; } spans[9];
-    int ns = 0;
-    for (auto& f : fills)
-      if (f.p && f.n) spans[ns++] = Span{(char*)f.p, (char*)f.p + sizeof(float) * f.n};
-    std::sort(spans, spans + ns, [](const Span& a, const Span& b) { return a.lo < b.lo; });
-    for (int i = 0; i < ns;) {
-      char* lo = spans[i].lo;
-      char* hi = spans[i].hi;
-      int j = i + 1;
-      while (j < ns && spans[j].lo >= hi && spans[j].lo - hi <= 256) hi = spans[j++].hi;
-      GSR_CUDA(cudaMemsetAsync(lo, 0, (size_t)(hi - lo), fill));
-      i = j;
-    }
-    if (ss) GSR_CUDA(cudaEventRecord(ss->join, fill));
   }
   delete ts_r;
   GSR_STAGE("render_backward", debug, stream);
@@ -620,7 +627,6 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
   pb.dL_dmean2D = dL_dmean2D, pb.dL_dconic = dL_dconic, pb.dL_dopacity = dL_dopacity, pb.dL_dcolor = dL_dcolor;
   pb.dL_dmean3D = dL_dmean3D, pb.dL_dcov3D = dL_dcov3D, pb.dL_dsh = dL_dsh, pb.dL_dscale = dL_dscale, pb.dL_drot = dL_drot;
   pb.dL_dtau = dL_dtau;
-  if (ss) GSR_CUDA(cudaStreamWaitEvent(stream, ss->join, 0));
   {
     StageScope ts(ST_BWD_PREPROCESS, stream);
     if (R > 0) launch_preprocess_bwd(pb, stream);

@@ -101,7 +101,16 @@ struct RenderParams {
 };
 void launch_render_fwd(const RenderParams& p, cudaStream_t stream);
 
+// Dense zero rows the API owes for culled Gaussians, written by the blend backward itself between its work units
+// (a memset on a side stream cannot overlap: the persistent blend CTAs leave it no SM slots).
+struct FillSpans {
+  float4* base[9];
+  unsigned long long n4[9];   // 16-byte words per span
+  int count;
+};
+
 struct RenderBwdParams {
+  FillSpans fills;
   int W, H;
   uint32_t grid_x, grid_y;
   const uint2* ranges;
