@@ -28,10 +28,10 @@ for name in names:
             fwd = arm.c_forward(m, bg, view, proj, campos, cams[q])
             arm.c_backward(m, bg, view, proj, campos, cams[q], fwd, gC, zD, zD)
             return fwd
-        for i in range(3): fwd = step(i)
+        for i in range(2 * len(cams)): fwd = step(i)   # every pose twice: the speculative-capacity history is warm
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n = 8
+        n = 2 * len(cams)
         e0.record()
         for i in range(n): fwd = step(i)
         e1.record(); torch.cuda.synchronize()
