@@ -201,3 +201,42 @@ def test_training_step_matches_framework_iteration():
         vis = radii > 0
         assert torch.equal(model.denom.squeeze(-1), vis.float() * 1 + (model.denom.squeeze(-1) - vis.float()))
     assert float(model.denom.max()) >= 1.0 and float(model.xyz_gradient_accum.max()) > 0
+
+
+@pytest.mark.gpu
+def test_training_loop_with_densification_and_opacity_reset():
+    """A short schedule on the GPU that crosses a densification and an opacity reset: shapes stay consistent, the
+    optimiser skips exactly the groups torch would skip, the loss keeps falling on a fixed view."""
+    dev = "cuda:0"
+    cfg = dict(P=20_000, W=160, H=120, deg=1, f=120.0, box=1.0, sigma0=0.05)
+    rng = np.random.default_rng(0)
+    pts = (rng.random((cfg["P"], 3)) - 0.5) * [6, 4, 6]
+    cols = rng.random((cfg["P"], 3))
+    model = gm.GaussianModel(cfg["deg"], device=dev)
+    model.create_from_pcd(pts, cols, spatial_lr_scale=1.0)
+    assert model.get_scaling.shape == (cfg["P"], 3) and float(model.get_opacity.mean()) == pytest.approx(0.1, abs=1e-6)
+    args = gm.default_training_args(densify_from_iter=3, densification_interval=4, opacity_reset_interval=6, densify_until_iter=12,
+                                    densify_grad_threshold=1e-7)
+    model.training_setup(args)
+    bg = torch.zeros(3, device=dev)
+    cam = syn.make_camera(cfg, 0)
+    gt = torch.rand(3, cam.H, cam.W, generator=torch.Generator().manual_seed(1)).to(dev)
+    sizes, losses = [], []
+    for it in range(1, 15):
+        loss, out = model.training_step(cam, gt, bg, args, it, extent=3.0)
+        n = model.get_xyz.shape[0]
+        sizes.append(n)
+        losses.append(float(loss))
+        assert out["radii"].shape[0] <= n or out["densify"] is not None
+        for t in model._params() + model._state["m"] + model._state["v"]:
+            assert t.shape[0] == n
+        assert model.xyz_gradient_accum.shape == (n, 1) and model.denom.shape == (n, 1) and model.max_radii2D.shape == (n,)
+        assert model.get_opacity.shape == (n, 1) and model.get_rotation.shape == (n, 4)
+        if it in (4, 8):                               # densification iterations: no optimiser step at all
+            assert out["densify"] is not None and out["densify"]["after"] == n
+            assert float(model.xyz_gradient_accum.abs().sum()) == 0.0
+        if it == 6:                                    # opacity reset: that group skips one step
+            assert float(model.get_opacity.max()) <= 0.01 + 1e-6 or model._steps["opacity"] < model._steps["xyz"]
+    assert len(set(sizes)) > 1                          # the map changed size
+    assert model._steps["opacity"] < model._steps["xyz"]
+    assert np.isfinite(losses).all() and losses[4] < losses[0]    # falling until the first opacity reset (iteration 6)
