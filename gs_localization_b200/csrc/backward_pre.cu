@@ -127,8 +127,16 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
   const uint32_t nvis = seg < (uint32_t)((p.P + PRE_THREADS - 1) / PRE_THREADS) ? p.geom.block_vis[seg] : 0u;
   const int M = p.M;
   const int row = 3 * M;                 // floats per SH row
-  const float* vm = p.viewmatrix;
-  const float* proj = p.projmatrix;
+  // camera constants through shared memory: read through the global pointers they would be re-loaded after every
+  // store of the loop (possible aliasing), a dozen serialised round trips per Gaussian
+  __shared__ float s_cam[16 + 16 + 16 + 4];
+  if (tid < 16) s_cam[tid] = p.viewmatrix[tid];
+  else if (tid < 32) s_cam[tid] = p.projmatrix[tid - 16];
+  else if (tid < 48) s_cam[tid] = p.projmatrix_raw ? p.projmatrix_raw[tid - 32] : 0.f;
+  else if (tid < 51) s_cam[tid] = p.campos[tid - 48];
+  __syncthreads();
+  const float* vm = s_cam;
+  const float* proj = s_cam + 16;
   float tau[6] = {0, 0, 0, 0, 0, 0};
 
   for (uint32_t t_in_seg = lane; t_in_seg < nvis; t_in_seg += 32) {
@@ -155,7 +163,20 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
     g_color = make_float3(a1.z, a1.w, a2.x);
     const float g_depth = a2.y;
 
+    // everything this Gaussian needs from the map is requested here, in one round trip: the SH row (two or more
+    // cache lines) as L1 prefetches, the rest into registers
+    if (p.shs) {
+      const char* sh_row = reinterpret_cast<const char*>(p.shs + idx * row);
+      for (int b = 0; b < row * 4; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(sh_row + b));
+    }
     const float3 mean = {__ldg(p.means3D + 3 * idx), __ldg(p.means3D + 3 * idx + 1), __ldg(p.means3D + 3 * idx + 2)};
+    float3 sc_in = {0, 0, 0};
+    float4 q_in = {0, 0, 0, 0};
+    if (p.scales) {
+      sc_in = make_float3(__ldg(p.scales + 3 * idx), __ldg(p.scales + 3 * idx + 1), __ldg(p.scales + 3 * idx + 2));
+      q_in = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+    }
+    const uint8_t cm = p.shs ? __ldg(p.geom.clamped + k) : (uint8_t)0;
     const float* c3 = p.cov3D_precomp ? p.cov3D_precomp + 6 * idx : p.geom.cov3D + 6 * (size_t)k;
     float cov3D[6];
 #pragma unroll
@@ -237,9 +258,8 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
     // ---------------- SH (backward.cu:389-391)
     float3 g_sh_mean = {0, 0, 0};
     if (p.shs) {
-      const uint8_t cm = __ldg(p.geom.clamped + k);
       const float3 dL_dRGB = {(cm & 1) ? 0.f : g_color.x, (cm & 2) ? 0.f : g_color.y, (cm & 4) ? 0.f : g_color.z};
-      const float3 cp = {__ldg(p.campos), __ldg(p.campos + 1), __ldg(p.campos + 2)};
+      const float3 cp = {s_cam[48], s_cam[49], s_cam[50]};
       // rows of the SH gradient were zero-filled; coefficients above the active degree stay zero
       const bool vec4 = (M % 4 == 0) && (((uintptr_t)p.shs | (uintptr_t)p.dL_dsh) % 16 == 0);
       g_sh_mean = sh_backward(p.D, mean, cp, p.shs + idx * row, dL_dRGB, p.dL_dsh ? p.dL_dsh + idx * row : nullptr, vec4);
@@ -248,8 +268,8 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
 
     // ---------------- computeCov3D backward (backward.cu:278-341)
     if (p.scales) {
-      const float3 sc = {__ldg(p.scales + 3 * idx), __ldg(p.scales + 3 * idx + 1), __ldg(p.scales + 3 * idx + 2)};
-      const float4 q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+      const float3 sc = sc_in;
+      const float4 q = q_in;
       const float r = q.x, x = q.y, y = q.z, z = q.w;
       // glm columns of R
       const float Rm[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
@@ -281,7 +301,7 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
 
     // ---------------- SE(3) chain rule (pose extension), camera-space derivation
     if (p.dL_dtau) {
-      const float* raw = p.projmatrix_raw;
+      const float* raw = s_cam + 32;
       // (1) screen-space mean through projmatrix_raw applied to the camera-space point
       const float pcx = t_orig.x, pcy = t_orig.y, pcz = t_orig.z;
       const float rw = raw[3] * pcx + raw[7] * pcy + raw[11] * pcz + raw[15];
