@@ -584,7 +584,8 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
     }
   }
   FillSpans fused{};
-  bool fuse_fill = R > 0 && !getenv("GSR_FILL_MEMSET");
+  static const bool fill_with_memset = getenv("GSR_FILL_MEMSET") != nullptr;   // A/B switch for measurements
+  bool fuse_fill = R > 0 && !fill_with_memset;
   for (int i = 0; i < ns && fuse_fill; i++) fuse_fill = ((uintptr_t)spans[i].lo % 16 == 0);
   if (fuse_fill) {
     for (int i = 0; i < ns; i++) {
