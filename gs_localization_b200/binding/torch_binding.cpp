@@ -146,11 +146,86 @@ torch::Tensor mark_visible(const torch::Tensor& means3D, const torch::Tensor& vi
   return present;
 }
 
+constexpr auto forward_impl = &forward;
+constexpr auto backward_impl = &backward;
+
+// The autograd node of the plain (non-pose) rasterizer in C++: same contract as the Python
+// `_RasterizeGaussians` (reference diff_gaussian_rasterization/__init__.py:44-158: 9 inputs, 4 outputs, radii
+// non-differentiable, gradients in input order), without the Python trampoline on either side of the autograd engine.
+// The Python class remains for debug mode (its snapshot files) and for the ctypes binding.
+struct RasterizeFn : public torch::autograd::Function<RasterizeFn> {
+  static torch::autograd::variable_list forward(torch::autograd::AutogradContext* ctx, torch::Tensor means3D, torch::Tensor means2D,
+                                                torch::Tensor sh, torch::Tensor colors_precomp, torch::Tensor opacities,
+                                                torch::Tensor scales, torch::Tensor rotations, torch::Tensor cov3Ds_precomp,
+                                                torch::Tensor bg, double scale_modifier, torch::Tensor viewmatrix,
+                                                torch::Tensor projmatrix, double tanfovx, double tanfovy, int64_t image_height,
+                                                int64_t image_width, int64_t sh_degree, torch::Tensor campos, bool prefiltered) {
+    (void)means2D;   // gradient sink only, never read (reference __init__.py:60-80)
+    auto out = forward_impl(bg, means3D, colors_precomp, opacities, scales, rotations, scale_modifier, cov3Ds_precomp, viewmatrix, projmatrix,
+                         tanfovx, tanfovy, image_height, image_width, sh, sh_degree, campos, prefiltered, false, false);
+    auto& color = std::get<1>(out);
+    auto& depth = std::get<2>(out);
+    auto& alpha = std::get<3>(out);
+    auto& radii = std::get<4>(out);
+    ctx->save_for_backward({colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, std::get<5>(out), std::get<6>(out),
+                            std::get<7>(out), alpha, bg, viewmatrix, projmatrix, campos});
+    ctx->saved_data["R"] = std::get<0>(out);
+    ctx->saved_data["scale_modifier"] = scale_modifier;
+    ctx->saved_data["tanfovx"] = tanfovx;
+    ctx->saved_data["tanfovy"] = tanfovy;
+    ctx->saved_data["H"] = image_height;
+    ctx->saved_data["W"] = image_width;
+    ctx->saved_data["degree"] = sh_degree;
+    ctx->mark_non_differentiable({radii});
+    return {color, radii, depth, alpha};
+  }
+
+  static torch::autograd::variable_list backward(torch::autograd::AutogradContext* ctx, torch::autograd::variable_list grad_out) {
+    const auto saved = ctx->get_saved_variables();
+    const auto& colors_precomp = saved[0];
+    const auto& means3D = saved[1];
+    const auto& scales = saved[2];
+    const auto& rotations = saved[3];
+    const auto& cov3Ds_precomp = saved[4];
+    const auto& radii = saved[5];
+    const auto& sh = saved[6];
+    const auto& alpha = saved[10];
+    const int64_t H = ctx->saved_data["H"].toInt(), W = ctx->saved_data["W"].toInt();
+    const auto f32 = torch::TensorOptions().device(means3D.device()).dtype(torch::kFloat32);
+    torch::Tensor gC = grad_out[0].defined() ? grad_out[0] : torch::zeros({3, H, W}, f32);
+    torch::Tensor gD = grad_out[2].defined() ? grad_out[2] : torch::zeros({1, H, W}, f32);
+    torch::Tensor gA = grad_out[3].defined() ? grad_out[3] : torch::zeros({1, H, W}, f32);
+    // forward inputs 0..7: means3D, means2D, sh, colors, opacities, scales, rotations, cov3D == the bits of `needs`
+    int64_t needs = 0;
+    for (int i = 0; i < 8; i++)
+      if (ctx->needs_input_grad(i)) needs |= 1ll << i;
+    auto res = backward_impl(saved[11], means3D, radii, colors_precomp, scales, rotations, ctx->saved_data["scale_modifier"].toDouble(),
+                          cov3Ds_precomp, saved[12], saved[13], ctx->saved_data["tanfovx"].toDouble(), ctx->saved_data["tanfovy"].toDouble(),
+                          gC, gD, gA, sh, ctx->saved_data["degree"].toInt(), saved[14], saved[7], ctx->saved_data["R"].toInt(), saved[8],
+                          saved[9], alpha, false, torch::Tensor(), false, needs);
+    // res: (means2D, colors, opacity, means3D, cov3D, sh, scales, rotations, tau); gradients in forward-input order
+    torch::Tensor none;
+    return {std::get<3>(res), std::get<0>(res), std::get<5>(res), std::get<1>(res), std::get<2>(res), std::get<6>(res), std::get<7>(res),
+            std::get<4>(res), none, none, none, none, none, none, none, none, none, none, none};
+  }
+};
+
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> rasterize(
+    torch::Tensor means3D, torch::Tensor means2D, torch::Tensor sh, torch::Tensor colors_precomp, torch::Tensor opacities,
+    torch::Tensor scales, torch::Tensor rotations, torch::Tensor cov3Ds_precomp, torch::Tensor bg, double scale_modifier,
+    torch::Tensor viewmatrix, torch::Tensor projmatrix, double tanfovx, double tanfovy, int64_t image_height, int64_t image_width,
+    int64_t sh_degree, torch::Tensor campos, bool prefiltered) {
+  auto out = RasterizeFn::apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, bg, scale_modifier,
+                                viewmatrix, projmatrix, tanfovx, tanfovy, image_height, image_width, sh_degree, campos, prefiltered);
+  return {out[0], out[1], out[2], out[3]};
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("forward", &forward);
   m.def("backward", &backward);
   m.def("mark_visible", &mark_visible);
+  m.def("rasterize", &rasterize);
   m.def("abi_version", []() { return gsr_abi_version(); });
 }

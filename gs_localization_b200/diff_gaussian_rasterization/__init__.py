@@ -21,6 +21,12 @@ def cpu_deep_copy_tuple(input_tuple):
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+    rs = raster_settings
+    if _C._B is not None and not rs.debug and means3D.is_cuda:
+        # the same autograd node written in C++ (binding/torch_binding.cpp): no Python on either side of the engine
+        return _C._B.rasterize(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs.bg,
+                               float(rs.scale_modifier), rs.viewmatrix, rs.projmatrix, float(rs.tanfovx), float(rs.tanfovy),
+                               int(rs.image_height), int(rs.image_width), int(rs.sh_degree), rs.campos, bool(rs.prefiltered))
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                                      raster_settings)
 
