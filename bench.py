@@ -288,7 +288,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
     losses_read = 0
-    nw = max(3, args.warmup // 2)
+    nw = max(2 * N_POSES, args.warmup)   # every pose twice: allocator and speculative-capacity history in steady state
     for i in range(nw):
         step_e2e(i, first=(i == 0))
     torch.cuda.synchronize()

@@ -18,9 +18,28 @@ S, Rz = arm.pkg.GaussianRasterizationSettings, arm.pkg.GaussianRasterizer
 loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
 loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
 acc = [0.0] * 5
+UPLOAD = "--upload" in sys.argv
+if UPLOAD:   # bench.py's per-step H2D of the packed inputs on a copy stream
+    import ctypes
+    rt = ctypes.CDLL("libcudart.so.12")
+    rt.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+    n_in = 36 + 3 * H * W
+    host = [torch.rand(n_in).pin_memory() for _ in range(len(cams))]
+    devs = [torch.empty(n_in, device=dev) for _ in range(2)]
+    cs = torch.cuda.Stream(dev)
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    used = [torch.cuda.Event(), torch.cuda.Event()]
+    for e in used:
+        e.record()
 def step(i, record):
     q, slot = i % len(cams), i % 2
     t0 = time.perf_counter()
+    if UPLOAD:
+        nslot = (i + 1) % 2
+        cs.wait_event(used[nslot])
+        rt.cudaMemcpyAsync(devs[nslot].data_ptr(), host[(i + 1) % len(cams)].data_ptr(), n_in * 4, 1, cs.cuda_stream)
+        done[nslot].record(cs)
+        torch.cuda.current_stream().wait_event(done[slot])
     view, proj, _, campos = mats[q]
     cam = cams[q]
     rs = S(image_height=H, image_width=W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=bg, scale_modifier=1.0, viewmatrix=view,
@@ -34,6 +53,8 @@ def step(i, record):
     t3 = time.perf_counter()
     for p_ in params:
         p_.grad = None
+    if UPLOAD:
+        used[slot].record()
     loss_host[slot].copy_(loss.detach(), non_blocking=True)
     loss_ready[slot].record()
     loss_ready[1 - slot].synchronize()
