@@ -39,6 +39,8 @@ struct GeometryView {           // replaces GeometryState (reference rasterizer_
   uint32_t* gid;                // [slots] Gaussian id held by the slot
   uint32_t* block_vis;          // [ceil(P/256)] visible Gaussians of each preprocess CTA
   uint32_t* block_tiles;        // [ceil(P/256)+1] instances of each CTA
+  uint32_t* block_cand;         // [ceil(P/256)+1] candidates of each segment after the cheap cull (preprocess pass 1)
+  uint8_t* cand;                // [S] their positions inside the segment, ascending
   uint32_t* block_off;          // [ceil(P/256)+1] their exclusive prefix sum (ordered-emission path only)
   uint32_t* counters;           // [32] 1: num_rendered, 4: largest tile list
   float* grad_acc;              // [12 slots] backward accumulators, zero between uses
@@ -105,6 +107,8 @@ inline char* carve_geometry(char* base, int P, GeometryView& g) {
   carve(p, g.gid, S);
   carve(p, g.block_vis, (size_t)num_pre_blocks(P) + 1);
   carve(p, g.block_tiles, (size_t)num_pre_blocks(P) + 1);
+  carve(p, g.block_cand, (size_t)num_pre_blocks(P) + 1);
+  carve(p, g.cand, S);
   carve(p, g.block_off, (size_t)num_pre_blocks(P) + 1);
   carve(p, g.counters, (size_t)32);
   carve(p, g.grad_acc, 12 * S);

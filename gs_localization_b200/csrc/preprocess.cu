@@ -134,20 +134,17 @@ __device__ __forceinline__ float3 color_from_sh(int deg, float3 pos, float3 camp
   return make_float3(fmaxf(r0, 0.f), fmaxf(r1, 0.f), fmaxf(r2, 0.f));
 }
 
-__global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_fwd_kernel(const PreprocessParams p) {
-  __shared__ uint32_t s_warp_vis[PRE_THREADS / 32];
-  __shared__ uint32_t s_warp_tiles[PRE_THREADS / 32];
+// Pass 1, one thread per Gaussian: depth cull + conservative screen-radius bound; the survivors ("candidates") of
+// each 256-Gaussian segment are compacted, in order, into the segment's candidate list.
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_cull_kernel(const PreprocessParams p) {
   __shared__ uint32_t s_warp_near[PRE_THREADS / 32];
-  __shared__ uint8_t s_cand[PRE_THREADS];
   __shared__ float s_cam[16 + 16];
-
   const int tid = threadIdx.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
   const uint32_t block = blockIdx.x;
   const int base = (int)block * PRE_THREADS;
   const int P = p.P;
-
-  // ---- phase 1, one thread per Gaussian: everything cheap.  The reference culls only on view-space depth
+  // ---- everything cheap.  The reference culls only on view-space depth
   //      (auxiliary.h:139-164; its x/y frustum test is commented out), so about half of a room-scale map survives
   //      the cull and goes through the covariance pipeline only to end with an empty tile rectangle.  Here a
   //      conservative bound of the screen radius decides first whether the rectangle CAN be non-empty:
@@ -212,53 +209,65 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_fwd_kernel(const Pr
       if (p.n_touched) p.n_touched[idx] = 0;
     }
   }
-  // compact the candidates: phase 2 runs the covariance pipeline on dense warps
-  uint32_t n_cand;
-  {
-    const uint32_t m = __ballot_sync(0xffffffffu, near);
-    if (lane == 0) s_warp_near[warp] = __popc(m);
-    __syncthreads();
-    uint32_t off = 0, tot = 0;
+  const uint32_t m = __ballot_sync(0xffffffffu, near);
+  if (lane == 0) s_warp_near[warp] = __popc(m);
+  __syncthreads();
+  uint32_t off = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < PRE_THREADS / 32; w++) {
-      const uint32_t c = s_warp_near[w];
-      if (w < (int)warp) off += c;
-      tot += c;
-    }
-    if (near) s_cand[off + __popc(m & ((1u << lane) - 1u))] = (uint8_t)tid;
-    n_cand = tot;
-    __syncthreads();
+  for (int w = 0; w < PRE_THREADS / 32; w++) {
+    const uint32_t c = s_warp_near[w];
+    if (w < (int)warp) off += c;
+    tot += c;
   }
+  if (near) p.geom.cand[(size_t)base + off + __popc(m & ((1u << lane) - 1u))] = (uint8_t)tid;
+  if (tid == 0) p.geom.block_cand[block] = tot;
+}
 
-  // ---- phase 2, thread t < n_cand takes candidate t (ascending Gaussian order is preserved)
-  const bool work = (uint32_t)tid < n_cand;
-  const int idx = work ? base + (int)s_cand[tid] : P;
-  float px = 0.f, py = 0.f, pz = 0.f, opacity = 0.f;
-  float3 sc = {0, 0, 0};
-  float4 q = {0, 0, 0, 0};
-  float cov3D[6] = {0, 0, 0, 0, 0, 0};
-  if (work) {
-    px = __ldg(p.means3D + 3 * (size_t)idx), py = __ldg(p.means3D + 3 * (size_t)idx + 1), pz = __ldg(p.means3D + 3 * (size_t)idx + 2);
-    opacity = __ldg(p.opacities + idx);
-    if (p.cov3D_precomp) {
+// Pass 2, one WARP per segment, lanes over its candidates: the pinned-rounding covariance pipeline on dense warps, no
+// block barrier after the camera constants are staged.  Visible Gaussians are packed into the segment's slots in order
+// (ballot ranks + a running count over the warp's iterations).
+constexpr int PRE2_WARPS = 8;
+__global__ void __launch_bounds__(PRE2_WARPS * 32) preprocess_fwd_kernel(const PreprocessParams p) {
+  __shared__ float s_cam[16 + 16];
+  const int tid = threadIdx.x;
+  const uint32_t lane = tid & 31, warp = tid >> 5;
+  if (tid < 16) s_cam[tid] = p.viewmatrix[tid];
+  else if (tid < 32) s_cam[tid] = p.projmatrix[tid - 16];
+  __syncthreads();
+  const uint32_t block = blockIdx.x * PRE2_WARPS + warp;      // segment of this warp
+  if (block >= (uint32_t)((p.P + PRE_THREADS - 1) / PRE_THREADS)) return;
+  const int base = (int)block * PRE_THREADS;
+  const uint32_t n_cand = p.geom.block_cand[block];
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t nvis = 0, ntiles = 0;
+  for (uint32_t c0 = 0; c0 < n_cand; c0 += 32) {
+    const bool work = c0 + lane < n_cand;
+    const int idx = work ? base + (int)p.geom.cand[(size_t)base + c0 + lane] : p.P;
+    float px = 0.f, py = 0.f, pz = 0.f, opacity = 0.f;
+    float3 sc = {0, 0, 0};
+    float4 q = {0, 0, 0, 0};
+    float cov3D[6] = {0, 0, 0, 0, 0, 0};
+    if (work) {
+      px = __ldg(p.means3D + 3 * (size_t)idx), py = __ldg(p.means3D + 3 * (size_t)idx + 1), pz = __ldg(p.means3D + 3 * (size_t)idx + 2);
+      opacity = __ldg(p.opacities + idx);
+      if (p.cov3D_precomp) {
 #pragma unroll
-      for (int k = 0; k < 6; k++) cov3D[k] = __ldg(p.cov3D_precomp + 6 * (size_t)idx + k);
-    } else {
-      sc = make_float3(__ldg(p.scales + 3 * (size_t)idx), __ldg(p.scales + 3 * (size_t)idx + 1), __ldg(p.scales + 3 * (size_t)idx + 2));
-      q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+        for (int k = 0; k < 6; k++) cov3D[k] = __ldg(p.cov3D_precomp + 6 * (size_t)idx + k);
+      } else {
+        sc = make_float3(__ldg(p.scales + 3 * (size_t)idx), __ldg(p.scales + 3 * (size_t)idx + 1), __ldg(p.scales + 3 * (size_t)idx + 2));
+        q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+      }
     }
-  }
-
-  uint32_t tiles = 0;
-  int radius = 0;
-  float vz = 0.f, pix_x = 0.f, pix_y = 0.f;
-  float3 conic = {0, 0, 0};
-  uint2 rect = {0, 0};
-  if (work) {
-    const float* vm = s_cam;
-    const float* pm = s_cam + 16;
-    vz = __fadd_rn(dot3c(px, vm[2], py, vm[6], pz, vm[10]), vm[14]);
-    {
+    uint32_t tiles = 0;
+    int radius = 0;
+    float vz = 0.f, pix_x = 0.f, pix_y = 0.f;
+    float3 conic = {0, 0, 0};
+    uint2 rect = {0, 0};
+    if (work) {
+      const float* vm = s_cam;
+      const float* pm = s_cam + 16;
+      vz = __fadd_rn(dot3c(px, vm[2], py, vm[6], pz, vm[10]), vm[14]);
+      {
       const float vx = __fadd_rn(dot3c(px, vm[0], py, vm[4], pz, vm[8]), vm[12]);
       const float vy = __fadd_rn(dot3c(px, vm[1], py, vm[5], pz, vm[9]), vm[13]);
       const float hx = __fadd_rn(dot3c(px, pm[0], py, pm[4], pz, pm[8]), pm[12]);
@@ -293,50 +302,41 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_fwd_kernel(const Pr
           rect = make_uint2(minx | (maxx << 16), miny | (maxy << 16));
         }
       }
+      }
+      p.radii[idx] = radius;
     }
-    p.radii[idx] = radius;
-  }
-
-  // ---- pack the visible Gaussians into the CTA's slot segment (ballot ranks keep Gaussian order)
-  const bool vis = tiles != 0;
-  const uint32_t vis_mask = __ballot_sync(0xffffffffu, vis);
-  const uint32_t vis_rank_in_warp = __popc(vis_mask & ((1u << lane) - 1u));
-  const uint32_t warp_tiles = __reduce_add_sync(0xffffffffu, tiles);
-  if (lane == 0) s_warp_vis[warp] = __popc(vis_mask), s_warp_tiles[warp] = warp_tiles;
-  __syncthreads();
-  uint32_t warp_off = 0, nvis = 0, ntiles = 0;
+    const bool vis = tiles != 0;
+    const uint32_t vis_mask = __ballot_sync(0xffffffffu, vis);
+    ntiles += __reduce_add_sync(0xffffffffu, tiles);
+    if (vis) {
+      const uint32_t k = (uint32_t)base + nvis + __popc(vis_mask & lt);   // slot: segment start + rank inside the segment
+      p.geom.depths[k] = vz;
+      p.geom.means2D[k] = make_float2(pix_x, pix_y);
+      p.geom.conic_opacity[k] = make_float4(conic.x, conic.y, conic.z, opacity);
+      p.geom.rect[k] = rect;
+      p.geom.gid[k] = (uint32_t)idx;
+      if (!p.cov3D_precomp) {
 #pragma unroll
-  for (int w = 0; w < PRE_THREADS / 32; w++) {
-    const uint32_t c = s_warp_vis[w];
-    if (w < (int)warp) warp_off += c;
-    nvis += c;
-    ntiles += s_warp_tiles[w];
-  }
-  if (tid == 0) p.geom.block_vis[block] = nvis, p.geom.block_tiles[block] = ntiles;
-  if (vis) {
-    const uint32_t k = (uint32_t)base + warp_off + vis_rank_in_warp;   // slot: CTA segment start + rank inside the CTA
-    p.geom.depths[k] = vz;
-    p.geom.means2D[k] = make_float2(pix_x, pix_y);
-    p.geom.conic_opacity[k] = make_float4(conic.x, conic.y, conic.z, opacity);
-    p.geom.rect[k] = rect;
-    p.geom.gid[k] = (uint32_t)idx;
-    if (!p.cov3D_precomp) {
-#pragma unroll
-      for (int i = 0; i < 6; i++) p.geom.cov3D[6 * (size_t)k + i] = cov3D[i];
+        for (int i = 0; i < 6; i++) p.geom.cov3D[6 * (size_t)k + i] = cov3D[i];
+      }
+      // tile coverage: +1/-1 at the rectangle corners of the 2-D difference grid
+      const uint32_t minx = rect.x & 0xffffu, maxx = rect.x >> 16, miny = rect.y & 0xffffu, maxy = rect.y >> 16;
+      const uint32_t stride = p.grid_x + 1;
+      atomicAdd(p.tile_diff + (size_t)(miny * stride + minx) * DIFF_STRIDE, 1);
+      atomicAdd(p.tile_diff + (size_t)(miny * stride + maxx) * DIFF_STRIDE, -1);
+      atomicAdd(p.tile_diff + (size_t)(maxy * stride + minx) * DIFF_STRIDE, -1);
+      atomicAdd(p.tile_diff + (size_t)(maxy * stride + maxx) * DIFF_STRIDE, 1);
     }
-    // tile coverage: +1/-1 at the rectangle corners of the 2-D difference grid
-    const uint32_t minx = rect.x & 0xffffu, maxx = rect.x >> 16, miny = rect.y & 0xffffu, maxy = rect.y >> 16;
-    const uint32_t stride = p.grid_x + 1;
-    atomicAdd(p.tile_diff + (size_t)(miny * stride + minx) * DIFF_STRIDE, 1);
-    atomicAdd(p.tile_diff + (size_t)(miny * stride + maxx) * DIFF_STRIDE, -1);
-    atomicAdd(p.tile_diff + (size_t)(maxy * stride + minx) * DIFF_STRIDE, -1);
-    atomicAdd(p.tile_diff + (size_t)(maxy * stride + maxx) * DIFF_STRIDE, 1);
+    nvis += __popc(vis_mask);
   }
+  if (lane == 0) p.geom.block_vis[block] = nvis, p.geom.block_tiles[block] = ntiles;
 }
 
 void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream) {
-  preprocess_fwd_kernel<<<num_pre_blocks(p.P), PRE_THREADS, 0, stream>>>(p);
-  count_launch();
+  const int nb = num_pre_blocks(p.P);
+  preprocess_cull_kernel<<<nb, PRE_THREADS, 0, stream>>>(p);
+  preprocess_fwd_kernel<<<(nb + PRE2_WARPS - 1) / PRE2_WARPS, PRE2_WARPS * 32, 0, stream>>>(p);
+  count_launch(2);
 }
 
 // Colour of the visible Gaussians (SH -> RGB, reference forward.cu:20-71, or the caller's precomputed colours),
