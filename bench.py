@@ -400,9 +400,12 @@ def make_roofline(split, ws, cfg):
         "radix_sort": 24 * passes * R,
         "tile_ranges": 8 * R + 8 * T,
         "render": 44 * R + 24 * N,
-        "render_backward": 44 * R + 28 * N + 36 * Pv,
-        "preprocess_backward": 4 * P + (107 + 12 * M) * Pv + (64 + 12 * M) * P,  # dense gradient rows are written for all P
+        # the blend backward also writes the dense zero rows the API owes for all P Gaussians (means3D, means2D, sh,
+        # colours, opacity, scales, rotations, cov3D: 92 + 12M bytes each; SURVEY.md §8d's B_fill without the conic)
+        "render_backward": 44 * R + 28 * N + 36 * Pv + (92 + 12 * M) * P,
+        "preprocess_backward": 4 * P + (107 + 12 * M) * Pv + (64 + 12 * M) * Pv,  # only the visible rows are written here
     }
+    without_fill = {"render_backward": 44 * R + 28 * N + 36 * Pv}
     dom = max(split, key=lambda k: split[k])
     peak, how = measured_peaks()
     traffic = None
@@ -414,8 +417,9 @@ def make_roofline(split, ws, cfg):
     return {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": how,
             "algorithmic_bytes_per_launch": int(bytes_per_stage[dom]), "ms_per_launch": round(split[dom], 4),
-            "note": "blend kernels re-use each staged splat 256x from shared memory; they are issue/latency bound, "
-                    "so a low HBM fraction is expected (DESIGN.md §4)"}
+            "algorithmic_bytes_without_zero_fill": int(without_fill.get(dom, bytes_per_stage[dom])),
+            "note": "the blend backward re-uses each staged splat 256x from shared memory and is issue-bound (DESIGN.md §4); "
+                    "most of its algorithmic bytes are the dense zero rows it writes between work units"}
 
 
 # --------------------------------------------------------------------------- CPU oracle timing
