@@ -1,7 +1,7 @@
 """Host timeline of bench.py's end-to-end step (public API, deferred loss read): where the host spends a step."""
 import os, sys, time
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench
 from gs_localization_b200 import synthetic as syn

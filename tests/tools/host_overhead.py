@@ -1,7 +1,7 @@
 """Host-side cost of one forward+backward through the public API on a tiny scene (GPU time negligible)."""
 import os, sys, time
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench
 from gs_localization_b200 import synthetic as syn

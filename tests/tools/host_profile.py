@@ -1,7 +1,7 @@
 """cProfile of the public-API forward+backward on a tiny scene (host cost only)."""
 import cProfile, pstats, os, sys, io
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench
 from gs_localization_b200 import synthetic as syn

@@ -1,7 +1,7 @@
 """queries/s of the graph-replayed refinement loop on several BASELINE configs (1 GPU)."""
 import os, sys, time, json
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench
 from gs_localization_b200 import synthetic as syn, localization as loc

@@ -1,7 +1,7 @@
 """One fwd+bwd per BASELINE config: stage split (ours) and total device time (ours vs reference)."""
 import os, sys, time, json
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench
 from gs_localization_b200 import synthetic as syn, _lib

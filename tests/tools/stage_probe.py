@@ -1,7 +1,7 @@
 """Stage split of the headline workload for A/B switches set through the environment (prints one line)."""
 import os, sys, json
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench
 dev = torch.device("cuda:0")

@@ -9,7 +9,7 @@ computed locally.
 import json, os, sys, time
 import torch
 import torch.distributed as dist
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from gs_localization_b200 import synthetic as syn, parallel
 from gs_localization_b200.diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer

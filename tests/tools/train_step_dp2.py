@@ -10,7 +10,7 @@ replicas still hold identical parameters after the timed steps.
 import json, os, sys, time
 import torch
 import torch.distributed as dist
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from gs_localization_b200 import gaussian_model as gm, io as gio, synthetic as syn, parallel
 
