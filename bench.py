@@ -239,16 +239,23 @@ def run_gpu_arm(args, rank, world, local_rank):
     # the copy is issued with one cudaMemcpyAsync on the copy stream (entering a torch stream context every step costs
     # more host time than the call it wraps)
     import ctypes
-    _rt = ctypes.CDLL("libcudart.so.12")
-    _rt.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
-    _rt.cudaMemcpyAsync.restype = ctypes.c_int
+    try:
+        _rt = ctypes.CDLL("libcudart.so.12")
+        _rt.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+        _rt.cudaMemcpyAsync.restype = ctypes.c_int
+    except OSError:
+        _rt = None      # runtime library under another name: go through torch's copy_ on the copy stream
 
     def upload(i):
         q, slot = i % N_POSES, i % 2
         copy_stream.wait_event(consumed[slot])              # the step that last used this slot has finished with it
-        rc = _rt.cudaMemcpyAsync(dev_slots[slot].data_ptr(), host_packed[q].data_ptr(), n_in * 4, 1, copy_stream.cuda_stream)
-        if rc != 0:
-            raise RuntimeError(f"cudaMemcpyAsync failed ({rc})")
+        if _rt is not None:
+            rc = _rt.cudaMemcpyAsync(dev_slots[slot].data_ptr(), host_packed[q].data_ptr(), n_in * 4, 1, copy_stream.cuda_stream)
+            if rc != 0:
+                raise RuntimeError(f"cudaMemcpyAsync failed ({rc})")
+        else:
+            with torch.cuda.stream(copy_stream):
+                dev_slots[slot].copy_(host_packed[q], non_blocking=True)
         copy_done[slot].record(copy_stream)
 
     for ev in consumed:
