@@ -1,3 +1,3 @@
-# usage: bash tools/ab_env.sh VAR v1 v2 ... : stage probe per value of an A/B environment switch
+# usage: bash tests/tools/ab_env.sh VAR v1 v2 ... : stage probe per value of an A/B environment switch
 var=$1; shift
-for v in "$@"; do env $var=$v python tools/stage_probe.py 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['env'], d['ms_per_step'], d['stage_ms'])"; done
+for v in "$@"; do env $var=$v python tests/tools/stage_probe.py 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['env'], d['ms_per_step'], d['stage_ms'])"; done
