@@ -126,8 +126,8 @@ void stage_collect(cudaStream_t stream) {
   }
 }
 
-// Side stream for the dense zero-fills of the backward: they run at copy bandwidth concurrently with the
-// (compute-bound) blend backward and re-join before the per-Gaussian kernel.  Fork/join through events,
+// Side stream for the colour (SH) kernel of the forward, which nothing before the blend depends on: it runs
+// concurrently with scan_tiles / scatter / tile_sort and re-joins before the blend.  Fork/join through events,
 // which is also legal while the caller's stream is being captured into a CUDA graph.
 struct SideStream {
   cudaStream_t stream = nullptr;
