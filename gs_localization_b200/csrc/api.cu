@@ -272,8 +272,7 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     char* geom_base = geometry_alloc(gsr_geometry_bytes(P), user);
     if (!geom_base) return fail(GSR_ERR_ALLOC, "geometry_alloc returned NULL");
     carve_geometry(geom_base, P, g);
-    GSR_CUDA(cudaMemsetAsync(g.counters, 0, 32 * sizeof(uint32_t), stream));
-    GSR_CUDA(cudaMemsetAsync(im.tile_diff, 0, sizeof(int) * (size_t)(gx + 1) * (gy + 1) * DIFF_STRIDE, stream));
+    // counters and the coverage grid are zeroed by the first preprocess kernel
 
     PreprocessParams pp{};
     pp.P = P, pp.D = D, pp.M = M, pp.W = width, pp.H = height, pp.grid_x = gx, pp.grid_y = gy;
@@ -462,8 +461,7 @@ int gsr_rasterize_forward_async(char* geometry_buffer, char* binning_buffer, lon
   carve_image(image_buffer, width, height, im);
   BinningView bl;
   carve_binning(binning_buffer, binning_capacity, bl, global_sort != 0, width, height);
-  GSR_CUDA(cudaMemsetAsync(g.counters, 0, 32 * sizeof(uint32_t), stream));
-  GSR_CUDA(cudaMemsetAsync(im.tile_diff, 0, sizeof(int) * (size_t)(gx + 1) * (gy + 1) * DIFF_STRIDE, stream));
+  // counters and the coverage grid are zeroed by the first preprocess kernel
   PreprocessParams pp{};
   pp.P = P, pp.D = D, pp.M = M, pp.W = width, pp.H = height, pp.grid_x = gx, pp.grid_y = gy;
   pp.means3D = means3D, pp.scales = scales, pp.rotations = rotations, pp.opacities = opacities, pp.shs = shs;

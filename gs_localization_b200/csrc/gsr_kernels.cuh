@@ -27,7 +27,7 @@ struct PreprocessParams {
   int sh_vec4;          // SH rows are 16-byte aligned and a multiple of 4 floats long
   int* radii;
   int* n_touched;       // may be null
-  int* tile_diff;       // [(grid_y+1)(grid_x+1)], zeroed before the launch
+  int* tile_diff;       // [(grid_y+1)(grid_x+1)], zeroed by preprocess_cull_kernel
   GeometryView geom;
 };
 

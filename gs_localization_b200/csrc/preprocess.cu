@@ -144,6 +144,13 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_cull_kernel(const Prep
   const uint32_t block = blockIdx.x;
   const int base = (int)block * PRE_THREADS;
   const int P = p.P;
+  // the frame's counters and coverage grid start at zero: done here (this is the first kernel of a forward and the
+  // grid's first atomics come from the next one) instead of two memset nodes in front of it
+  if (block == 0 && tid < 32) p.geom.counters[tid] = 0;
+  {
+    const uint32_t n_diff = (p.grid_x + 1) * (p.grid_y + 1) * (uint32_t)DIFF_STRIDE;
+    for (uint32_t i = block * PRE_THREADS + tid; i < n_diff; i += gridDim.x * PRE_THREADS) p.tile_diff[i] = 0;
+  }
   // ---- everything cheap.  The reference culls only on view-space depth
   //      (auxiliary.h:139-164; its x/y frustum test is commented out), so about half of a room-scale map survives
   //      the cull and goes through the covariance pipeline only to end with an empty tile rectangle.  Here a
