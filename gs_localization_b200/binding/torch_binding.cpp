@@ -161,6 +161,7 @@ struct RasterizeFn : public torch::autograd::Function<RasterizeFn> {
                                                 torch::Tensor projmatrix, double tanfovx, double tanfovy, int64_t image_height,
                                                 int64_t image_width, int64_t sh_degree, torch::Tensor campos, bool prefiltered) {
     (void)means2D;   // gradient sink only, never read (reference __init__.py:60-80)
+    ctx->set_materialize_grads(false);   // outputs the loss does not use arrive as undefined gradients, not as zero tensors + fill kernels
     auto out = forward_impl(bg, means3D, colors_precomp, opacities, scales, rotations, scale_modifier, cov3Ds_precomp, viewmatrix, projmatrix,
                          tanfovx, tanfovy, image_height, image_width, sh, sh_degree, campos, prefiltered, false, false);
     auto& color = std::get<1>(out);
@@ -193,8 +194,8 @@ struct RasterizeFn : public torch::autograd::Function<RasterizeFn> {
     const int64_t H = ctx->saved_data["H"].toInt(), W = ctx->saved_data["W"].toInt();
     const auto f32 = torch::TensorOptions().device(means3D.device()).dtype(torch::kFloat32);
     torch::Tensor gC = grad_out[0].defined() ? grad_out[0] : torch::zeros({3, H, W}, f32);
-    torch::Tensor gD = grad_out[2].defined() ? grad_out[2] : torch::zeros({1, H, W}, f32);
-    torch::Tensor gA = grad_out[3].defined() ? grad_out[3] : torch::zeros({1, H, W}, f32);
+    const torch::Tensor& gD = grad_out[2];   // undefined == no upstream gradient: the library takes NULL for these two
+    const torch::Tensor& gA = grad_out[3];
     // forward inputs 0..7: means3D, means2D, sh, colors, opacities, scales, rotations, cov3D == the bits of `needs`
     int64_t needs = 0;
     for (int i = 0; i < 8; i++)

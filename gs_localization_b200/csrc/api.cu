@@ -543,7 +543,7 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
   if (dL_dtau) GSR_CUDA(cudaMemsetAsync(dL_dtau, 0, 6 * sizeof(float), stream));
   if (P == 0) return GSR_OK;   // reference rasterize_points.cu:168
   if (!geometry_buffer || !image_buffer || !binning_buffer) return fail(GSR_ERR_INVALID_ARGUMENT, "scratch buffers are required");
-  if (!background || !means3D || !out_alpha || !viewmatrix || !projmatrix || !cam_pos || !radii || !dL_dpix || !dL_ddepth || !dL_dalpha)
+  if (!background || !means3D || !out_alpha || !viewmatrix || !projmatrix || !cam_pos || !radii || !dL_dpix)   // dL_ddepth / dL_dalpha may be NULL: no upstream gradient on that output
     return fail(GSR_ERR_INVALID_ARGUMENT, "null required pointer");
   if (dL_dtau && !projmatrix_raw) return fail(GSR_ERR_INVALID_ARGUMENT, "projmatrix_raw is required for the pose gradient");
   (void)colors_precomp;

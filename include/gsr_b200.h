@@ -122,6 +122,9 @@ GSR_API int gsr_read_counters(const char* geometry_buffer, int P, unsigned int* 
  *   dL_dmean2D[P,3], dL_dconic[P,4] (x,y,_,w as the reference's float4), dL_dopacity[P],
  *   dL_dcolor[P,3], dL_dmean3D[P,3], dL_dcov3D[P,6], dL_dsh[P,M,3], dL_dscale[P,3], dL_drot[P,4]
  *
+ * Upstream gradients: dL_dpix[3,H,W] is required; dL_ddepth[H,W] and dL_dalpha[H,W] may be NULL, meaning no
+ * gradient flows into that output (the same result as a tensor of zeros, without the tensor).
+ *
  * Pose extension (diff_gaussian_rasterization_pose surface used by
  * gs_localization/pipelines/tools/__init__.py:58-141): when dL_dtau is non-NULL, six floats
  * [d/drho(3), d/dtheta(3)] of the loss w.r.t. the left perturbation T_w2c <- exp(tau) T_w2c

@@ -307,3 +307,30 @@ def test_backward_with_masked_upstream_gradients():
     want = run_oracle(m, cam, bg, "f64").backward(wc, wd, wa)
     for k in ("dL_dmeans2D", "dL_dopacity", "dL_dmeans3D", "dL_dsh", "dL_dscales", "dL_drotations"):
         assert util.rel_err(got[k], want[k]) <= GRAD_REL_TOL, k
+
+
+def test_unused_outputs_need_no_zero_gradients():
+    """A loss on the colour image alone reaches the library with NULL depth / alpha upstream gradients (the compiled
+    autograd node does not materialise them); the result must equal the same loss with explicit zero gradients."""
+    from gs_localization_b200.diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    m, cam = util.scene(**SCENES["deg1"])
+    view, proj, _, campos = cam.matrices(DEV)
+    bg = torch.tensor([0.2, 0.1, 0.3], device=DEV)
+    d = m.to(DEV)
+    w = torch.from_numpy(np.random.default_rng(5).standard_normal((3, cam.H, cam.W)).astype(np.float32)).to(DEV)
+    rs = GaussianRasterizationSettings(cam.H, cam.W, cam.tanfovx, cam.tanfovy, bg, 1.0, view, proj, m.sh_degree, campos, False, False)
+
+    def grads(explicit_zeros):
+        params = [t.clone().requires_grad_(True) for t in (d.means3D, d.shs, d.opacities, d.scales, d.rotations)]
+        m2 = torch.zeros_like(params[0], requires_grad=True)
+        color, radii, depth, alpha = GaussianRasterizer(rs)(means3D=params[0], means2D=m2, opacities=params[2], shs=params[1],
+                                                             scales=params[3], rotations=params[4])
+        loss = (color * w).sum()
+        if explicit_zeros:
+            loss = loss + (depth * 0.0).sum() + (alpha * 0.0).sum()
+        loss.backward()
+        return [p.grad.cpu().numpy() for p in params] + [m2.grad.cpu().numpy()]
+
+    for a, b in zip(grads(False), grads(True)):
+        assert np.isfinite(a).all() and np.abs(a).max() > 0
+        assert util.rel_err(a, b) <= 1e-4
