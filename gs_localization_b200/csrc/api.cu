@@ -334,7 +334,7 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
       GSR_STAGE("scatter", debug, stream);
       {
         StageScope ts(ST_SORT, stream);
-        launch_tile_sort(T, im.ranges, bl.comp, bl.point_list, (uint32_t)capacity, stream);
+        launch_tile_sort(T, im.ranges, bl.comp, bl.point_list, (uint32_t)capacity, im.tile_order, stream);
       }
       GSR_STAGE("tile_sort", debug, stream);
     } else if (capacity > 0) {
@@ -487,7 +487,7 @@ int gsr_rasterize_forward_async(char* geometry_buffer, char* binning_buffer, lon
   const BinHeader hv{(unsigned long long)binning_capacity, bl.units_off, bl.ckpt_off};
   if (!global_sort) {
     launch_scatter(P, g, im.tile_cursor, bl.comp, gx, hv, hdr, stream);
-    launch_tile_sort(T, im.ranges, bl.comp, bl.point_list, (uint32_t)binning_capacity, stream);
+    launch_tile_sort(T, im.ranges, bl.comp, bl.point_list, (uint32_t)binning_capacity, im.tile_order, stream);
   } else {
     const int end_bit = sort_end_bit(width, height);
     const int passes = sort_passes(end_bit);

@@ -24,6 +24,8 @@
 //      budget are sorted by the same network directly in global memory (L2).
 // The onesweep radix sort (Adinets & Merrill) that replaces cub::DeviceRadixSort as a library
 // primitive is kept below and exported as gsr_sort_pairs.
+#include <cstdlib>
+
 #include "gsr_kernels.cuh"
 
 namespace gsr {
@@ -458,9 +460,12 @@ __device__ __forceinline__ void tile_sort_small(const uint64_t* __restrict__ com
 }
 
 __global__ void __launch_bounds__(TS_THREADS) tile_sort_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ comp,
-                                                               uint32_t* __restrict__ point_list, uint32_t capacity) {
+                                                               uint32_t* __restrict__ point_list, uint32_t capacity,
+                                                               const uint32_t* __restrict__ tile_order) {
   __shared__ uint64_t s_keys[TS_SMEM_KEYS];
-  const uint2 rg = ranges[blockIdx.x];
+  // longest lists first (the blend kernels' launch order): a 4096-key network takes many times longer than the median
+  // tile's, and started late it finishes the kernel alone
+  const uint2 rg = ranges[tile_order ? tile_order[blockIdx.x] : blockIdx.x];
   const uint32_t start = min(rg.x, capacity), end = min(rg.y, capacity);
   if (end <= start) return;
   const uint32_t n = end - start;
@@ -486,9 +491,10 @@ __global__ void __launch_bounds__(TS_THREADS) tile_sort_kernel(const uint2* __re
 }
 
 void launch_tile_sort(int num_tiles, const uint2* ranges, uint64_t* comp, uint32_t* point_list, uint32_t capacity,
-                      cudaStream_t stream) {
+                      const uint32_t* tile_order, cudaStream_t stream) {
   if (num_tiles <= 0) return;
-  tile_sort_kernel<<<num_tiles, TS_THREADS, 0, stream>>>(ranges, comp, point_list, capacity);
+  static const bool natural = getenv("GSR_SORT_NATURAL_ORDER") != nullptr;   // A/B switch for measurements
+  tile_sort_kernel<<<num_tiles, TS_THREADS, 0, stream>>>(ranges, comp, point_list, capacity, natural ? nullptr : tile_order);
   count_launch();
 }
 

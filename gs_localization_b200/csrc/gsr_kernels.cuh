@@ -67,7 +67,7 @@ void launch_emit_ordered(int P, const GeometryView& g, uint64_t* keys, uint32_t*
                          BinHeader* header, cudaStream_t stream);
 void launch_reset_cursors(int T, const uint2* ranges, uint32_t* cursor, cudaStream_t stream);
 // per-tile sort of the buckets on the composite key; writes the sorted slots to point_list
-void launch_tile_sort(int num_tiles, const uint2* ranges, uint64_t* comp, uint32_t* point_list, uint32_t capacity,
+void launch_tile_sort(int num_tiles, const uint2* ranges, uint64_t* comp, uint32_t* point_list, uint32_t capacity, const uint32_t* tile_order,
                       cudaStream_t stream);
 // library radix sort (gsr_sort_pairs): the element count is a host upper bound and, optionally, a device pointer
 void launch_sort_histogram(const uint64_t* keys, const uint32_t* n_ptr, long long n_host, int end_bit, uint32_t* hist,
