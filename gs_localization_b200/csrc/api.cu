@@ -599,8 +599,8 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
 
   // the accumulator rows of all visible slots are zero here: the forward's scatter kernel zeroed
   // them and every preprocess-backward leaves them zero again
-  StageScope* ts_r = new StageScope(ST_BWD_RENDER, stream);
   if (R > 0) {
+    StageScope ts(ST_BWD_RENDER, stream);
     RenderBwdParams rb{};
     rb.fills = fused;
     rb.W = width, rb.H = height, rb.grid_x = gx, rb.grid_y = gy;
@@ -612,7 +612,6 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
     rb.dL_dpix = dL_dpix, rb.dL_ddepth = dL_ddepth, rb.dL_dalpha = dL_dalpha, rb.grad_acc = g.grad_acc;
     launch_render_bwd(rb, stream);
   }
-  delete ts_r;
   GSR_STAGE("render_backward", debug, stream);
 
   PreBwdParams pb{};
