@@ -157,13 +157,14 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
     float4* acc = reinterpret_cast<float4*>(p.geom.grad_acc + 12 * (size_t)k);
     const float4 a0 = acc[0], a1 = acc[1], a2 = acc[2];
     acc[0] = acc[1] = acc[2] = make_float4(0.f, 0.f, 0.f, 0.f);   // leave the row zero for the next backward
-    // moments -> gradients: the blend backward accumulates S = sum over pixels of u * (dx, dy, dx^2, dx dy, dy^2, 1) with
+    // moments -> gradients: the blend backward accumulates Q S1 (first moments sum u (dx, dy), conic applied per lane) and
+    // the second and zeroth moments sum u * (dx^2, dx dy, dy^2, 1) with
     // u = G * dL/dalpha; the per-Gaussian factors of backward.cu:549-578 (dL_dG = opacity * ..., dG/ddel through the conic,
     // ddelx_dx = W/2, the -0.5 of the conic terms) are applied here, once per Gaussian instead of once per pixel.
     {
       const float4 co = __ldg(p.geom.conic_opacity + k);
       const float ddelx_dx = 0.5f * p.W, ddely_dy = 0.5f * p.H;
-      g_mean2D = make_float3(ddelx_dx * co.w * (-(co.x * a0.x) - co.y * a0.y), ddely_dy * co.w * (-(co.z * a0.y) - co.y * a0.x), 0.f);
+      g_mean2D = make_float3(ddelx_dx * co.w * -a0.x, ddely_dy * co.w * -a0.y, 0.f);   // a0.xy = Q S, the conic already applied per lane
       const float mh = -0.5f * co.w;
       g_conic = make_float4(mh * a0.z, mh * a0.w, 0.f, mh * a1.x);
       g_opacity = a1.y;

@@ -128,7 +128,7 @@ struct RenderBwdParams {
   const float* dL_dpix;
   const float* dL_ddepth;
   const float* dL_dalpha;
-  float* grad_acc;           // [slots][12]: moments sum u*(dx, dy, dx^2, dx dy, dy^2, 1) (-> mean2D, conic, opacity), rgb, depth, pad, pad
+  float* grad_acc;           // [slots][12]: Q*sum u*(dx, dy), sum u*(dx^2, dx dy, dy^2, 1) (-> mean2D, conic, opacity), rgb, depth, pad, pad
 };
 void launch_render_bwd(const RenderBwdParams& p, cudaStream_t stream);
 
