@@ -182,3 +182,37 @@ def test_full_tracking_loss_loops_agree():
     assert float(exposure[0]) > 0.005                              # gain moved toward log(1.03)
     e0, e1 = syn.pose_error(start.w2c, gt.w2c), syn.pose_error(w_graph.cpu(), gt.w2c)
     assert e1[0] < e0[0] and e1[1] < e0[1], (e0, e1)
+
+
+def test_refined_pose_matches_oracle_loop_c2():
+    """Config C2 (300K Gaussians, 640x480, SH degree 3): 24 pose-refinement steps, the CUDA path (framework loop and the
+    CUDA-graph refiner) against the float64 CPU oracle driving the identical Adam / update_pose loop.
+    north_star: final refined poses within 1 mm / 0.01 degrees."""
+    cfg = syn.CONFIGS["C2"]
+    m = syn.make_map(cfg["P"], cfg["deg"], cfg["sigma0"], cfg["box"], seed=0)
+    gt = syn.make_camera(cfg, 4)
+    dm = m.to(DEV)
+    target_t = loc.render_pose(dm, loc.PoseCamera(gt, DEV), torch.zeros(3, device=DEV))[0].detach()
+    target = target_t.cpu().numpy()
+    start = gt.perturbed(syn.initial_perturbation(4, trans_m=0.02, rot_deg=1.0))
+    iters = 24
+
+    pc = loc.PoseCamera(start, DEV)
+    w2c_cuda, _ = loc.refine_pose(dm, pc, target_t, iters=iters, lr=1e-3)
+    pg = loc.PoseCamera(start, DEV)
+    w2c_graph, _ = loc.GraphRefiner(dm, pg, lr=1e-3).refine(pg, target_t, iters=iters)
+
+    oc = loc.PoseCamera(start, "cpu")
+    opt = torch.optim.Adam([{"params": [oc.cam_rot_delta], "lr": 1e-3}, {"params": [oc.cam_trans_delta], "lr": 1e-3}])
+    for _ in range(iters):
+        _, tau = _oracle_loss_and_tau(m, oc.world_view_transform, oc.full_proj_transform, oc.camera_center, start, target)
+        opt.zero_grad(set_to_none=True)
+        oc.cam_trans_delta.grad = torch.from_numpy(tau[:3].astype(np.float32))
+        oc.cam_rot_delta.grad = torch.from_numpy(tau[3:].astype(np.float32))
+        opt.step()
+        oc.update_pose()
+    for w in (w2c_cuda, w2c_graph):
+        dt, dr = syn.pose_error(w.cpu(), oc.w2c)
+        assert dt <= 1e-3 and dr <= 0.01, (dt, dr)
+    e0, e1 = syn.pose_error(start.w2c, gt.w2c), syn.pose_error(w2c_cuda.cpu(), gt.w2c)
+    assert e1[0] < e0[0] and e1[1] < e0[1], (e0, e1)
