@@ -15,6 +15,18 @@
 
 namespace gsr {
 std::atomic<unsigned long long> g_launch_count{0};
+
+int sm_count() {
+  static std::atomic<int> cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
 }
 using namespace gsr;
 
@@ -69,13 +81,16 @@ char* carve_binning(char* base, long long cap, BinningView& b, bool global_path 
     p += sort_temp_bytes(cap, sort_passes(sort_end_bit(W, H)));
     b.comp = nullptr;
   }
-  b.units = nullptr, b.ckpt = nullptr, b.units_off = b.ckpt_off = 0;
+  b.units = nullptr, b.ckpt = nullptr, b.rec = nullptr, b.units_off = b.ckpt_off = b.rec_off = b.units_cap = 0;
   if (W > 0 && H > 0) {
     const size_t tiles = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
     const size_t nu = max_units(cap, tiles);
-    carve(p, b.units, nu);
-    carve(p, b.ckpt, nu * CKPT_FLOATS);
+    b.units_cap = 4 * BSEG_PER_SEG * nu;
+    carve(p, b.units, 2 * b.units_cap);
+    carve(p, b.ckpt, BSEG_PER_SEG * nu * CKPT_FLOATS);
+    carve(p, b.rec, nu * REC_FLOAT4);
     b.units_off = (size_t)((char*)b.units - base), b.ckpt_off = (size_t)((char*)b.ckpt - base);
+    b.rec_off = (size_t)((char*)b.rec - base);
   }
   return p;
 }
@@ -179,9 +194,10 @@ long long round_capacity(long long c) {
   return (c + step - 1) / step * step;
 }
 void capacity_guess(int P, int W, int H, long long& cap, long long& longest) {
-  static const bool disabled = getenv("GSR_NO_SPECULATION") != nullptr;   // A/B switch for measurements
   cap = longest = 0;
-  if (disabled) return;
+#ifdef GSR_AB_NO_SPECULATION      // measurement build: wait for num_rendered like the reference
+  return;
+#endif
   for (auto& h : t_hist)
     if (h.P == P && h.W == W && h.H == H && h.n > 0) {
       long long m = 0, l = 0;
@@ -267,7 +283,17 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
   BinningView bl{};
   Mailbox* box = nullptr;
   SideStream* color_side = nullptr;
-  bool color_joined = false;
+  bool color_joined = false, count_waited = false;
+  // Whatever path leaves this function (error returns included): the num_rendered copy into this thread's pinned mailbox
+  // has landed — a later forward must never see a stale copy arrive after it wrote its sentinel — and the colour side
+  // stream has re-joined the caller's stream, so that its kernel cannot race with the caller freeing the scratch.
+  struct Cleanup {
+    Mailbox*& box; SideStream*& side; bool& joined; bool& waited; cudaStream_t stream;
+    ~Cleanup() {
+      if (box && !waited) cudaEventSynchronize(box->ready);
+      if (side && !joined) cudaStreamWaitEvent(stream, side->join, 0);
+    }
+  } cleanup{box, color_side, color_joined, count_waited, stream};
   if (P > 0) {
     char* geom_base = geometry_alloc(gsr_geometry_bytes(P), user);
     if (!geom_base) return fail(GSR_ERR_ALLOC, "geometry_alloc returned NULL");
@@ -329,7 +355,7 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     if (capacity > 0 && !global_path) {
       {
         StageScope ts(ST_DUPLICATE, stream);
-        launch_scatter(P, g, im.tile_cursor, bl.comp, gx, BinHeader{(unsigned long long)capacity, bl.units_off, bl.ckpt_off}, bin_header, stream);
+        launch_scatter(P, g, im.tile_cursor, bl.comp, gx, BinHeader{(unsigned long long)capacity, bl.units_off, bl.ckpt_off, bl.rec_off, bl.units_cap}, bin_header, stream);
       }
       GSR_STAGE("scatter", debug, stream);
       {
@@ -352,7 +378,7 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
       {
         StageScope ts(ST_DUPLICATE, stream);
         sort_temp_reset(bl.sort_temp, capacity, passes, stream);
-        launch_emit_ordered(P, g, keys[0], vals[0], gx, BinHeader{(unsigned long long)capacity, bl.units_off, bl.ckpt_off}, bin_header, stream);
+        launch_emit_ordered(P, g, keys[0], vals[0], gx, BinHeader{(unsigned long long)capacity, bl.units_off, bl.ckpt_off, bl.rec_off, bl.units_cap}, bin_header, stream);
       }
       GSR_STAGE("emit_ordered", debug, stream);
       {
@@ -365,11 +391,11 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     RenderParams rp{};
     rp.W = width, rp.H = height, rp.grid_x = gx, rp.grid_y = gy;
     rp.ranges = im.ranges, rp.point_list = bl.point_list, rp.tile_order = (P > 0) ? im.tile_order : nullptr;
-    rp.means2D = g.means2D, rp.conic_opacity = g.conic_opacity, rp.rgbd = g.rgbd, rp.gid = g.gid;
+    rp.mean_tau = g.mean_tau, rp.conic_opacity = g.conic_opacity, rp.rgbd = g.rgbd, rp.gid = g.gid;
     rp.bg = background, rp.out_color = out_color, rp.out_depth = out_depth, rp.out_alpha = out_alpha;
     rp.n_contrib = im.n_contrib, rp.n_touched = (P > 0) ? n_touched : nullptr;
     rp.capacity = (uint32_t)capacity;
-    rp.final_cd = im.final_cd, rp.units = bl.units, rp.ckpt = bl.ckpt, rp.unit_count = (P > 0) ? g.counters + 5 : nullptr;
+    rp.final_cd = im.final_cd, rp.units = bl.units, rp.ckpt = bl.ckpt, rp.rec = bl.rec, rp.units_cap = (uint32_t)bl.units_cap, rp.unit_count = (P > 0) ? g.counters + 5 : nullptr;
     if (color_side && !color_joined) {
       GSR_CUDA(cudaStreamWaitEvent(stream, color_side->join, 0));
       color_joined = true;
@@ -414,6 +440,7 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
       }
       if (*v == 0xffffffffu) GSR_CUDA(cudaEventSynchronize(box->ready));
     }
+    count_waited = true;
     R = (long long)box->value[0];
     longest = (long long)box->value[4];
     remember_count(P, width, height, R, longest);
@@ -484,7 +511,7 @@ int gsr_rasterize_forward_async(char* geometry_buffer, char* binning_buffer, lon
   }
   launch_scan_tiles(im.tile_diff, gx, gy, im.ranges, im.tile_cursor, im.tile_order, g.counters, (uint32_t)binning_capacity, stream);
   BinHeader* hdr = reinterpret_cast<BinHeader*>(binning_buffer);
-  const BinHeader hv{(unsigned long long)binning_capacity, bl.units_off, bl.ckpt_off};
+  const BinHeader hv{(unsigned long long)binning_capacity, bl.units_off, bl.ckpt_off, bl.rec_off, bl.units_cap};
   if (!global_sort) {
     launch_scatter(P, g, im.tile_cursor, bl.comp, gx, hv, hdr, stream);
     launch_tile_sort(T, im.ranges, bl.comp, bl.point_list, (uint32_t)binning_capacity, im.tile_order, stream);
@@ -505,8 +532,8 @@ int gsr_rasterize_forward_async(char* geometry_buffer, char* binning_buffer, lon
   RenderParams rp{};
   rp.W = width, rp.H = height, rp.grid_x = gx, rp.grid_y = gy;
   rp.ranges = im.ranges, rp.point_list = bl.point_list, rp.tile_order = im.tile_order;
-  rp.final_cd = im.final_cd, rp.units = bl.units, rp.ckpt = bl.ckpt, rp.unit_count = g.counters + 5;
-  rp.means2D = g.means2D, rp.conic_opacity = g.conic_opacity, rp.rgbd = g.rgbd, rp.gid = g.gid;
+  rp.final_cd = im.final_cd, rp.units = bl.units, rp.ckpt = bl.ckpt, rp.rec = bl.rec, rp.units_cap = (uint32_t)bl.units_cap, rp.unit_count = g.counters + 5;
+  rp.mean_tau = g.mean_tau, rp.conic_opacity = g.conic_opacity, rp.rgbd = g.rgbd, rp.gid = g.gid;
   rp.bg = background, rp.out_color = out_color, rp.out_depth = out_depth, rp.out_alpha = out_alpha;
   rp.n_contrib = im.n_contrib, rp.n_touched = n_touched, rp.capacity = (uint32_t)binning_capacity;
   if (ss) GSR_CUDA(cudaStreamWaitEvent(stream, ss->join, 0));
@@ -522,10 +549,20 @@ int gsr_read_counters(const char* geometry_buffer, int P, unsigned int* out, voi
   if (!geometry_buffer || P <= 0 || !out) return fail(GSR_ERR_INVALID_ARGUMENT, "bad arguments");
   GeometryView g;
   carve_geometry(const_cast<char*>(geometry_buffer), P, g);
-  uint32_t h[8];
+  uint32_t h[32];
   GSR_CUDA(cudaMemcpyAsync(h, g.counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
   GSR_CUDA(cudaStreamSynchronize(stream));
-  out[0] = h[1], out[1] = h[3], out[2] = h[4];
+  out[0] = h[1], out[1] = (h[3] | h[16]) ? 1u : 0u, out[2] = h[4];
+  return GSR_OK;
+}
+
+// The overflow flag returned by gsr_read_counters is sticky across forwards on the same geometry buffer (a CUDA graph
+// replays many forwards between two reads); this clears it.  Call once after allocating the buffer and per query.
+int gsr_clear_overflow(char* geometry_buffer, int P, void* stream_) {
+  if (!geometry_buffer || P <= 0) return fail(GSR_ERR_INVALID_ARGUMENT, "bad arguments");
+  GeometryView g;
+  carve_geometry(geometry_buffer, P, g);
+  GSR_CUDA(cudaMemsetAsync(g.counters + 16, 0, 16 * sizeof(uint32_t), (cudaStream_t)stream_));
   return GSR_OK;
 }
 
@@ -558,7 +595,7 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
 
   // Dense outputs: zero rows for culled Gaussians (the reference's nine torch::zeros, rasterize_points.cu:158-166).
   // Outputs that sit next to each other in memory (a caller carving them from one arena; gaps of alignment padding
-  // allowed) are merged.  When the blend backward runs, it writes the zeros itself between its work units — a memset
+  // below 128 bytes are zeroed with them — documented in include/gsr_b200.h) are merged.  When the blend backward runs, it writes the zeros itself between its work units — a memset
   // on a side stream cannot overlap with it, the persistent blend CTAs leave it no SM slots (measured: the fills
   // cost 45 us of a 0.49 ms step that way).  Otherwise (nothing rendered, unaligned spans) plain memsets.
   struct Span { char* lo; char* hi; } spans[9];
@@ -576,14 +613,17 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
     for (int i = 0; i < nr;) {
       Span m = raw[i];
       int j = i + 1;
-      while (j < nr && raw[j].lo >= m.hi && raw[j].lo - m.hi <= 256) m.hi = raw[j++].hi;
+      while (j < nr && raw[j].lo >= m.hi && raw[j].lo - m.hi < 128) m.hi = raw[j++].hi;   // contract: include/gsr_b200.h
       spans[ns++] = m;
       i = j;
     }
   }
   FillSpans fused{};
-  static const bool fill_with_memset = getenv("GSR_FILL_MEMSET") != nullptr;   // A/B switch for measurements
-  bool fuse_fill = R > 0 && !fill_with_memset;
+#ifdef GSR_AB_FILL_MEMSET          // measurement build: zero rows by cudaMemsetAsync
+  bool fuse_fill = false;
+#else
+  bool fuse_fill = R > 0;
+#endif
   for (int i = 0; i < ns && fuse_fill; i++) fuse_fill = ((uintptr_t)spans[i].lo % 16 == 0);
   if (fuse_fill) {
     for (int i = 0; i < ns; i++) {
@@ -604,10 +644,8 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
     RenderBwdParams rb{};
     rb.fills = fused;
     rb.W = width, rb.H = height, rb.grid_x = gx, rb.grid_y = gy;
-    rb.ranges = im.ranges, rb.point_list = bl.point_list;
-    rb.binning_base = binning_buffer, rb.unit_count = g.counters + 5, rb.final_cd = im.final_cd;
-    rb.max_units = (uint32_t)max_units(R, (size_t)gx * gy);
-    rb.means2D = g.means2D, rb.conic_opacity = g.conic_opacity, rb.rgbd = g.rgbd;
+    rb.binning_base = binning_buffer, rb.unit_count = g.counters + 5, rb.queue = g.counters + 6, rb.final_cd = im.final_cd;
+    rb.max_units = (uint32_t)(4 * BSEG_PER_SEG * max_units(R, (size_t)gx * gy));
     rb.bg = background, rb.out_alpha = out_alpha, rb.n_contrib = im.n_contrib;
     rb.dL_dpix = dL_dpix, rb.dL_ddepth = dL_ddepth, rb.dL_dalpha = dL_dalpha, rb.grad_acc = g.grad_acc;
     launch_render_bwd(rb, stream);
@@ -656,7 +694,7 @@ __global__ void export_geometry_kernel(GeometryView g, float* depths, float* mea
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   const size_t i = g.gid[k];
   if (depths) depths[i] = g.depths[k];
-  if (means2D) means2D[2 * i] = g.means2D[k].x, means2D[2 * i + 1] = g.means2D[k].y;
+  if (means2D) means2D[2 * i] = g.mean_tau[k].x, means2D[2 * i + 1] = g.mean_tau[k].y;
   if (cov3D)
     for (int q = 0; q < 6; q++) cov3D[6 * i + q] = g.cov3D[6 * (size_t)k + q];
   if (conic_opacity) {

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(ST_THREADS) scan_tiles_kernel(int* __restrict_
     const uint32_t m = __reduce_max_sync(0xffffffffu, s_max[lane]);
     if (lane == 31) {
       counters[1] = wi;                          // num_rendered
-      if (capacity && wi > capacity) counters[3] = 1;   // sync-free forward: the caller's binning buffer is too small
+      if (capacity && wi > capacity) counters[3] = 1, counters[16] = 1;   // sync-free forward: the caller's binning buffer is too small (16: sticky copy)
     }
     if (lane == 0) counters[4] = m, s_max[0] = m;  // longest tile list
   }
@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict
   __shared__ uint32_t s_wsum[8];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (header) *header = hv;
-    *unit_count = 0;   // the forward blend appends the backward's work units
+    unit_count[0] = 0;   // the forward blend appends the backward's work units ...
+    unit_count[3] = unit_count[4] = unit_count[5] = unit_count[6] = 0;   // ... in four cost classes
   }
   const uint32_t cnt = block_vis[blockIdx.x];
   if (cnt == 0) return;
@@ -493,8 +494,7 @@ __global__ void __launch_bounds__(TS_THREADS) tile_sort_kernel(const uint2* __re
 void launch_tile_sort(int num_tiles, const uint2* ranges, uint64_t* comp, uint32_t* point_list, uint32_t capacity,
                       const uint32_t* tile_order, cudaStream_t stream) {
   if (num_tiles <= 0) return;
-  static const bool natural = getenv("GSR_SORT_NATURAL_ORDER") != nullptr;   // A/B switch for measurements
-  tile_sort_kernel<<<num_tiles, TS_THREADS, 0, stream>>>(ranges, comp, point_list, capacity, natural ? nullptr : tile_order);
+  tile_sort_kernel<<<num_tiles, TS_THREADS, 0, stream>>>(ranges, comp, point_list, capacity, tile_order);
   count_launch();
 }
 
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(256) sort_histogram_kernel(const uint64_t* __r
 void launch_sort_histogram(const uint64_t* keys, const uint32_t* n_ptr, long long n_host, int end_bit, uint32_t* hist,
                            cudaStream_t stream) {
   if (n_host <= 0) return;
-  const int blocks = (int)std::min<long long>((n_host + 256 * 8 - 1) / (256 * 8), 148 * 4);
+  const int blocks = (int)std::min<long long>((n_host + 256 * 8 - 1) / (256 * 8), sm_count() * 4);
   sort_histogram_kernel<<<blocks, 256, 0, stream>>>(keys, n_ptr, (uint32_t)n_host, end_bit, hist);
   count_launch();
 }

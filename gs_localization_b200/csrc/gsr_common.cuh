@@ -30,7 +30,7 @@ __device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f,
 // slot order == Gaussian order, so ties keep the reference's order.  No CTA depends on another.
 struct GeometryView {           // replaces GeometryState (reference rasterizer_impl.h:29-44)
   float* depths;                // [slots] view-space z
-  float2* means2D;              // [slots] pixel-space centre
+  float4* mean_tau;             // [slots] (pixel-space centre x, y, 2 ln(255 o) inflated: the opacity-aware culling bound, unused)
   float4* conic_opacity;        // [slots] (conic.x, conic.y, conic.z, opacity)
   float4* rgbd;                 // [slots] (r, g, b, depth): one 16-byte gather for the blend kernels
   float* cov3D;                 // [6 slots]
@@ -42,7 +42,8 @@ struct GeometryView {           // replaces GeometryState (reference rasterizer_
   uint32_t* block_cand;         // [ceil(P/256)+1] candidates of each segment after the cheap cull (preprocess pass 1)
   uint8_t* cand;                // [S] their positions inside the segment, ascending
   uint32_t* block_off;          // [ceil(P/256)+1] their exclusive prefix sum (ordered-emission path only)
-  uint32_t* counters;           // [32] 1: num_rendered, 4: largest tile list
+  uint32_t* counters;           // [32] 1: num_rendered, 3: overflow, 4: largest tile list, 5: backward units, 6-7: backward queue,
+                                //      8-11: units per cost class, 16: sticky overflow
   float* grad_acc;              // [12 slots] backward accumulators, zero between uses
 };
 
@@ -69,20 +70,34 @@ struct BinningView {            // replaces BinningState (reference rasterizer_i
   char* sort_temp;
   // backward work units and the forward's per-segment pixel checkpoints (both layouts; offsets are from the buffer base
   // and are recorded in the header by the scatter kernel, because the backward is not told the capacity)
-  uint2* units;                 // [max_units] (tile, segment)
-  float* ckpt;                  // [max_units][5][256]  T, C0, C1, C2, D of the tile's pixels at the start of a segment
-  size_t units_off, ckpt_off;
+  uint4* units;                 // [2][units_cap] (tile | quadrant << 30, segment, range start, range end): one per 8x8 pixel quadrant and
+                                //   piece, in four cost classes (render.cu); units_cap = 16 max_units
+  float* ckpt;                  // [4 max_units][5][256]  T, C0, C1, C2, D of the tile's pixels in front of a backward piece
+  float4* rec;                  // [4 max_units][BSEG][3] the forward's staged 48-byte splat records of every batch it blended, contiguous:
+                                //                     the backward fetches a piece with one bulk copy (cp.async.bulk, 3 KB)
+  size_t units_off, ckpt_off, rec_off, units_cap;
 };
 
-// The blend backward runs one CTA per (tile, segment of SEG list entries); the forward leaves the pixel state at every
-// segment boundary so that a segment can be walked back to front without the ones behind it.
+// The forward blends a tile's list in batches of SEG entries; the backward walks it in independent pieces of BSEG
+// entries (one warp per (tile, 8x8 pixel quadrant, piece)): the forward leaves the pixel state at every BSEG boundary so
+// that a piece can be walked back to front without the ones behind it.
 constexpr int SEG = 256;
+constexpr int BSEG = 64;
+constexpr int BSEG_PER_SEG = SEG / BSEG;
 constexpr int CKPT_FLOATS = 5 * 256;
-struct BinHeader { unsigned long long capacity, units_off, ckpt_off; };
+constexpr int REC_BYTES = 48;               // staged splat record: (x, y, 2 tau, slot bits) (conic x, y, z, opacity) (r, g, b, depth)
+constexpr int REC_FLOAT4 = SEG * REC_BYTES / 16;   // float4 words per batch of records
+constexpr int BREC_FLOAT4 = BSEG * REC_BYTES / 16; // float4 words per backward piece
+struct BinHeader { unsigned long long capacity, units_off, ckpt_off, rec_off, units_cap; };
 inline size_t max_units(long long cap, size_t tiles) { return (size_t)(cap / SEG) + tiles + 2; }
-// slot of tile t's checkpoint for segment r: sum_{i<t} ceil(len_i / SEG) <= floor(start_t / SEG) + t, and consecutive
+// slot of tile t's batch r: sum_{i<t} ceil(len_i / SEG) <= floor(start_t / SEG) + t, and consecutive
 // tiles never overlap, so no prefix sum over segment counts is needed
 __host__ __device__ inline uint32_t ckpt_slot(uint32_t range_start, uint32_t tile, uint32_t seg) { return range_start / SEG + tile + seg; }
+// slot of tile t's backward piece s (list positions [s BSEG, (s+1) BSEG)): 4 (floor(start_t / SEG) + t) + s; the slots of a tile
+// end at most 4 floor(len_t / SEG) + 4 after its base, which is where the next tile's begin at the earliest
+__host__ __device__ inline uint32_t piece_slot(uint32_t range_start, uint32_t tile, uint32_t piece) {
+  return BSEG_PER_SEG * (range_start / SEG + tile) + piece;
+}
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -98,7 +113,7 @@ inline char* carve_geometry(char* base, int P, GeometryView& g) {
   char* p = base;
   const size_t S = (size_t)num_pre_blocks(P) * PRE_THREADS;
   carve(p, g.depths, S);
-  carve(p, g.means2D, S);
+  carve(p, g.mean_tau, S);
   carve(p, g.conic_opacity, S);
   carve(p, g.rgbd, S);
   carve(p, g.cov3D, 6 * S);
@@ -151,6 +166,17 @@ __device__ __forceinline__ float dot3c(float a0, float b0, float a1, float b1, f
   t = __fmaf_rn(a0, b0, t);
   t = __fmaf_rn(a2, b2, t);
   return t;
+}
+
+// A splat can only reach alpha = min(0.99, o * exp(power)) >= 1/255 where power >= -tau, tau = ln(255 o),
+// i.e. inside the ellipse Q(d) = a dx^2 + 2 b dx dy + c dy^2 <= 2 tau around its centre.  two_tau is
+// inflated (0.1 % + 1e-3) so that rounding in the exact per-pixel test can never accept a pixel this bound
+// rejects; < 0 means "never visible" (o < 1/255), +inf disables culling (degenerate conic).
+__device__ __forceinline__ float splat_two_tau(float a, float b, float c, float opacity) {
+  const float o255 = opacity * 255.0f;
+  if (!(o255 >= 1.0f)) return -1.0f;
+  if (!(a * c - b * b > 0.f) || !(a > 0.f) || !(c > 0.f)) return __int_as_float(0x7f800000);
+  return 2.0f * __logf(o255) * 1.001f + 1e-3f;
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }

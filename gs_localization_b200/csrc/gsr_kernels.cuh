@@ -83,7 +83,7 @@ struct RenderParams {
   const uint2* ranges;
   const uint32_t* tile_order;   // CTA index -> tile (longest lists first)
   const uint32_t* point_list;   // sorted slots
-  const float2* means2D;
+  const float4* mean_tau;      // (x, y, 2 tau, -) per slot
   const float4* conic_opacity;
   const float4* rgbd;        // (r, g, b, depth) per slot
   const uint32_t* gid;       // slot -> Gaussian id (n_touched only)
@@ -95,9 +95,11 @@ struct RenderParams {
   int* n_touched;            // may be null
   uint32_t capacity;         // entries of point_list that exist (speculative launch: ranges may exceed it)
   float4* final_cd;          // [N] final (C0, C1, C2, D) for the segment-parallel backward
-  uint2* units;              // backward work units appended here, *unit_count of them
+  uint4* units;              // backward work units appended here, *unit_count of them
   float* ckpt;               // pixel state at segment boundaries
-  uint32_t* unit_count;
+  float4* rec;               // staged records of every blended segment, for the backward's bulk copies
+  uint32_t units_cap;        // entries per unit array
+  uint32_t* unit_count;      // counters + 5: [0] units, [3..6] units per cost class
 };
 void launch_render_fwd(const RenderParams& p, cudaStream_t stream);
 
@@ -113,15 +115,11 @@ struct RenderBwdParams {
   FillSpans fills;
   int W, H;
   uint32_t grid_x, grid_y;
-  const uint2* ranges;
-  const char* binning_base;     // BinHeader at offset 0: where the units and checkpoints of this forward live
+  const char* binning_base;     // BinHeader at offset 0: where the units, checkpoints and records of this forward live
   const uint32_t* unit_count;
+  uint32_t* queue;              // [2] ticket counter + finished-CTA counter of the unit queue, zero between launches
   const float4* final_cd;
-  uint32_t max_units;           // launch bound: floor(R / SEG) + T + 2
-  const uint32_t* point_list;   // sorted visible ranks
-  const float2* means2D;
-  const float4* conic_opacity;
-  const float4* rgbd;
+  uint32_t max_units;           // launch bound: 4 (floor(R / SEG) + T + 2)
   const float* bg;
   const float* out_alpha;
   const uint32_t* n_contrib;
@@ -131,6 +129,9 @@ struct RenderBwdParams {
   float* grad_acc;           // [slots][12]: Q*sum u*(dx, dy), sum u*(dx^2, dx dy, dy^2, 1) (-> mean2D, conic, opacity), rgb, depth, pad, pad
 };
 void launch_render_bwd(const RenderBwdParams& p, cudaStream_t stream);
+
+// SM count of the current device (cached per device)
+int sm_count();
 
 // ---- preprocess backward (backward_pre.cu)
 struct PreBwdParams {

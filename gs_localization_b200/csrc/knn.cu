@@ -264,7 +264,7 @@ int launch_dist2_knn3(const float* points, long long P, float* mean_dists, char*
   const int n = (int)P;
   const int nb = (n + KNN_BOX - 1) / KNN_BOX, nsb = (nb + KNN_SUPER - 1) / KNN_SUPER;
   knn_bounds_init_kernel<<<1, 32, 0, stream>>>(w.bounds);
-  knn_bounds_kernel<<<std::min((n + 255) / 256, 148 * 8), 256, 0, stream>>>(points, n, w.bounds);
+  knn_bounds_kernel<<<std::min((n + 255) / 256, sm_count() * 8), 256, 0, stream>>>(points, n, w.bounds);
   knn_morton_kernel<<<(n + 255) / 256, 256, 0, stream>>>(points, n, w.bounds, w.keys[0], w.vals[0]);
   SortTemp st;
   const int end_bit = 63, passes = sort_passes(end_bit);

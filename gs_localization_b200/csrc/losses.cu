@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256) depth_loss_grad_kernel(const float* __res
 void launch_depth_loss_grad(const float* depth, const float* pseudo, const float* gt, int n, float k, float w_pearson, float w_l1,
                             float* loss, float* dL_ddepth, double* scratch, cudaStream_t stream) {
   cudaMemsetAsync(scratch, 0, 9 * sizeof(double), stream);
-  const int blocks = std::min((n + 255) / 256, 148 * 4);
+  const int blocks = std::min((n + 255) / 256, sm_count() * 4);
   depth_loss_sums_kernel<<<blocks, 256, 0, stream>>>(depth, pseudo, gt, n, k, scratch);
   depth_loss_grad_kernel<<<blocks, 256, 0, stream>>>(depth, pseudo, gt, n, k, w_pearson, w_l1, scratch, dL_ddepth, loss);
   count_launch(2);

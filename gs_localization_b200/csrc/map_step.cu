@@ -144,7 +144,7 @@ void launch_map_step(const MapStepParams& s, float beta1, float beta2, float eps
   count_launch();
   if (s.do_adam && s.features && (s.lr_f_dc >= 0.f || s.lr_f_rest >= 0.f)) {
     const size_t n = (size_t)s.P * s.M * 3;
-    const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)148 * 16);
+    const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)sm_count() * 16);
     map_features_step_kernel<<<blocks, 256, 0, stream>>>((float4*)s.features, (const float4*)s.g_features, (float4*)s.m_features,
                                                          (float4*)s.v_features, n, s.M * 3, s.lr_f_dc, s.lr_f_rest, a);
     count_launch();

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) l1_loss_grad_kernel(const float* __restri
 void launch_l1_loss_grad(const float* image, const float* target, float* dL_dimage, size_t n, float weight, float* loss_out,
                          cudaStream_t stream) {
   if (n == 0) return;
-  const int blocks = (int)std::min<size_t>((n + 256 * 4 - 1) / (256 * 4), 148 * 4);
+  const int blocks = (int)std::min<size_t>((n + 256 * 4 - 1) / (256 * 4), sm_count() * 4);
   l1_loss_grad_kernel<<<blocks, 256, 0, stream>>>(image, target, dL_dimage, n, weight / (float)n, loss_out);
   count_launch();
 }
@@ -106,7 +106,7 @@ void launch_tracking_loss_grad(const float* image, const float* depth, const flo
                                const float* grad_mask, const float* exposure, int npix, float opacity_threshold, float depth_weight,
                                float* dL_dimage, float* dL_ddepth, float* loss_out, float* dL_dexposure, cudaStream_t stream) {
   if (npix <= 0) return;
-  const int blocks = std::min((npix + 255) / 256, 148 * 4);
+  const int blocks = std::min((npix + 255) / 256, sm_count() * 4);
   tracking_loss_grad_kernel<<<blocks, 256, 0, stream>>>(image, depth, opacity, gt_image, gt_depth, grad_mask, exposure, npix,
                                                         opacity_threshold, depth_weight, dL_dimage, dL_ddepth, loss_out, dL_dexposure);
   count_launch();

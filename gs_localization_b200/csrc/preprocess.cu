@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_cull_kernel(const Prep
   const int P = p.P;
   // the frame's counters and coverage grid start at zero: done here (this is the first kernel of a forward and the
   // grid's first atomics come from the next one) instead of two memset nodes in front of it
-  if (block == 0 && tid < 32) p.geom.counters[tid] = 0;
+  // (words 16..31 are sticky across forwards: 16 = "some forward overflowed the binning capacity", cleared by gsr_clear_overflow)
+  if (block == 0 && tid < 16) p.geom.counters[tid] = 0;
   {
     const uint32_t n_diff = (p.grid_x + 1) * (p.grid_y + 1) * (uint32_t)DIFF_STRIDE;
     for (uint32_t i = block * PRE_THREADS + tid; i < n_diff; i += gridDim.x * PRE_THREADS) p.tile_diff[i] = 0;
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(PRE2_WARPS * 32) preprocess_fwd_kernel(const P
     if (vis) {
       const uint32_t k = (uint32_t)base + nvis + __popc(vis_mask & lt);   // slot: segment start + rank inside the segment
       p.geom.depths[k] = vz;
-      p.geom.means2D[k] = make_float2(pix_x, pix_y);
+      p.geom.mean_tau[k] = make_float4(pix_x, pix_y, splat_two_tau(conic.x, conic.y, conic.z, opacity), 0.f);
       p.geom.conic_opacity[k] = make_float4(conic.x, conic.y, conic.z, opacity);
       p.geom.rect[k] = rect;
       p.geom.gid[k] = (uint32_t)idx;

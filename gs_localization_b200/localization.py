@@ -349,6 +349,10 @@ class GraphRefiner:
             self.grad_mask.fill_(1.0)
         for t in (self.adam_m, self.adam_v, self.step, self.exposure, self.dL_dexposure, self.exp_m, self.exp_v, self.exp_step):
             t.zero_()
+        # the overflow flag is sticky across the replays of a query (any iteration that exceeded the binning capacity
+        # invalidates the trajectory); it is cleared here and read once in collect()
+        self._lib.check(self.lib.gsr_clear_overflow(self.geom.data_ptr(), self.P, torch.cuda.current_stream(self.dev).cuda_stream),
+                        "gsr_clear_overflow")
 
     def _counters(self):
         cnt = (self.C.c_uint * 3)()

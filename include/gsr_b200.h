@@ -110,11 +110,19 @@ GSR_API int gsr_rasterize_forward_async(
     float tan_fovx, float tan_fovy,
     float* out_color, float* out_depth, float* out_alpha, int* radii, int* n_touched, void* stream);
 GSR_API int gsr_read_counters(const char* geometry_buffer, int P, unsigned int* out3, void* stream);
+/* The overflow flag reported by gsr_read_counters is STICKY: it stays set until cleared, however many forwards ran on the
+ * geometry buffer in between (a CUDA graph replays many forwards between two reads).  Clear it once after allocating the
+ * buffer (its contents are otherwise undefined) and whenever a new query starts. */
+GSR_API int gsr_clear_overflow(char* geometry_buffer, int P, void* stream);
 
 /*
  * Backward.  Replaces CudaRasterizer::Rasterizer::backward (rasterizer_impl.cu:343-444,
  * declared rasterizer.h:62-88) as called from RasterizeGaussiansBackwardCUDA
  * (rasterize_points.cu:170-203).
+ *
+ * Zero-fill contract: output buffers that lie within 128 bytes of each other (one arena carved into 128-byte
+ * aligned slices, or a framework allocator's padding) are zero-filled as ONE span, gap included — do not keep live
+ * data in a gap smaller than 128 bytes between two gradient outputs.
  *
  * Gradient outputs are written densely for ALL P Gaussians (invisible ones get zeros), so
  * the caller does NOT need to zero-fill them first (the reference needs nine torch::zeros,

@@ -1,8 +1,21 @@
-"""Stage split of the headline workload for A/B switches set through the environment (prints one line)."""
+"""Stage split of a workload (default: headline), one JSON line.
+
+A/B against another build of the library: GSR_AB_LIB=/path/to/other/libgsr_b200.so runs the same probe on that .so
+through the ctypes binding (e.g. ab/libgsr_b200_r1.so, the end-of-round-1 kernels, built by tests/tools/build_ab_lib.sh);
+the stage times are CUDA-event device times, so the binding does not enter them."""
 import os, sys, json
-import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+if os.environ.get("GSR_AB_LIB"):
+    os.environ["GSR_BINDING"] = "ctypes"
+    from gs_localization_b200 import _lib as _l
+    _l.LIB_PATH = os.path.abspath(os.environ["GSR_AB_LIB"])
+    import ctypes as _C
+    _probe = _C.CDLL(_l.LIB_PATH)
+    for _name in list(_l.SIGNATURES):
+        if not hasattr(_probe, _name):
+            del _l.SIGNATURES[_name]          # symbols added after that build
+import torch
 import bench
 dev = torch.device("cuda:0")
 arm = bench.Arm("ours", dev)
@@ -27,5 +40,5 @@ arm.lib.stage_timing(True)
 for i in range(32): step(i)
 torch.cuda.synchronize()
 split = arm.lib.stage_times()
-print(json.dumps({"env": {k: v for k, v in os.environ.items() if k.startswith("GSR_")}, "ms_per_step": round(total, 4),
+print(json.dumps({"lib": os.environ.get("GSR_AB_LIB", "in-tree"), "workload": sys.argv[1] if len(sys.argv) > 1 else "headline", "ms_per_step": round(total, 4),
                   "stage_ms": {k: round(v, 4) for k, v in split.items()}}))
