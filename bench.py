@@ -195,16 +195,20 @@ def run_gpu_arm(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     sampler.start()
     torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    # one event per step boundary: total = first -> last (the reported mean), plus the per-step median
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record()
     Rs = []
     for i in range(args.steps):
         Rs.append(step_device(i))
-    ev1.record()
+        evs[i + 1].record()
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = evs[0].elapsed_time(evs[-1])
+    per_step = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps))
+    stats["ms_per_step_median"] = per_step[len(per_step) // 2]
+    stats["ms_per_step_p10_p90"] = [per_step[len(per_step) // 10], per_step[(len(per_step) * 9) // 10]]
     launches = (arm.lib.launch_count() - launches0) if arm.lib else 0
 
     # ---- e2e: public API, host inputs, wall clock
@@ -335,7 +339,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         rng = st["ranges"].to(torch.int64)
         workload_stats = dict(P=cfg["P"], Pv=Pv, R=int(Rq), N=W * H, T=int(rng.shape[0]), n_contrib_sum=n_contrib_sum,
                               mean_n_contrib=n_contrib_sum / (W * H))
-        roofline = make_roofline(split, workload_stats, cfg)
+        roofline = make_roofline(split, workload_stats, cfg, ms_total / args.steps)
     # ---- localized queries/s (second half of BASELINE's metric): full pose refinements through the pose API,
     # queries sharded over ranks with no collective; fixed iteration count, convergence break disabled
     queries_s = None
@@ -387,46 +391,123 @@ def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         try:
-            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)", float(d.get("sm_max_mhz", 1965.0))
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)", 1965.0
 
 
-def make_roofline(split, ws, cfg):
-    """Roofline of the dominant kernel.  Algorithmic bytes per launch from DESIGN.md §4
-    (SURVEY.md §8d terms restricted to that kernel)."""
+def kernel_source_sha256():
+    """Hash of the kernel sources the timed library was built from: a committed ncu profile is only used if it was
+    captured on exactly these sources."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(glob.glob(os.path.join(ROOT, "gs_localization_b200", "csrc", "*.cu")) +
+                   glob.glob(os.path.join(ROOT, "gs_localization_b200", "csrc", "*.cuh")) +
+                   [os.path.join(ROOT, "include", "gsr_b200.h")])
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
+PROFILE_JSON = os.path.join(ROOT, "profiles", "r2_roofline_profile.json")   # written by tests/tools/make_roofline_profile.py
+STAGE_KERNELS = {   # stage of gsr_stage_timing -> kernels of the ncu capture that run inside it
+    "preprocess": ["preprocess_cull_kernel", "preprocess_fwd_kernel", "color_fwd_kernel"],
+    "tile_ranges": ["scan_tiles_kernel"],
+    "duplicate_with_keys": ["scatter_kernel"],
+    "radix_sort": ["tile_sort_kernel", "long_tile"],
+    "render": ["render_fwd_kernel"],
+    "render_backward": ["render_bwd_kernel"],
+    "preprocess_backward": ["preprocess_bwd_kernel"],
+}
+
+
+def load_profile():
+    """(per-stage {dram_bytes, warp_instructions, ncu_us} per launch, note).  None if absent or captured on other sources."""
+    try:
+        d = json.load(open(PROFILE_JSON))
+    except Exception:
+        return None, "no committed ncu profile (profiles/r2_roofline_profile.json)"
+    if d.get("source_sha256") != kernel_source_sha256():
+        return None, "committed ncu profile is STALE (captured on other kernel sources) - not used"
+    out = {}
+    for stage, names in STAGE_KERNELS.items():
+        rows = [k for k in d["kernels"] if any(n in k["name"] for n in names)]
+        if rows:
+            out[stage] = {"dram_bytes": sum(k["dram_bytes_per_launch"] for k in rows),
+                          "warp_instructions": sum(k["warp_instructions_per_launch"] for k in rows),
+                          "ncu_us": sum(k["us_per_launch"] for k in rows)}
+    return out, f"ncu --set full capture of these sources (git {d.get('git', '?')}, {d.get('when', '?')}): {os.path.relpath(PROFILE_JSON, ROOT)}"
+
+
+def make_roofline(split, ws, cfg, ms_per_step):
+    """Roofline record: the dominant kernel against the bound that actually limits it, every stage against HBM on its
+    algorithmic bytes (SURVEY.md section 8d terms regrouped for the fused kernels; zero rows counted separately), and the
+    whole iteration on SURVEY section 8d's B_fwd + B_bwd.  Everything needed to recompute it is in the record."""
     if not split:
         return None
     M = (cfg["deg"] + 1) ** 2
     P, Pv, R, N, T = ws["P"], ws["Pv"], ws["R"], ws["N"], ws["T"]
     passes = -(-(32 + max(1, (T - 1).bit_length())) // 8)
-    bytes_per_stage = {
-        "preprocess": 44 * P + 12 * M * Pv + 8 * P + 4 * P + 75 * Pv,        # reads + radii/tiles/offsets + per-visible records
-        "duplicate_with_keys": 8 * P + 16 * Pv + 12 * R,
-        "radix_sort": 24 * passes * R,
-        "tile_ranges": 8 * R + 8 * T,
-        "render": 44 * R + 24 * N,
-        # the blend backward also writes the dense zero rows the API owes for all P Gaussians (means3D, means2D, sh,
-        # colours, opacity, scales, rotations, cov3D: 92 + 12M bytes each; SURVEY.md §8d's B_fill without the conic)
-        "render_backward": 44 * R + 28 * N + 36 * Pv + (92 + 12 * M) * P,
-        "preprocess_backward": 4 * P + (107 + 12 * M) * Pv + (64 + 12 * M) * Pv,  # only the visible rows are written here
+    fill = (92 + 12 * M) * P        # dense zero rows of the eight returned gradient tensors (B_fill without the internal conic)
+    alg = {
+        "preprocess": 44 * P + 12 * M * Pv + 4 * P + 97 * Pv,      # map read + SH rows of the visible + radii + per-visible records (89 B) + rect (8 B)
+        "tile_ranges": 12 * T,
+        "duplicate_with_keys": 12 * Pv + 8 * R + 48 * Pv,          # rect+depth per visible, one 8-byte composite per instance, accumulator rows zeroed
+        "radix_sort": 8 * R + 4 * R,                               # tile-local sort: read the composites once, write the sorted slots
+        "render": 52 * R + 24 * N + 48 * R + 20 * N,               # gather (4 + 48 B) per instance, images, + the record stream and the checkpoints it leaves for the backward (>= 1 per 64 entries blended)
+        "render_backward": 48 * R + 28 * N + 36 * Pv,              # record stream back in, per-pixel reads, accumulator rows
+        "preprocess_backward": 4 * P + (107 + 12 * M) * Pv + (64 + 12 * M) * Pv,
     }
-    without_fill = {"render_backward": 44 * R + 28 * N + 36 * Pv}
-    dom = max(split, key=lambda k: split[k])
-    peak, how = measured_peaks()
-    traffic = None
-    try:   # per-launch DRAM bytes of that kernel from the committed ncu --set full capture
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json"))).get(dom)
+    peak, how, sm_mhz = measured_peaks()
+    prof, prof_note = load_profile()
+    try:
+        sms = torch.cuda.get_device_properties(0).multi_processor_count
     except Exception:
-        pass
-    achieved = bytes_per_stage[dom] / (split[dom] * 1e-3) / 1e9 if split[dom] > 0 else 0.0
-    return {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": how,
-            "algorithmic_bytes_per_launch": int(bytes_per_stage[dom]), "ms_per_launch": round(split[dom], 4),
-            "algorithmic_bytes_without_zero_fill": int(without_fill.get(dom, bytes_per_stage[dom])),
-            "note": "the blend backward re-uses each staged splat 256x from shared memory and is issue-bound (DESIGN.md §4); "
-                    "most of its algorithmic bytes are the dense zero rows it writes between work units"}
+        sms = 148
+    issue_peak = sms * 4 * sm_mhz * 1e6            # warp instructions per second: one per SM sub-partition and cycle
+    stages = {}
+    for k, ms in split.items():
+        if ms <= 0:
+            continue
+        e = {"ms": round(ms, 4), "algorithmic_bytes": int(alg[k]), "hbm_frac": round(alg[k] / (ms * 1e-3) / 1e9 / peak, 4)}
+        if k == "render_backward":
+            e["algorithmic_bytes_with_zero_rows"] = int(alg[k] + fill)
+            e["hbm_frac_with_zero_rows"] = round((alg[k] + fill) / (ms * 1e-3) / 1e9 / peak, 4)
+        if prof and k in prof:
+            e["dram_bytes_ncu"] = int(prof[k]["dram_bytes"])
+            e["warp_instructions_ncu"] = int(prof[k]["warp_instructions"])
+            e["issue_frac"] = round(prof[k]["warp_instructions"] / (ms * 1e-3) / issue_peak, 4)
+        stages[k] = e
+    dom = max(split, key=lambda k: split[k])
+    d = stages[dom]
+    blend = dom in ("render", "render_backward")
+    rec = {"kernel": dom, "ms_per_launch": d["ms"], "peak_source": how, "profile": prof_note}
+    if blend and "issue_frac" in d:
+        # the blend kernels re-use every staged record for 64 pixels out of shared memory: instruction issue bounds them, not bytes
+        rec.update(bound="issue", achieved=round(d["warp_instructions_ncu"] / (d["ms"] * 1e-3) / 1e9, 2), peak=round(issue_peak / 1e9, 2),
+                   unit="Gwarp-inst/s", frac=d["issue_frac"],
+                   how="warp instructions per launch (smsp__inst_executed.sum of the committed ncu capture) / live CUDA-event time / "
+                       f"({sms} SMs x 4 schedulers x {sm_mhz:.0f} MHz)")
+    else:
+        rec.update(bound="hbm", achieved=round(d["algorithmic_bytes"] / (d["ms"] * 1e-3) / 1e9, 2), peak=peak, unit="GB/s", frac=d["hbm_frac"])
+    rec["traffic"] = d.get("dram_bytes_ncu")
+    rec["hbm"] = {"algorithmic_bytes_per_launch": d["algorithmic_bytes"], "frac": d["hbm_frac"],
+                  "frac_with_zero_rows": d.get("hbm_frac_with_zero_rows"), "peak_GBs": peak}
+    # whole iteration, SURVEY.md section 8d
+    b_fwd = 64 * P + (83 + 12 * M) * Pv + (72 + 24 * passes) * R + 24 * N + 8 * T
+    b_bwd = 44 * R + 28 * N + 4 * P + (207 + 24 * M) * Pv
+    b_fill = (108 + 12 * M) * P
+    it = {"B_fwd": int(b_fwd), "B_bwd": int(b_bwd), "B_fill": int(b_fill), "passes_reference_sort": passes, "ms_per_step": round(ms_per_step, 4),
+          "hbm_frac": round((b_fwd + b_bwd) / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+          "hbm_frac_with_fill": round((b_fwd + b_bwd + b_fill) / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+          "formula": "SURVEY.md section 8d (the REFERENCE pipeline's bytes for this frame: what a byte-for-byte port would move)"}
+    rec["stages"] = stages
+    rec["iteration"] = it
+    return rec
 
 
 # --------------------------------------------------------------------------- CPU oracle timing
@@ -499,7 +580,9 @@ def main():
         ms_total, e2e_s, queries_s = float(t[0]), float(t[1]), float(t[2])
     if rank == 0:
         value = world * args.steps / (ms_total * 1e-3)
-        line = dict(base, value=round(value, 3), ms_per_step=round(ms_total / args.steps, 4), clocks=st["clocks"],
+        line = dict(base, value=round(value, 3), ms_per_step=round(ms_total / args.steps, 4),
+                    ms_per_step_median=round(st["ms_per_step_median"], 4), ms_per_step_p10_p90=[round(x, 4) for x in st["ms_per_step_p10_p90"]],
+                    clocks=st["clocks"],
                     e2e={"value": round(world * args.steps / e2e_s, 3), "unit": "iterations/s",
                          "h2d_bytes_per_step": st["h2d"], "d2h_bytes_per_step": st["d2h"]},
                     gpu_launches=int(st["launches"]))
@@ -527,7 +610,8 @@ def main():
                 # secondary roofline of the two blend kernels: contributing (pixel, splat) pairs against the
                 # FP32 non-tensor peak, 148 SMs x 128 lanes x 2 FLOP x max clock; ~34 FLOP/pair forward, ~90 backward
                 kc = pairs["pairs_contributing"]
-                peak_tf = 148 * 128 * 2 * 1.965e9 / 1e12
+                props = torch.cuda.get_device_properties(0)
+                peak_tf = props.multi_processor_count * 128 * 2 * measured_peaks()[2] * 1e6 / 1e12
                 fl = {"render": 34.0, "render_backward": 90.0}
                 line["blend_compute"] = {k: {"pairs_per_s": round(kc / (st["split"][k] * 1e-3), 0),
                                              "tflops": round(kc * fl[k] / (st["split"][k] * 1e-3) / 1e12, 2),

@@ -1,8 +1,8 @@
 """queries/s of the graph-replayed refinement loop on several BASELINE configs (1 GPU)."""
 import os, sys, time, json
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _ablib  # noqa: F401  (GSR_AB_LIB switch)
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, ROOT)
 import bench
 from gs_localization_b200 import synthetic as syn, localization as loc
 dev = torch.device("cuda:0")
@@ -18,7 +18,7 @@ for name in sys.argv[1:] or ["C1", "C2", "headline", "C3"]:
         target = arm.c_forward(m, bg, v, p_, c, gt)[1].clone()
         qs.append((gt, target))
     res = {"config": name, "iters": iters}
-    for mode in ("graph", "fused_eager", "framework"):
+    for mode in (("graph",) if os.environ.get("QUICK") else ("graph", "fused_eager", "framework")):
         cams_q = [loc.PoseCamera(gt.perturbed(syn.initial_perturbation(q, 0.02, 1.0)), dev) for q, (gt, _) in enumerate(qs)]
         if mode == "graph":
             refiner = loc.GraphRefiner(m, cams_q[0])

@@ -4,17 +4,9 @@ A/B against another build of the library: GSR_AB_LIB=/path/to/other/libgsr_b200.
 through the ctypes binding (e.g. ab/libgsr_b200_r1.so, the end-of-round-1 kernels, built by tests/tools/build_ab_lib.sh);
 the stage times are CUDA-event device times, so the binding does not enter them."""
 import os, sys, json
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, ROOT)
-if os.environ.get("GSR_AB_LIB"):
-    os.environ["GSR_BINDING"] = "ctypes"
-    from gs_localization_b200 import _lib as _l
-    _l.LIB_PATH = os.path.abspath(os.environ["GSR_AB_LIB"])
-    import ctypes as _C
-    _probe = _C.CDLL(_l.LIB_PATH)
-    for _name in list(_l.SIGNATURES):
-        if not hasattr(_probe, _name):
-            del _l.SIGNATURES[_name]          # symbols added after that build
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _ablib  # noqa: F401  (GSR_AB_LIB switch)
+ROOT = _ablib.ROOT
 import torch
 import bench
 dev = torch.device("cuda:0")
