@@ -59,27 +59,41 @@ int fail(int code, const char* fmt, ...) {
 
 // Binning buffer: [header 128 B][point_list u32[cap]] then, depending on the path,
 //   tile-local sort : [comp u64[cap]]
-//   global radix    : [vals u32[cap]][keys u64[cap]][keys u64[cap]][sort temp]
+//   long lists      : [words u64[cap]][words u64[cap]][sort temp][scratch of the Gaussian-level depth sort]
 // The backward only needs point_list, whose offset depends on neither the path nor the capacity the
 // forward happened to allocate (speculative launches over-allocate).
-int sort_end_bit(int W, int H) {
+int tile_bits(int W, int H) {
   const uint32_t gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
-  return 32 + (int)get_higher_msb(gx * gy);   // reference rasterizer_impl.cu:301,309
+  return (int)get_higher_msb(gx * gy);   // reference rasterizer_impl.cu:301,309: its keys are sorted over 32 + this many bits
 }
-char* carve_binning(char* base, long long cap, BinningView& b, bool global_path = false, int W = 0, int H = 0) {
+PackedKey packed_key_for(int P, int W, int H) {
+  PackedKey pk;
+  pk.tile_bits = tile_bits(W, H);
+  pk.slot_bits = std::max(1, bits_for((unsigned long long)num_pre_blocks(P) * PRE_THREADS));
+  return pk;      // slot_bits <= 31 and tile_bits <= 32: always fits one 64-bit word
+}
+char* carve_binning(char* base, long long cap, BinningView& b, bool global_path = false, int W = 0, int H = 0, int P = 0) {
   char* p = base + 128;
   carve(p, b.point_list, (size_t)cap);
+  b.keys[0] = b.keys[1] = nullptr, b.sort_temp = nullptr, b.comp = nullptr;
+  b.gkeys[0] = b.gkeys[1] = nullptr, b.gvals[0] = b.gvals[1] = nullptr, b.gsort_temp = nullptr, b.gcap = 0;
   if (!global_path) {
     carve(p, b.comp, (size_t)cap);
-    b.keys[0] = b.keys[1] = nullptr, b.vals_other = nullptr, b.sort_temp = nullptr;
   } else {
-    carve(p, b.vals_other, (size_t)cap);
     carve(p, b.keys[0], (size_t)cap);
     carve(p, b.keys[1], (size_t)cap);
     p = (char*)align_up((size_t)p, 128);
     b.sort_temp = p;
-    p += sort_temp_bytes(cap, sort_passes(sort_end_bit(W, H)));
-    b.comp = nullptr;
+    p += sort_temp_bytes(cap, sort_passes(tile_bits(W, H)));
+    // Gaussian-level depth sort: at most min(slots, capacity) visible Gaussians (each has at least one instance)
+    b.gcap = std::min<long long>((long long)num_pre_blocks(P) * PRE_THREADS, cap);
+    carve(p, b.gkeys[0], (size_t)b.gcap);
+    carve(p, b.gkeys[1], (size_t)b.gcap);
+    carve(p, b.gvals[0], (size_t)b.gcap);
+    carve(p, b.gvals[1], (size_t)b.gcap);
+    p = (char*)align_up((size_t)p, 128);
+    b.gsort_temp = p;
+    p += sort_temp_bytes(b.gcap, sort_passes(32));
   }
   b.units = nullptr, b.ckpt = nullptr, b.rec = nullptr, b.units_off = b.ckpt_off = b.rec_off = b.units_cap = 0;
   if (W > 0 && H > 0) {
@@ -240,13 +254,13 @@ size_t gsr_image_bytes(int width, int height) {
   return (size_t)end + 128;
 }
 size_t gsr_binning_bytes(long long num_rendered, int width, int height) {
-  BinningView b;   // worst case: the global radix-sort layout
-  char* end = carve_binning(nullptr, num_rendered, b, true, width, height);
+  BinningView b;   // worst case: the long-list layout with as many visible Gaussians as instances
+  char* end = carve_binning(nullptr, num_rendered, b, true, width, height, num_rendered > 0x7fffff00ll ? 0x7fffff00 : (int)num_rendered);
   return (size_t)end + 128;
 }
-static size_t binning_bytes_for(long long cap, bool global_path, int width, int height) {
+static size_t binning_bytes_for(long long cap, bool global_path, int width, int height, int P) {
   BinningView b;
-  char* end = carve_binning(nullptr, cap, b, global_path, width, height);
+  char* end = carve_binning(nullptr, cap, b, global_path, width, height, P);
   return (size_t)end + 128;
 }
 
@@ -364,27 +378,15 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
       }
       GSR_STAGE("tile_sort", debug, stream);
     } else if (capacity > 0) {
-      // tile lists too long for the shared-memory sort: the reference's global formulation — instances in
-      // Gaussian order with tile|depth keys, stable onesweep radix sort over the low 32+bit bits.  The last
-      // pass is steered into point_list; the tile ranges are already known from scan_tiles.
-      const int end_bit = sort_end_bit(width, height);
-      const int passes = sort_passes(end_bit);
-      uint64_t* keys[2] = {bl.keys[0], bl.keys[1]};
-      uint32_t* vals[2];
-      vals[passes & 1] = bl.point_list;
-      vals[(passes & 1) ^ 1] = bl.vals_other;
-      SortTemp st;
-      carve_sort_temp(bl.sort_temp, capacity, passes, st);
+      // tile lists too long for the shared-memory sort (binning.cu, "long lists")
       {
         StageScope ts(ST_DUPLICATE, stream);
-        sort_temp_reset(bl.sort_temp, capacity, passes, stream);
-        launch_emit_ordered(P, g, keys[0], vals[0], gx, BinHeader{(unsigned long long)capacity, bl.units_off, bl.ckpt_off, bl.rec_off, bl.units_cap}, bin_header, stream);
+        launch_long_emit(P, g, bl, capacity, packed_key_for(P, width, height), gx, BinHeader{(unsigned long long)capacity, bl.units_off, bl.ckpt_off, bl.rec_off, bl.units_cap}, bin_header, stream);
       }
-      GSR_STAGE("emit_ordered", debug, stream);
+      GSR_STAGE("long_emit", debug, stream);
       {
         StageScope ts(ST_SORT, stream);
-        launch_sort_histogram(keys[0], g.counters + 1, capacity, end_bit, st.hist, stream);
-        launch_onesweep(keys, vals, g.counters + 1, capacity, end_bit, st, stream);
+        launch_long_sort(T, im.ranges, g, bl, capacity, packed_key_for(P, width, height), stream);
       }
       GSR_STAGE("radix_sort", debug, stream);
     }
@@ -408,9 +410,9 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     return GSR_OK;
   };
   auto alloc_binning = [&](long long cap, bool global_path) -> int {
-    char* bin_base = binning_alloc(binning_bytes_for(cap, global_path, width, height), user);
+    char* bin_base = binning_alloc(binning_bytes_for(cap, global_path, width, height, P), user);
     if (!bin_base) return fail(GSR_ERR_ALLOC, "binning_alloc returned NULL");
-    carve_binning(bin_base, cap, bl, global_path, width, height);
+    carve_binning(bin_base, cap, bl, global_path, width, height, P);
     bin_header = reinterpret_cast<BinHeader*>(bin_base);   // capacity and the unit/checkpoint offsets are recorded there by the scatter kernel
     return GSR_OK;
   };
@@ -487,7 +489,7 @@ int gsr_rasterize_forward_async(char* geometry_buffer, char* binning_buffer, lon
   ImageView im;
   carve_image(image_buffer, width, height, im);
   BinningView bl;
-  carve_binning(binning_buffer, binning_capacity, bl, global_sort != 0, width, height);
+  carve_binning(binning_buffer, binning_capacity, bl, global_sort != 0, width, height, P);
   // counters and the coverage grid are zeroed by the first preprocess kernel
   PreprocessParams pp{};
   pp.P = P, pp.D = D, pp.M = M, pp.W = width, pp.H = height, pp.grid_x = gx, pp.grid_y = gy;
@@ -516,18 +518,8 @@ int gsr_rasterize_forward_async(char* geometry_buffer, char* binning_buffer, lon
     launch_scatter(P, g, im.tile_cursor, bl.comp, gx, hv, hdr, stream);
     launch_tile_sort(T, im.ranges, bl.comp, bl.point_list, (uint32_t)binning_capacity, im.tile_order, stream);
   } else {
-    const int end_bit = sort_end_bit(width, height);
-    const int passes = sort_passes(end_bit);
-    uint64_t* keys[2] = {bl.keys[0], bl.keys[1]};
-    uint32_t* vals[2];
-    vals[passes & 1] = bl.point_list;
-    vals[(passes & 1) ^ 1] = bl.vals_other;
-    SortTemp st;
-    carve_sort_temp(bl.sort_temp, binning_capacity, passes, st);
-    sort_temp_reset(bl.sort_temp, binning_capacity, passes, stream);
-    launch_emit_ordered(P, g, keys[0], vals[0], gx, hv, hdr, stream);
-    launch_sort_histogram(keys[0], g.counters + 1, binning_capacity, end_bit, st.hist, stream);
-    launch_onesweep(keys, vals, g.counters + 1, binning_capacity, end_bit, st, stream);
+    launch_long_emit(P, g, bl, binning_capacity, packed_key_for(P, width, height), gx, hv, hdr, stream);
+    launch_long_sort(T, im.ranges, g, bl, binning_capacity, packed_key_for(P, width, height), stream);
   }
   RenderParams rp{};
   rp.W = width, rp.H = height, rp.grid_x = gx, rp.grid_y = gy;
@@ -913,7 +905,7 @@ int gsr_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* 
   SortTemp st;
   carve_sort_temp(temp, n, passes, st);
   sort_temp_reset(temp, n, passes, stream);
-  launch_sort_histogram(keys_in, nullptr, n, end_bit, st.hist, stream);
+  launch_sort_histogram(keys_in, nullptr, n, 0, end_bit, st.hist, stream);
   // arrange the ping-pong so that the last pass lands in keys_out: odd passes in->out directly
   uint64_t* kb[2];
   uint32_t* vb[2];

@@ -228,16 +228,12 @@ void launch_reset_cursors(int T, const uint2* ranges, uint32_t* cursor, cudaStre
 }
 
 // ------------------------------------------------------------------ instances -> tile buckets
-// One CTA per preprocess slot segment.  Also zeroes the backward accumulator rows of its slots.
-// ORDERED = false: bucket mode (atomic cursor per tile, composite depth|slot).
-// ORDERED = true : the reference's layout for the global radix sort — instance j of the CTA goes to
-//                  block_off[b] + j (Gaussian order, rows-then-columns), key = tile << 32 | depth bits, value = slot.
-template <bool ORDERED>
+// One CTA per preprocess slot segment: atomic cursor per tile, composite depth|slot.  Also zeroes the backward
+// accumulator rows of its slots.
 __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict__ block_vis, const uint2* __restrict__ rects,
                                                       const float* __restrict__ depths, uint32_t* __restrict__ cursor,
                                                       uint64_t* __restrict__ comp, float* __restrict__ grad_acc,
-                                                      uint32_t grid_x, BinHeader hv, BinHeader* header, uint32_t* unit_count,
-                                                      const uint32_t* __restrict__ block_off, uint32_t* __restrict__ vals) {
+                                                      uint32_t grid_x, BinHeader hv, BinHeader* header, uint32_t* unit_count) {
   const uint32_t capacity = (uint32_t)hv.capacity;
   __shared__ uint32_t s_end[256];     // CTA-local inclusive prefix of tile counts
   __shared__ uint2 s_rect[256];
@@ -282,21 +278,14 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict
     const uint32_t minx = rc.x & 0xffffu, w = (rc.x >> 16) - minx, miny = rc.y & 0xffffu;
     const uint32_t row = within / w, col = within - row * w;
     const uint32_t tile = (miny + row) * grid_x + (minx + col);
-    if (ORDERED) {
-      const uint32_t pos = __ldg(block_off + blockIdx.x) + j;
-      if (pos < capacity) {
-        comp[pos] = ((uint64_t)tile << 32) | s_depth[lo];
-        vals[pos] = first + lo;
-      }
-    } else {
-      const uint32_t pos = atomicAdd(cursor + (size_t)tile * CURSOR_STRIDE, 1u);
-      if (pos < capacity) comp[pos] = ((uint64_t)s_depth[lo] << 32) | (first + lo);
-    }
+    const uint32_t pos = atomicAdd(cursor + (size_t)tile * CURSOR_STRIDE, 1u);
+    if (pos < capacity) comp[pos] = ((uint64_t)s_depth[lo] << 32) | (first + lo);
   }
 }
 
 // exclusive scan, in place, of the per-CTA instance counts (one CTA; n = ceil(P/256) values)
-__global__ void __launch_bounds__(1024) scan_blocks_kernel(const uint32_t* __restrict__ a, uint32_t* __restrict__ out, uint32_t n) {
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(const uint32_t* __restrict__ a, uint32_t* __restrict__ out, uint32_t n,
+                                                           uint32_t* __restrict__ total_out) {
   __shared__ uint32_t s_warp[32];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t chunk = (n + 1023) / 1024;
@@ -318,23 +307,18 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(const uint32_t* __res
   __syncthreads();
   uint32_t run = s_warp[warp] + incl - sum;
   for (uint32_t i = i0; i < i1; i++) { const uint32_t c = a[i]; out[i] = run; run += c; }
+  if (tid == 1023) {           // the last thread's running sum is the total
+    out[n] = run;
+    if (total_out) *total_out = run;
+  }
 }
 
 void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* comp, uint32_t grid_x, BinHeader hv,
                     BinHeader* header, cudaStream_t stream) {
   if (P <= 0) return;
-  scatter_kernel<false><<<num_pre_blocks(P), 256, 0, stream>>>(g.block_vis, g.rect, g.depths, cursor, comp, g.grad_acc, grid_x,
-                                                              hv, header, g.counters + 5, nullptr, nullptr);
+  scatter_kernel<<<num_pre_blocks(P), 256, 0, stream>>>(g.block_vis, g.rect, g.depths, cursor, comp, g.grad_acc, grid_x, hv, header,
+                                                       g.counters + 5);
   count_launch();
-}
-
-void launch_emit_ordered(int P, const GeometryView& g, uint64_t* keys, uint32_t* vals, uint32_t grid_x, BinHeader hv,
-                         BinHeader* header, cudaStream_t stream) {
-  if (P <= 0) return;
-  scan_blocks_kernel<<<1, 1024, 0, stream>>>(g.block_tiles, g.block_off, (uint32_t)num_pre_blocks(P));
-  scatter_kernel<true><<<num_pre_blocks(P), 256, 0, stream>>>(g.block_vis, g.rect, g.depths, nullptr, keys, g.grad_acc, grid_x,
-                                                             hv, header, g.counters + 5, g.block_off, vals);
-  count_launch(2);
 }
 
 // ------------------------------------------------------------------ tile-local sort (kernel)
@@ -502,10 +486,10 @@ void launch_tile_sort(int num_tiles, const uint2* ranges, uint64_t* comp, uint32
 // Keys of one Gaussian are adjacent and share every depth digit, so equal digits are first
 // aggregated inside the warp (match_any) and cost one shared-memory atomic per group.
 __global__ void __launch_bounds__(256) sort_histogram_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ n_ptr,
-                                                             uint32_t n_host, int end_bit, uint32_t* __restrict__ hist) {
+                                                             uint32_t n_host, int lo_bit, int end_bit, uint32_t* __restrict__ hist) {
   __shared__ uint32_t s_hist[SORT_MAX_PASSES * SORT_RADIX];
   const uint32_t n = n_ptr ? min(*n_ptr, n_host) : n_host;
-  const int passes = (end_bit + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS;
+  const int passes = (end_bit - lo_bit + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS;
   for (int i = threadIdx.x; i < passes * SORT_RADIX; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
@@ -518,7 +502,7 @@ __global__ void __launch_bounds__(256) sort_histogram_kernel(const uint64_t* __r
     const uint32_t act = __ballot_sync(0xffffffffu, valid);
     if (valid) {
       for (int p = 0; p < passes; p++) {
-        const int shift = SORT_RADIX_BITS * p;
+        const int shift = lo_bit + SORT_RADIX_BITS * p;
         const uint32_t mask = (1u << min(SORT_RADIX_BITS, end_bit - shift)) - 1u;
         const uint32_t d = digit_of(k, shift, mask);
         const uint32_t peers = __match_any_sync(act, d);
@@ -532,11 +516,11 @@ __global__ void __launch_bounds__(256) sort_histogram_kernel(const uint64_t* __r
     if (c) atomicAdd(&hist[i], c);
   }
 }
-void launch_sort_histogram(const uint64_t* keys, const uint32_t* n_ptr, long long n_host, int end_bit, uint32_t* hist,
+void launch_sort_histogram(const uint64_t* keys, const uint32_t* n_ptr, long long n_host, int lo_bit, int end_bit, uint32_t* hist,
                            cudaStream_t stream) {
   if (n_host <= 0) return;
-  const int blocks = (int)std::min<long long>((n_host + 256 * 8 - 1) / (256 * 8), sm_count() * 4);
-  sort_histogram_kernel<<<blocks, 256, 0, stream>>>(keys, n_ptr, (uint32_t)n_host, end_bit, hist);
+  const int blocks = (int)std::min<long long>((n_host + 256 * 8 - 1) / (256 * 8), sm_count() * 8);
+  sort_histogram_kernel<<<blocks, 256, 0, stream>>>(keys, n_ptr, (uint32_t)n_host, lo_bit, end_bit, hist);
   count_launch();
 }
 
@@ -562,22 +546,27 @@ __global__ void __launch_bounds__(SORT_RADIX) sort_scan_hist_kernel(uint32_t* __
 // ------------------------------------------------------------------ onesweep pass
 constexpr uint32_t FLAG_AGG = 1u << 30, FLAG_INCL = 2u << 30, VALUE_MASK = (1u << 30) - 1u;
 
-struct __align__(16) SortSmem {
+template <bool PAIRS>
+struct __align__(16) SortSmemT {
   uint64_t keys[SORT_TILE];
-  uint32_t vals[SORT_TILE];
+  uint32_t vals[PAIRS ? SORT_TILE : 1];
   uint32_t warp_hist[SORT_THREADS / 32][SORT_RADIX];
   uint32_t local_start[SORT_RADIX];
   uint32_t adj[SORT_RADIX];
   uint32_t warp_tot[SORT_RADIX / 32];
 };
+using SortSmem = SortSmemT<true>;
 
+// MODE 0: (key, value) pairs.  MODE 1: keys only (the value rides in the key's low bits).  MODE 2: keys only, last pass:
+// the low `out_bits` of every key are written, as a u32, to vout instead of the key to kout.
+template <int MODE>
 __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout,
                                                                     const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
                                                                     const uint32_t* __restrict__ n_ptr, uint32_t n_host, int shift,
                                                                     uint32_t mask, const uint32_t* __restrict__ bases,
-                                                                    volatile uint32_t* status) {
+                                                                    volatile uint32_t* status, int out_bits) {
   extern __shared__ __align__(16) char smem_raw[];
-  SortSmem& s = *reinterpret_cast<SortSmem*>(smem_raw);
+  SortSmemT<MODE == 0>& s = *reinterpret_cast<SortSmemT<MODE == 0>*>(smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = SORT_THREADS / 32;
 
@@ -674,16 +663,31 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_pass_kernel(const uint6
       const uint32_t d = digit_of(key[i], shift, mask);
       const uint32_t lp = s.local_start[d] + s.warp_hist[warp][d] + rank[i];
       s.keys[lp] = key[i];
-      s.vals[lp] = __ldg(vin + tile_base + pos);
+      if (MODE == 0) s.vals[lp] = __ldg(vin + tile_base + pos);
     }
   }
   __syncthreads();
   // ---- write runs out
+  const uint64_t out_mask = out_bits >= 64 ? ~0ull : (1ull << out_bits) - 1ull;
   for (uint32_t j = tid; j < count; j += SORT_THREADS) {
     const uint64_t k = s.keys[j];
     const uint32_t dst = s.adj[digit_of(k, shift, mask)] + j;
-    kout[dst] = k;
-    vout[dst] = s.vals[j];
+    if (MODE == 2) {
+      vout[dst] = (uint32_t)(k & out_mask);
+    } else {
+      kout[dst] = k;
+      if (MODE == 0) vout[dst] = s.vals[j];
+    }
+  }
+}
+
+template <int MODE> static void onesweep_set_smem() {
+  static bool attr_set[64] = {};   // per device: the attribute belongs to the device's copy of the kernel
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaFuncSetAttribute(onesweep_pass_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmemT<MODE == 0>));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
 }
 
@@ -691,15 +695,7 @@ int launch_onesweep(uint64_t* keys[2], uint32_t* vals[2], const uint32_t* n_ptr,
                     cudaStream_t stream) {
   const int passes = sort_passes(end_bit);
   if (n <= 0 || passes == 0) return 0;
-  {
-    static bool attr_set[64] = {};   // per device: the attribute belongs to the device's copy of the kernel
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-      cudaFuncSetAttribute(onesweep_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
-      if (dev >= 0 && dev < 64) attr_set[dev] = true;
-    }
-  }
+  onesweep_set_smem<0>();
   sort_scan_hist_kernel<<<passes, SORT_RADIX, 0, stream>>>(t.hist);
   count_launch();
   const size_t ntiles = sort_num_tiles(n);
@@ -707,13 +703,197 @@ int launch_onesweep(uint64_t* keys[2], uint32_t* vals[2], const uint32_t* n_ptr,
   for (int p = 0; p < passes; p++) {
     const int shift = SORT_RADIX_BITS * p;
     const uint32_t mask = (1u << std::min(SORT_RADIX_BITS, end_bit - shift)) - 1u;
-    onesweep_pass_kernel<<<(unsigned)ntiles, SORT_THREADS, sizeof(SortSmem), stream>>>(
+    onesweep_pass_kernel<0><<<(unsigned)ntiles, SORT_THREADS, sizeof(SortSmem), stream>>>(
         keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n_ptr, (uint32_t)n, shift, mask, t.hist + p * SORT_RADIX,
-        t.status + (size_t)p * ntiles * SORT_RADIX);
+        t.status + (size_t)p * ntiles * SORT_RADIX, 64);
     count_launch();
     cur ^= 1;
   }
   return cur;
+}
+
+// Packed words (PackedKey): stable LSD passes over the bit window [sort_lo, sort_hi) only — the slot in the low bits is the
+// value.  keys[0] holds the input, keys[1] is scratch; the last pass writes the slots to `list`.  The digit histograms of
+// all passes are already in t.hist (exclusive scan pending).
+void launch_onesweep_packed(uint64_t* keys[2], uint32_t* list, const uint32_t* n_ptr, long long n, PackedKey pk, const SortTemp& t,
+                            cudaStream_t stream) {
+  const int lo = pk.sort_lo(), hi = pk.sort_hi();
+  const int passes = sort_passes(hi - lo);
+  if (n <= 0 || passes == 0) return;
+  onesweep_set_smem<1>();
+  onesweep_set_smem<2>();
+  sort_scan_hist_kernel<<<passes, SORT_RADIX, 0, stream>>>(t.hist);
+  count_launch();
+  const size_t ntiles = sort_num_tiles(n);
+  int cur = 0;
+  for (int p = 0; p < passes; p++) {
+    const int shift = lo + SORT_RADIX_BITS * p;
+    const uint32_t mask = (1u << std::min(SORT_RADIX_BITS, hi - shift)) - 1u;
+    const uint32_t* bases = t.hist + p * SORT_RADIX;
+    volatile uint32_t* status = t.status + (size_t)p * ntiles * SORT_RADIX;
+    if (p + 1 < passes)
+      onesweep_pass_kernel<1><<<(unsigned)ntiles, SORT_THREADS, sizeof(SortSmemT<false>), stream>>>(
+          keys[cur], keys[cur ^ 1], nullptr, nullptr, n_ptr, (uint32_t)n, shift, mask, bases, status, 64);
+    else
+      onesweep_pass_kernel<2><<<(unsigned)ntiles, SORT_THREADS, sizeof(SortSmemT<false>), stream>>>(
+          keys[cur], nullptr, nullptr, list, n_ptr, (uint32_t)n, shift, mask, bases, status, pk.slot_bits);
+    count_launch();
+    cur ^= 1;
+  }
+}
+
+// ------------------------------------------------------------------ long lists
+// Frames with tile lists beyond the shared-memory sort (config C5: 36 K entries per tile, 2.9e8 instances).  The
+// reference sorts all instances on tile|depth: six radix passes over (key, value) pairs.  Here the depth half of that
+// order is established on the GAUSSIANS, of which there are hundreds of times fewer than instances:
+//   1. the visible slots are compacted and sorted by (depth bits, slot) — the pair onesweep on ~6e5 elements;
+//   2. instances are emitted in that order, one packed word tile << slot_bits | slot each (no atomics: output position =
+//      exclusive sum of tile counts in sorted order + rank inside the Gaussian's rectangle);
+//   3. a STABLE sort of the words on the tile bits alone (two key-only passes for up to 65 K tiles) is then exactly the
+//      reference's order: tile-major, and inside a tile by depth with ties in Gaussian order.  The digit histograms of
+//      these passes are sums of the per-tile list lengths, which the coverage grid already gave: no pass over the
+//      instances to count digits.  The last pass writes the slots straight into point_list.
+// Per instance: 8 B written by the emission, 16 B + 12 B by the two passes (the reference: 12 + 8 + 6 x 24 = 164 B).
+__global__ void __launch_bounds__(256) compact_visible_kernel(const uint32_t* __restrict__ block_vis, const uint32_t* __restrict__ vis_off,
+                                                              const float* __restrict__ depths, uint64_t* __restrict__ gkeys,
+                                                              uint32_t* __restrict__ gvals, uint32_t gcap) {
+  const uint32_t cnt = block_vis[blockIdx.x];
+  if (threadIdx.x >= cnt) return;
+  const uint32_t slot = blockIdx.x * 256u + threadIdx.x, i = vis_off[blockIdx.x] + threadIdx.x;
+  if (i < gcap) {
+    gkeys[i] = (uint64_t)__float_as_uint(__ldg(depths + slot));     // visible depths are > 0.2: the bits order like the values
+    gvals[i] = slot;
+  }
+}
+
+__device__ __forceinline__ uint32_t rect_tiles(uint2 rc) { return ((rc.x >> 16) - (rc.x & 0xffffu)) * ((rc.y >> 16) - (rc.y & 0xffffu)); }
+
+// instances of every block of 256 depth-sorted Gaussians
+__global__ void __launch_bounds__(256) sorted_block_tiles_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ n_vis_ptr,
+                                                                 uint32_t gcap, const uint2* __restrict__ rects,
+                                                                 uint32_t* __restrict__ sblock_tiles) {
+  __shared__ uint32_t s_w[8];
+  const uint32_t n_vis = min(*n_vis_ptr, gcap);
+  const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+  uint32_t tiles = i < n_vis ? rect_tiles(__ldg(rects + __ldg(order + i))) : 0u;
+  tiles = __reduce_add_sync(0xffffffffu, tiles);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = tiles;
+  __syncthreads();
+  if (threadIdx.x == 0) sblock_tiles[blockIdx.x] = s_w[0] + s_w[1] + s_w[2] + s_w[3] + s_w[4] + s_w[5] + s_w[6] + s_w[7];
+}
+
+// One CTA per block of 256 depth-sorted Gaussians: cooperative expansion as in scatter_kernel, position = exclusive
+// prefix of the blocks before + rank inside the block.  Also zeroes the backward accumulator rows of its slots.
+__global__ void __launch_bounds__(256) emit_sorted_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ n_vis_ptr,
+                                                          uint32_t gcap, const uint2* __restrict__ rects, const uint32_t* __restrict__ sblock_off,
+                                                          uint64_t* __restrict__ words, float* __restrict__ grad_acc, uint32_t grid_x,
+                                                          BinHeader hv, BinHeader* header, uint32_t* unit_count, PackedKey pk) {
+  const uint32_t capacity = (uint32_t)hv.capacity;
+  __shared__ uint32_t s_end[256];
+  __shared__ uint2 s_rect[256];
+  __shared__ uint32_t s_slot[256];
+  __shared__ uint32_t s_wsum[8];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (header) *header = hv;
+    unit_count[0] = 0;
+    unit_count[3] = unit_count[4] = unit_count[5] = unit_count[6] = 0;
+  }
+  const uint32_t n_vis = min(*n_vis_ptr, gcap);
+  const uint32_t first = blockIdx.x * 256u;
+  if (first >= n_vis) return;
+  const uint32_t cnt = min(256u, n_vis - first);
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t tiles = 0;
+  if (tid < cnt) {
+    const uint32_t slot = __ldg(order + first + tid);
+    const uint2 rc = __ldg(rects + slot);
+    s_rect[tid] = rc;
+    s_slot[tid] = slot;
+    tiles = rect_tiles(rc);
+    float4* acc = reinterpret_cast<float4*>(grad_acc + 12 * (size_t)slot);
+    acc[0] = acc[1] = acc[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  uint32_t incl = tiles;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (uint32_t w = 0; w < warp; w++) woff += s_wsum[w];
+  s_end[tid] = woff + incl;
+  __syncthreads();
+  const uint32_t total = s_end[255];
+  const uint32_t base = __ldg(sblock_off + blockIdx.x);
+  for (uint32_t j = tid; j < total; j += 256u) {
+    uint32_t lo = 0, hi = cnt - 1;      // smallest t with s_end[t] > j
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s_end[mid] > j) hi = mid; else lo = mid + 1;
+    }
+    const uint32_t within = j - (lo == 0 ? 0u : s_end[lo - 1]);
+    const uint2 rc = s_rect[lo];
+    const uint32_t minx = rc.x & 0xffffu, w = (rc.x >> 16) - minx, miny = rc.y & 0xffffu;
+    const uint32_t row = within / w, col = within - row * w;
+    const uint32_t tile = (miny + row) * grid_x + (minx + col);
+    const uint32_t pos = base + j;
+    if (pos < capacity) __stcs(words + pos, ((uint64_t)tile << pk.slot_bits) | (uint64_t)s_slot[lo]);
+  }
+}
+
+// digit histograms of the tile passes from the per-tile list lengths
+__global__ void __launch_bounds__(256) tile_digit_hist_kernel(const uint2* __restrict__ ranges, uint32_t T, int tile_bits,
+                                                              uint32_t* __restrict__ hist) {
+  const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+  if (t >= T) return;
+  const uint2 rg = ranges[t];
+  const uint32_t len = rg.y - rg.x;
+  if (!len) return;
+  for (int p = 0; p * SORT_RADIX_BITS < tile_bits; p++) {
+    const uint32_t mask = (1u << min(SORT_RADIX_BITS, tile_bits - p * SORT_RADIX_BITS)) - 1u;
+    atomicAdd(&hist[p * SORT_RADIX + ((t >> (p * SORT_RADIX_BITS)) & mask)], len);
+  }
+}
+
+void launch_long_emit(int P, const GeometryView& g, const BinningView& bl, long long capacity, PackedKey pk, uint32_t grid_x, BinHeader hv,
+                      BinHeader* header, cudaStream_t stream) {
+  if (P <= 0) return;
+  const uint32_t nblocks = (uint32_t)num_pre_blocks(P);
+  const uint32_t gcap = (uint32_t)bl.gcap;
+  const uint32_t gblocks = (gcap + 255u) / 256u;
+  uint32_t* n_vis = g.counters + 13;
+  // 1. visible slots, compacted, keyed by depth bits
+  scan_blocks_kernel<<<1, 1024, 0, stream>>>(g.block_vis, g.block_off, nblocks, n_vis);
+  compact_visible_kernel<<<nblocks, 256, 0, stream>>>(g.block_vis, g.block_off, g.depths, bl.gkeys[0], bl.gvals[0], gcap);
+  count_launch(2);
+  // 2. sorted by (depth bits, slot): stable pair sort, the input is in slot order
+  SortTemp st;
+  carve_sort_temp(bl.gsort_temp, gcap, sort_passes(32), st);
+  sort_temp_reset(bl.gsort_temp, gcap, sort_passes(32), stream);
+  uint64_t* gk[2] = {bl.gkeys[0], bl.gkeys[1]};
+  uint32_t* gv[2] = {bl.gvals[0], bl.gvals[1]};
+  launch_sort_histogram(gk[0], n_vis, gcap, 0, 32, st.hist, stream);
+  const int cur = launch_onesweep(gk, gv, n_vis, gcap, 32, st, stream);
+  const uint32_t* order = gv[cur];
+  // 3. instances in that order
+  sorted_block_tiles_kernel<<<gblocks, 256, 0, stream>>>(order, n_vis, gcap, g.rect, g.sblock_tiles);
+  scan_blocks_kernel<<<1, 1024, 0, stream>>>(g.sblock_tiles, g.sblock_off, gblocks, nullptr);
+  emit_sorted_kernel<<<gblocks, 256, 0, stream>>>(order, n_vis, gcap, g.rect, g.sblock_off, bl.keys[0], g.grad_acc, grid_x, hv, header,
+                                                 g.counters + 5, pk);
+  count_launch(3);
+  (void)capacity;
+}
+
+void launch_long_sort(int T, const uint2* ranges, const GeometryView& g, const BinningView& bl, long long capacity, PackedKey pk,
+                      cudaStream_t stream) {
+  if (T <= 0 || capacity <= 0) return;
+  const int passes = sort_passes(pk.tile_bits);
+  SortTemp st;
+  carve_sort_temp(bl.sort_temp, capacity, passes, st);
+  sort_temp_reset(bl.sort_temp, capacity, passes, stream);
+  tile_digit_hist_kernel<<<(T + 255) / 256, 256, 0, stream>>>(ranges, (uint32_t)T, pk.tile_bits, st.hist);
+  count_launch();
+  uint64_t* keys[2] = {bl.keys[0], bl.keys[1]};
+  launch_onesweep_packed(keys, bl.point_list, g.counters + 1, capacity, pk, st, stream);
 }
 
 }  // namespace gsr

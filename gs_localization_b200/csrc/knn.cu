@@ -270,7 +270,7 @@ int launch_dist2_knn3(const float* points, long long P, float* mean_dists, char*
   const int end_bit = 63, passes = sort_passes(end_bit);
   carve_sort_temp(w.sort_temp, P, passes, st);
   sort_temp_reset(w.sort_temp, P, passes, stream);
-  launch_sort_histogram(w.keys[0], nullptr, P, end_bit, st.hist, stream);
+  launch_sort_histogram(w.keys[0], nullptr, P, 0, end_bit, st.hist, stream);
   launch_onesweep(w.keys, w.vals, nullptr, P, end_bit, st, stream);
   const uint32_t* order = w.vals[passes & 1];
   knn_boxes_kernel<<<(nb + 7) / 8, 256, 0, stream>>>(points, n, order, w.sorted, w.box_min, w.box_max, nb);

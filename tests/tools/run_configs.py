@@ -1,8 +1,8 @@
 """One fwd+bwd per BASELINE config: stage split (ours) and total device time (ours vs reference)."""
 import os, sys, time, json
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _ablib  # noqa: F401  (GSR_AB_LIB switch)
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, ROOT)
 import bench
 from gs_localization_b200 import synthetic as syn, _lib
 
@@ -15,7 +15,7 @@ for name in names:
     zD = torch.zeros(1, H, W, device=dev)
     gC = torch.full((3, H, W), 1.0 / (3 * H * W), device=dev)
     res = {"config": name}
-    for impl in ("ours", "reference"):
+    for impl in (("ours",) if os.environ.get("ONLY_OURS") else ("ours", "reference")):
         try:
             arm = bench.Arm(impl, dev)
         except Exception as ex:
