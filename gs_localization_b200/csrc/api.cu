@@ -59,19 +59,9 @@ int fail(int code, const char* fmt, ...) {
 
 // Binning buffer: [header 128 B][point_list u32[cap]] then, depending on the path,
 //   tile-local sort : [comp u64[cap]]
-//   long lists      : [words u64[cap]][words u64[cap]][sort temp][scratch of the Gaussian-level depth sort]
+//   long lists      : [scratch of the Gaussian-level depth sort] (instances go straight to point_list)
 // The backward only needs point_list, whose offset depends on neither the path nor the capacity the
 // forward happened to allocate (speculative launches over-allocate).
-int tile_bits(int W, int H) {
-  const uint32_t gx = (W + TILE_X - 1) / TILE_X, gy = (H + TILE_Y - 1) / TILE_Y;
-  return (int)get_higher_msb(gx * gy);   // reference rasterizer_impl.cu:301,309: its keys are sorted over 32 + this many bits
-}
-PackedKey packed_key_for(int P, int W, int H) {
-  PackedKey pk;
-  pk.tile_bits = tile_bits(W, H);
-  pk.slot_bits = std::max(1, bits_for((unsigned long long)num_pre_blocks(P) * PRE_THREADS));
-  return pk;      // slot_bits <= 31 and tile_bits <= 32: always fits one 64-bit word
-}
 char* carve_binning(char* base, long long cap, BinningView& b, bool global_path = false, int W = 0, int H = 0, int P = 0) {
   char* p = base + 128;
   carve(p, b.point_list, (size_t)cap);
@@ -80,11 +70,6 @@ char* carve_binning(char* base, long long cap, BinningView& b, bool global_path 
   if (!global_path) {
     carve(p, b.comp, (size_t)cap);
   } else {
-    carve(p, b.keys[0], (size_t)cap);
-    carve(p, b.keys[1], (size_t)cap);
-    p = (char*)align_up((size_t)p, 128);
-    b.sort_temp = p;
-    p += sort_temp_bytes(cap, sort_passes(tile_bits(W, H)));
     // Gaussian-level depth sort: at most min(slots, capacity) visible Gaussians (each has at least one instance)
     b.gcap = std::min<long long>((long long)num_pre_blocks(P) * PRE_THREADS, cap);
     carve(p, b.gkeys[0], (size_t)b.gcap);
@@ -254,9 +239,12 @@ size_t gsr_image_bytes(int width, int height) {
   return (size_t)end + 128;
 }
 size_t gsr_binning_bytes(long long num_rendered, int width, int height) {
-  BinningView b;   // worst case: the long-list layout with as many visible Gaussians as instances
-  char* end = carve_binning(nullptr, num_rendered, b, true, width, height, num_rendered > 0x7fffff00ll ? 0x7fffff00 : (int)num_rendered);
-  return (size_t)end + 128;
+  // worst case over the two layouts (the long-list one with as many visible Gaussians as instances)
+  BinningView b;
+  const int p_bound = num_rendered > 0x7fffff00ll ? 0x7fffff00 : (int)num_rendered;
+  char* end_long = carve_binning(nullptr, num_rendered, b, true, width, height, p_bound);
+  char* end_local = carve_binning(nullptr, num_rendered, b, false, width, height, p_bound);
+  return (size_t)std::max(end_long, end_local) + 128;
 }
 static size_t binning_bytes_for(long long cap, bool global_path, int width, int height, int P) {
   BinningView b;
@@ -380,13 +368,8 @@ long long gsr_rasterize_forward(gsr_alloc_fn geometry_alloc, gsr_alloc_fn binnin
     } else if (capacity > 0) {
       // tile lists too long for the shared-memory sort (binning.cu, "long lists")
       {
-        StageScope ts(ST_DUPLICATE, stream);
-        launch_long_emit(P, g, bl, capacity, packed_key_for(P, width, height), gx, BinHeader{(unsigned long long)capacity, bl.units_off, bl.ckpt_off, bl.rec_off, bl.units_cap}, bin_header, stream);
-      }
-      GSR_STAGE("long_emit", debug, stream);
-      {
         StageScope ts(ST_SORT, stream);
-        launch_long_sort(T, im.ranges, g, bl, capacity, packed_key_for(P, width, height), stream);
+        launch_long_bin(P, T, gx, gy, im.ranges, g, bl, capacity, BinHeader{(unsigned long long)capacity, bl.units_off, bl.ckpt_off, bl.rec_off, bl.units_cap}, bin_header, stream);
       }
       GSR_STAGE("radix_sort", debug, stream);
     }
@@ -518,8 +501,7 @@ int gsr_rasterize_forward_async(char* geometry_buffer, char* binning_buffer, lon
     launch_scatter(P, g, im.tile_cursor, bl.comp, gx, hv, hdr, stream);
     launch_tile_sort(T, im.ranges, bl.comp, bl.point_list, (uint32_t)binning_capacity, im.tile_order, stream);
   } else {
-    launch_long_emit(P, g, bl, binning_capacity, packed_key_for(P, width, height), gx, hv, hdr, stream);
-    launch_long_sort(T, im.ranges, g, bl, binning_capacity, packed_key_for(P, width, height), stream);
+    launch_long_bin(P, T, gx, gy, im.ranges, g, bl, binning_capacity, hv, hdr, stream);
   }
   RenderParams rp{};
   rp.W = width, rp.H = height, rp.grid_x = gx, rp.grid_y = gy;

@@ -712,158 +712,175 @@ int launch_onesweep(uint64_t* keys[2], uint32_t* vals[2], const uint32_t* n_ptr,
   return cur;
 }
 
-// Packed words (PackedKey): stable LSD passes over the bit window [sort_lo, sort_hi) only — the slot in the low bits is the
-// value.  keys[0] holds the input, keys[1] is scratch; the last pass writes the slots to `list`.  The digit histograms of
-// all passes are already in t.hist (exclusive scan pending).
-void launch_onesweep_packed(uint64_t* keys[2], uint32_t* list, const uint32_t* n_ptr, long long n, PackedKey pk, const SortTemp& t,
-                            cudaStream_t stream) {
-  const int lo = pk.sort_lo(), hi = pk.sort_hi();
-  const int passes = sort_passes(hi - lo);
-  if (n <= 0 || passes == 0) return;
-  onesweep_set_smem<1>();
-  onesweep_set_smem<2>();
-  sort_scan_hist_kernel<<<passes, SORT_RADIX, 0, stream>>>(t.hist);
-  count_launch();
-  const size_t ntiles = sort_num_tiles(n);
-  int cur = 0;
-  for (int p = 0; p < passes; p++) {
-    const int shift = lo + SORT_RADIX_BITS * p;
-    const uint32_t mask = (1u << std::min(SORT_RADIX_BITS, hi - shift)) - 1u;
-    const uint32_t* bases = t.hist + p * SORT_RADIX;
-    volatile uint32_t* status = t.status + (size_t)p * ntiles * SORT_RADIX;
-    if (p + 1 < passes)
-      onesweep_pass_kernel<1><<<(unsigned)ntiles, SORT_THREADS, sizeof(SortSmemT<false>), stream>>>(
-          keys[cur], keys[cur ^ 1], nullptr, nullptr, n_ptr, (uint32_t)n, shift, mask, bases, status, 64);
-    else
-      onesweep_pass_kernel<2><<<(unsigned)ntiles, SORT_THREADS, sizeof(SortSmemT<false>), stream>>>(
-          keys[cur], nullptr, nullptr, list, n_ptr, (uint32_t)n, shift, mask, bases, status, pk.slot_bits);
-    count_launch();
-    cur ^= 1;
-  }
-}
-
 // ------------------------------------------------------------------ long lists
 // Frames with tile lists beyond the shared-memory sort (config C5: 36 K entries per tile, 2.9e8 instances).  The
-// reference sorts all instances on tile|depth: six radix passes over (key, value) pairs.  Here the depth half of that
-// order is established on the GAUSSIANS, of which there are hundreds of times fewer than instances:
-//   1. the visible slots are compacted and sorted by (depth bits, slot) — the pair onesweep on ~6e5 elements;
-//   2. instances are emitted in that order, one packed word tile << slot_bits | slot each (no atomics: output position =
-//      exclusive sum of tile counts in sorted order + rank inside the Gaussian's rectangle);
-//   3. a STABLE sort of the words on the tile bits alone (two key-only passes for up to 65 K tiles) is then exactly the
-//      reference's order: tile-major, and inside a tile by depth with ties in Gaussian order.  The digit histograms of
-//      these passes are sums of the per-tile list lengths, which the coverage grid already gave: no pass over the
-//      instances to count digits.  The last pass writes the slots straight into point_list.
-// Per instance: 8 B written by the emission, 16 B + 12 B by the two passes (the reference: 12 + 8 + 6 x 24 = 164 B).
+// reference materialises all instances as (tile|depth, id) pairs and radix-sorts them: six passes over 2.9e8 pairs.
+// Here no instance is ever written before its final place:
+//   1. the visible slots are compacted and sorted by (depth bits, slot) — the pair onesweep on the ~6e5 GAUSSIANS, of
+//      which there are hundreds of times fewer than instances; their tile rectangles are gathered into that order;
+//   2. tile-major scan: one CTA per super-tile of 4 x 4 tiles streams the sorted rectangles once, keeps — in order — the
+//      candidates that overlap the super-tile in shared memory, and each of its 16 warps appends the candidates that
+//      contain ITS tile to the tile's range of point_list (ballot + prefix: order preserved).  The k-th entry of a tile
+//      is the k-th Gaussian in (depth, slot) order whose rectangle contains it: exactly the reference's sorted list.
+// Per instance: 4 bytes written, once (the reference moves 12 + 8 + 6 x 24 = 164 B per instance).
+constexpr int TB_THREADS = 512;
+constexpr int TB_WARPS = TB_THREADS / 32;
+constexpr int TB_SUPER = 4;                  // super-tile edge in tiles (TB_SUPER^2 == TB_WARPS)
+constexpr int TB_CAND = 3840;                // candidate buffer entries (45 KB)
+static_assert(TB_SUPER * TB_SUPER == TB_WARPS, "one warp per tile of the super-tile");
+
+__device__ __forceinline__ uint32_t rect_tiles(uint2 rc) { return ((rc.x >> 16) - (rc.x & 0xffffu)) * ((rc.y >> 16) - (rc.y & 0xffffu)); }
+
+// visible slots -> dense (depth bits, slot) pairs; also the per-forward duties of the bucket scatter: zero the backward
+// accumulator rows of the visible slots, record the buffer header, reset the backward's unit counters
 __global__ void __launch_bounds__(256) compact_visible_kernel(const uint32_t* __restrict__ block_vis, const uint32_t* __restrict__ vis_off,
                                                               const float* __restrict__ depths, uint64_t* __restrict__ gkeys,
-                                                              uint32_t* __restrict__ gvals, uint32_t gcap) {
+                                                              uint32_t* __restrict__ gvals, uint32_t gcap, float* __restrict__ grad_acc,
+                                                              BinHeader hv, BinHeader* header, uint32_t* unit_count) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (header) *header = hv;
+    unit_count[0] = 0;
+    unit_count[3] = unit_count[4] = unit_count[5] = unit_count[6] = 0;
+  }
   const uint32_t cnt = block_vis[blockIdx.x];
   if (threadIdx.x >= cnt) return;
   const uint32_t slot = blockIdx.x * 256u + threadIdx.x, i = vis_off[blockIdx.x] + threadIdx.x;
+  float4* acc = reinterpret_cast<float4*>(grad_acc + 12 * (size_t)slot);
+  acc[0] = acc[1] = acc[2] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i < gcap) {
     gkeys[i] = (uint64_t)__float_as_uint(__ldg(depths + slot));     // visible depths are > 0.2: the bits order like the values
     gvals[i] = slot;
   }
 }
 
-__device__ __forceinline__ uint32_t rect_tiles(uint2 rc) { return ((rc.x >> 16) - (rc.x & 0xffffu)) * ((rc.y >> 16) - (rc.y & 0xffffu)); }
-
-// instances of every block of 256 depth-sorted Gaussians
-__global__ void __launch_bounds__(256) sorted_block_tiles_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ n_vis_ptr,
-                                                                 uint32_t gcap, const uint2* __restrict__ rects,
-                                                                 uint32_t* __restrict__ sblock_tiles) {
-  __shared__ uint32_t s_w[8];
+// tile rectangles in depth order (so that the scan below streams them with coalesced loads)
+__global__ void __launch_bounds__(256) gather_sorted_rects_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ n_vis_ptr,
+                                                                  uint32_t gcap, const uint2* __restrict__ rects, uint2* __restrict__ srect) {
   const uint32_t n_vis = min(*n_vis_ptr, gcap);
   const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-  uint32_t tiles = i < n_vis ? rect_tiles(__ldg(rects + __ldg(order + i))) : 0u;
-  tiles = __reduce_add_sync(0xffffffffu, tiles);
-  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = tiles;
-  __syncthreads();
-  if (threadIdx.x == 0) sblock_tiles[blockIdx.x] = s_w[0] + s_w[1] + s_w[2] + s_w[3] + s_w[4] + s_w[5] + s_w[6] + s_w[7];
+  if (i < n_vis) srect[i] = __ldg(rects + __ldg(order + i));
 }
 
-// One CTA per block of 256 depth-sorted Gaussians: cooperative expansion as in scatter_kernel, position = exclusive
-// prefix of the blocks before + rank inside the block.  Also zeroes the backward accumulator rows of its slots.
-__global__ void __launch_bounds__(256) emit_sorted_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ n_vis_ptr,
-                                                          uint32_t gcap, const uint2* __restrict__ rects, const uint32_t* __restrict__ sblock_off,
-                                                          uint64_t* __restrict__ words, float* __restrict__ grad_acc, uint32_t grid_x,
-                                                          BinHeader hv, BinHeader* header, uint32_t* unit_count, PackedKey pk) {
-  const uint32_t capacity = (uint32_t)hv.capacity;
-  __shared__ uint32_t s_end[256];
-  __shared__ uint2 s_rect[256];
-  __shared__ uint32_t s_slot[256];
-  __shared__ uint32_t s_wsum[8];
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    if (header) *header = hv;
-    unit_count[0] = 0;
-    unit_count[3] = unit_count[4] = unit_count[5] = unit_count[6] = 0;
-  }
-  const uint32_t n_vis = min(*n_vis_ptr, gcap);
-  const uint32_t first = blockIdx.x * 256u;
-  if (first >= n_vis) return;
-  const uint32_t cnt = min(256u, n_vis - first);
+constexpr int TB_ITEMS = 2;                  // sorted Gaussians per thread and chunk (consecutive: order = thread order)
+constexpr int TB_CHUNK = TB_THREADS * TB_ITEMS;
+static_assert(TB_CAND >= 2 * TB_CHUNK - TB_CHUNK / 2, "the candidate buffer must take a chunk on top of a partly filled buffer");
+
+__global__ void __launch_bounds__(TB_THREADS, 4) tile_scan_bin_kernel(const uint32_t* __restrict__ order, const uint2* __restrict__ srect,
+                                                                      const uint32_t* __restrict__ n_vis_ptr, uint32_t gcap,
+                                                                      const uint2* __restrict__ ranges, uint32_t* __restrict__ point_list,
+                                                                      uint32_t grid_x, uint32_t grid_y, uint32_t capacity) {
+  __shared__ uint2 s_rect[TB_CAND];
+  __shared__ uint32_t s_slot[TB_CAND];
+  __shared__ uint32_t s_wcount[2][TB_WARPS];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t tiles = 0;
-  if (tid < cnt) {
-    const uint32_t slot = __ldg(order + first + tid);
-    const uint2 rc = __ldg(rects + slot);
-    s_rect[tid] = rc;
-    s_slot[tid] = slot;
-    tiles = rect_tiles(rc);
-    float4* acc = reinterpret_cast<float4*>(grad_acc + 12 * (size_t)slot);
-    acc[0] = acc[1] = acc[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  uint32_t incl = tiles;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
-  if (lane == 31) s_wsum[warp] = incl;
-  __syncthreads();
-  uint32_t woff = 0;
-  for (uint32_t w = 0; w < warp; w++) woff += s_wsum[w];
-  s_end[tid] = woff + incl;
-  __syncthreads();
-  const uint32_t total = s_end[255];
-  const uint32_t base = __ldg(sblock_off + blockIdx.x);
-  for (uint32_t j = tid; j < total; j += 256u) {
-    uint32_t lo = 0, hi = cnt - 1;      // smallest t with s_end[t] > j
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (s_end[mid] > j) hi = mid; else lo = mid + 1;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t n_vis = min(*n_vis_ptr, gcap);
+  // super-tile of this CTA and tile of this warp
+  const uint32_t sgx = (grid_x + TB_SUPER - 1) / TB_SUPER;
+  const uint32_t sx0 = (blockIdx.x % sgx) * TB_SUPER, sy0 = (blockIdx.x / sgx) * TB_SUPER;
+  const uint32_t sx1 = min(sx0 + TB_SUPER, grid_x), sy1 = min(sy0 + TB_SUPER, grid_y);
+  const uint32_t tx = sx0 + (warp % TB_SUPER), ty = sy0 + (warp / TB_SUPER);
+  const bool have_tile = tx < grid_x && ty < grid_y;
+  uint32_t cursor = have_tile ? ranges[ty * grid_x + tx].x : 0u;      // next free position of the tile's list (warp-uniform)
+
+  auto flush = [&](uint32_t ncand) {
+    // every warp walks the candidates in order and appends those whose rectangle contains its tile
+    if (have_tile) {
+      for (uint32_t c0 = 0; c0 < ncand; c0 += 32) {
+        const uint32_t c = c0 + lane;
+        bool h = false;
+        if (c < ncand) {
+          const uint2 rc = s_rect[c];
+          h = tx >= (rc.x & 0xffffu) && tx < (rc.x >> 16) && ty >= (rc.y & 0xffffu) && ty < (rc.y >> 16);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, h);
+        if (h) {
+          const uint32_t pos = cursor + __popc(bal & lt);
+          if (pos < capacity) point_list[pos] = s_slot[c];
+        }
+        cursor += __popc(bal);
+      }
     }
-    const uint32_t within = j - (lo == 0 ? 0u : s_end[lo - 1]);
-    const uint2 rc = s_rect[lo];
-    const uint32_t minx = rc.x & 0xffffu, w = (rc.x >> 16) - minx, miny = rc.y & 0xffffu;
-    const uint32_t row = within / w, col = within - row * w;
-    const uint32_t tile = (miny + row) * grid_x + (minx + col);
-    const uint32_t pos = base + j;
-    if (pos < capacity) __stcs(words + pos, ((uint64_t)tile << pk.slot_bits) | (uint64_t)s_slot[lo]);
+  };
+
+  uint32_t ncand = 0;      // candidates buffered (identical in all threads)
+  uint32_t par = 0;
+  // Each thread owns TB_ITEMS consecutive entries of a chunk (two 16-byte loads of rectangles, one of slots), so the
+  // order of the candidates is thread order.  The next chunk is requested one iteration ahead: the loop has a block
+  // barrier per chunk and would otherwise pay a memory round trip between every two of them.
+  uint2 rc_next[TB_ITEMS];
+  uint32_t slot_next[TB_ITEMS];
+  auto request = [&](uint32_t first) {
+#pragma unroll
+    for (int k = 0; k < TB_ITEMS; k++) {
+      const uint32_t i = first + k;
+      rc_next[k] = i < n_vis ? __ldg(srect + i) : make_uint2(0u, 0u);     // empty rectangle: never a candidate
+      slot_next[k] = i < n_vis ? __ldg(order + i) : 0u;
+    }
+  };
+  request(tid * TB_ITEMS);
+  for (uint32_t base = 0; base < n_vis; base += TB_CHUNK, par ^= 1u) {
+    uint2 rc[TB_ITEMS];
+    uint32_t slot[TB_ITEMS];
+    uint32_t mine = 0, hits = 0;
+#pragma unroll
+    for (int k = 0; k < TB_ITEMS; k++) {
+      rc[k] = rc_next[k], slot[k] = slot_next[k];
+      // rectangles are [min, max) in tiles
+      const bool hit = (rc[k].x & 0xffffu) < sx1 && (rc[k].x >> 16) > sx0 && (rc[k].y & 0xffffu) < sy1 && (rc[k].y >> 16) > sy0;
+      mine |= (hit ? 1u : 0u) << k;
+      hits += hit ? 1u : 0u;
+    }
+    if (base + TB_CHUNK < n_vis) request(base + TB_CHUNK + tid * TB_ITEMS);
+    // exclusive prefix of the per-thread hit counts inside the warp
+    uint32_t incl = hits;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += v; }
+    if (lane == 31) s_wcount[par][warp] = incl;
+    __syncthreads();                                   // counts visible (double-buffered: one barrier per chunk)
+    // prefix over the 16 warps, computed by every warp with shuffles
+    uint32_t wc = lane < TB_WARPS ? s_wcount[par][lane] : 0u, wincl = wc;
+#pragma unroll
+    for (int o = 1; o < TB_WARPS; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wincl, o); if (lane >= (uint32_t)o) wincl += v; }
+    const uint32_t total = __shfl_sync(0xffffffffu, wincl, TB_WARPS - 1);
+    const uint32_t before = __shfl_sync(0xffffffffu, wincl - wc, warp);
+    if (ncand + total > TB_CAND) {                     // does not fit on top of what is buffered: drain first (uniform decision)
+      flush(ncand);
+      ncand = 0;
+      __syncthreads();                                 // every warp is done reading the buffer
+    }
+    uint32_t pos = ncand + before + incl - hits;
+#pragma unroll
+    for (int k = 0; k < TB_ITEMS; k++) {
+      if (mine & (1u << k)) {
+        s_rect[pos] = rc[k];
+        s_slot[pos] = slot[k];
+        pos++;
+      }
+    }
+    ncand += total;
+    if (ncand > TB_CAND - TB_CHUNK) {                  // the next chunk might not fit: make the candidates visible for the next drain
+      __syncthreads();
+      flush(ncand);
+      ncand = 0;
+      __syncthreads();
+    }
   }
+  __syncthreads();
+  flush(ncand);
 }
 
-// digit histograms of the tile passes from the per-tile list lengths
-__global__ void __launch_bounds__(256) tile_digit_hist_kernel(const uint2* __restrict__ ranges, uint32_t T, int tile_bits,
-                                                              uint32_t* __restrict__ hist) {
-  const uint32_t t = blockIdx.x * 256u + threadIdx.x;
-  if (t >= T) return;
-  const uint2 rg = ranges[t];
-  const uint32_t len = rg.y - rg.x;
-  if (!len) return;
-  for (int p = 0; p * SORT_RADIX_BITS < tile_bits; p++) {
-    const uint32_t mask = (1u << min(SORT_RADIX_BITS, tile_bits - p * SORT_RADIX_BITS)) - 1u;
-    atomicAdd(&hist[p * SORT_RADIX + ((t >> (p * SORT_RADIX_BITS)) & mask)], len);
-  }
-}
-
-void launch_long_emit(int P, const GeometryView& g, const BinningView& bl, long long capacity, PackedKey pk, uint32_t grid_x, BinHeader hv,
-                      BinHeader* header, cudaStream_t stream) {
-  if (P <= 0) return;
+void launch_long_bin(int P, int T, uint32_t grid_x, uint32_t grid_y, const uint2* ranges, const GeometryView& g, const BinningView& bl,
+                     long long capacity, BinHeader hv, BinHeader* header, cudaStream_t stream) {
+  if (P <= 0 || T <= 0) return;
   const uint32_t nblocks = (uint32_t)num_pre_blocks(P);
   const uint32_t gcap = (uint32_t)bl.gcap;
   const uint32_t gblocks = (gcap + 255u) / 256u;
   uint32_t* n_vis = g.counters + 13;
   // 1. visible slots, compacted, keyed by depth bits
   scan_blocks_kernel<<<1, 1024, 0, stream>>>(g.block_vis, g.block_off, nblocks, n_vis);
-  compact_visible_kernel<<<nblocks, 256, 0, stream>>>(g.block_vis, g.block_off, g.depths, bl.gkeys[0], bl.gvals[0], gcap);
+  compact_visible_kernel<<<nblocks, 256, 0, stream>>>(g.block_vis, g.block_off, g.depths, bl.gkeys[0], bl.gvals[0], gcap, g.grad_acc, hv,
+                                                     header, g.counters + 5);
   count_launch(2);
   // 2. sorted by (depth bits, slot): stable pair sort, the input is in slot order
   SortTemp st;
@@ -874,26 +891,13 @@ void launch_long_emit(int P, const GeometryView& g, const BinningView& bl, long 
   launch_sort_histogram(gk[0], n_vis, gcap, 0, 32, st.hist, stream);
   const int cur = launch_onesweep(gk, gv, n_vis, gcap, 32, st, stream);
   const uint32_t* order = gv[cur];
-  // 3. instances in that order
-  sorted_block_tiles_kernel<<<gblocks, 256, 0, stream>>>(order, n_vis, gcap, g.rect, g.sblock_tiles);
-  scan_blocks_kernel<<<1, 1024, 0, stream>>>(g.sblock_tiles, g.sblock_off, gblocks, nullptr);
-  emit_sorted_kernel<<<gblocks, 256, 0, stream>>>(order, n_vis, gcap, g.rect, g.sblock_off, bl.keys[0], g.grad_acc, grid_x, hv, header,
-                                                 g.counters + 5, pk);
-  count_launch(3);
-  (void)capacity;
-}
-
-void launch_long_sort(int T, const uint2* ranges, const GeometryView& g, const BinningView& bl, long long capacity, PackedKey pk,
-                      cudaStream_t stream) {
-  if (T <= 0 || capacity <= 0) return;
-  const int passes = sort_passes(pk.tile_bits);
-  SortTemp st;
-  carve_sort_temp(bl.sort_temp, capacity, passes, st);
-  sort_temp_reset(bl.sort_temp, capacity, passes, stream);
-  tile_digit_hist_kernel<<<(T + 255) / 256, 256, 0, stream>>>(ranges, (uint32_t)T, pk.tile_bits, st.hist);
-  count_launch();
-  uint64_t* keys[2] = {bl.keys[0], bl.keys[1]};
-  launch_onesweep_packed(keys, bl.point_list, g.counters + 1, capacity, pk, st, stream);
+  uint2* srect = reinterpret_cast<uint2*>(gk[cur ^ 1]);      // the other key buffer is free now: 8 bytes per entry
+  gather_sorted_rects_kernel<<<gblocks, 256, 0, stream>>>(order, n_vis, gcap, g.rect, srect);
+  // 3. tile-major scan into point_list
+  const uint32_t sgx = (grid_x + TB_SUPER - 1) / TB_SUPER, sgy = (grid_y + TB_SUPER - 1) / TB_SUPER;
+  tile_scan_bin_kernel<<<sgx * sgy, TB_THREADS, 0, stream>>>(order, srect, n_vis, gcap, ranges, bl.point_list, grid_x, grid_y,
+                                                           (uint32_t)capacity);
+  count_launch(2);
 }
 
 }  // namespace gsr

@@ -41,9 +41,7 @@ struct GeometryView {           // replaces GeometryState (reference rasterizer_
   uint32_t* block_tiles;        // [ceil(P/256)+1] instances of each CTA
   uint32_t* block_cand;         // [ceil(P/256)+1] candidates of each segment after the cheap cull (preprocess pass 1)
   uint8_t* cand;                // [S] their positions inside the segment, ascending
-  uint32_t* block_off;          // [ceil(P/256)+1] exclusive prefix sums of the long-list path: visible Gaussians per segment, then
-  uint32_t* sblock_tiles;       // [ceil(P/256)+1] instances per block of 256 depth-sorted Gaussians and
-  uint32_t* sblock_off;         // [ceil(P/256)+1] their exclusive prefix sum
+  uint32_t* block_off;          // [ceil(P/256)+1] exclusive prefix sum of block_vis (long-list path)
   uint32_t* counters;           // [32] 1: num_rendered, 3: overflow, 4: largest tile list, 5: backward units, 6-7: backward queue,
                                 //      8-11: units per cost class, 13: visible Gaussians (long-list path),
                                 //      16: sticky overflow
@@ -67,9 +65,9 @@ struct ImageView {              // replaces ImageState (reference rasterizer_imp
 struct BinningView {            // replaces BinningState (reference rasterizer_impl.h:54-64)
   uint32_t* point_list;         // [cap] sorted slots (same offset in both layouts: the backward needs nothing else)
   uint64_t* comp;               // tile-local path: [cap] depth bits << 32 | slot, bucketed by tile
-  // long-list path (tile lists too long for shared memory): ping-pong arrays of packed instance words + sort temp, and the
-  // scratch of the Gaussian-level depth sort that precedes the emission (gcap = min(slots, capacity) entries)
-  uint64_t* keys[2];
+  // long-list path (tile lists too long for shared memory): scratch of the Gaussian-level depth sort
+  // (gcap = min(slots, capacity) entries); the instances themselves go straight to point_list
+  uint64_t* keys[2];       // unused (kept for layout helpers)
   char* sort_temp;
   uint64_t* gkeys[2];
   uint32_t* gvals[2];
@@ -132,8 +130,6 @@ inline char* carve_geometry(char* base, int P, GeometryView& g) {
   carve(p, g.block_cand, (size_t)num_pre_blocks(P) + 1);
   carve(p, g.cand, S);
   carve(p, g.block_off, (size_t)num_pre_blocks(P) + 1);
-  carve(p, g.sblock_tiles, (size_t)num_pre_blocks(P) + 1);
-  carve(p, g.sblock_off, (size_t)num_pre_blocks(P) + 1);
   carve(p, g.counters, (size_t)32);
   carve(p, g.grad_acc, 12 * S);
   return p;
@@ -149,19 +145,6 @@ inline char* carve_image(char* base, int W, int H, ImageView& im) {
   carve(p, im.tile_order, gx * gy);
   carve(p, im.final_cd, (size_t)W * H);
   return p;
-}
-
-// Packed word of the long-list path: tile << slot_bits | slot.  The instances are emitted in (depth, slot) order of
-// their Gaussians, so a stable sort on the tile bits alone completes the reference's tile|depth order.
-struct PackedKey {
-  int slot_bits, tile_bits;                       // low to high; slot_bits + tile_bits <= 64
-  __host__ __device__ int sort_lo() const { return slot_bits; }
-  __host__ __device__ int sort_hi() const { return slot_bits + tile_bits; }
-};
-inline int bits_for(unsigned long long n) {          // bits needed for values 0 .. n-1
-  int b = 0;
-  while (b < 64 && (1ull << b) < n) b++;
-  return b;
 }
 
 // reference rasterizer_impl.cu:35-50

@@ -62,12 +62,9 @@ void launch_scan_tiles(int* tile_diff, uint32_t gx, uint32_t gy, uint2* ranges, 
 // (Gaussian, tile) instances -> tile buckets as depth_bits << 32 | slot; also zeroes the slots' backward accumulators
 void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* comp, uint32_t grid_x, BinHeader hv,
                     BinHeader* header, cudaStream_t stream);
-// long-list path (binning.cu "long lists"): Gaussian-level depth sort + emission of packed instance words in that order,
-// then the stable tile passes into point_list
-void launch_long_emit(int P, const GeometryView& g, const BinningView& bl, long long capacity, PackedKey pk, uint32_t grid_x, BinHeader hv,
-                      BinHeader* header, cudaStream_t stream);
-void launch_long_sort(int T, const uint2* ranges, const GeometryView& g, const BinningView& bl, long long capacity, PackedKey pk,
-                      cudaStream_t stream);
+// long-list path (binning.cu "long lists"): Gaussian-level depth sort, then a tile-major scan straight into point_list
+void launch_long_bin(int P, int T, uint32_t grid_x, uint32_t grid_y, const uint2* ranges, const GeometryView& g, const BinningView& bl,
+                     long long capacity, BinHeader hv, BinHeader* header, cudaStream_t stream);
 void launch_reset_cursors(int T, const uint2* ranges, uint32_t* cursor, cudaStream_t stream);
 // per-tile sort of the buckets on the composite key; writes the sorted slots to point_list
 void launch_tile_sort(int num_tiles, const uint2* ranges, uint64_t* comp, uint32_t* point_list, uint32_t capacity, const uint32_t* tile_order,
@@ -78,9 +75,6 @@ void launch_sort_histogram(const uint64_t* keys, const uint32_t* n_ptr, long lon
 // exclusive scan of the histograms + all onesweep passes; returns index (0/1) of the buffer holding the result
 int launch_onesweep(uint64_t* keys[2], uint32_t* vals[2], const uint32_t* n_ptr, long long n_host, int end_bit,
                     const SortTemp& t, cudaStream_t stream);
-// packed words: key-only passes over [pk.sort_lo(), pk.sort_hi()), histograms already in t.hist; last pass -> list
-void launch_onesweep_packed(uint64_t* keys[2], uint32_t* list, const uint32_t* n_ptr, long long n_host, PackedKey pk, const SortTemp& t,
-                            cudaStream_t stream);
 
 // ---- blending (render.cu)
 struct RenderParams {
