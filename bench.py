@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--workload", default="headline", choices=list(syn.CONFIGS))
     ap.add_argument("--queries", type=int, default=12, help="pose-refinement queries per rank for the queries/s figure (ours only)")
     ap.add_argument("--query-iters", type=int, default=50)
+    ap.add_argument("--c3-queries", type=int, default=512, help="queries of the localization_c3 block (BASELINE config 3), sharded over ranks")
+    ap.add_argument("--no-scale-blocks", action="store_true", help="skip the localization_c3 and train_dp blocks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stage-split", action="store_true")
     return ap.parse_args()
@@ -387,6 +389,152 @@ def run_gpu_arm(args, rank, world, local_rank):
     return stats
 
 
+# --------------------------------------------------------------------------- the two sharded paths of north_star
+def run_localization_c3(args, rank, world, device):
+    """BASELINE config 3: 2M-Gaussian map, 1024x576, `--c3-queries` DISTINCT queries split over the ranks with
+    parallel.shard_queries (no collective on the data path, loop shape of pipelines/7scenes_localize_full_dslam.py:352-365),
+    results gathered with parallel.gather_query_results.  Strong scaling: the query set is fixed, value = queries / max-rank time."""
+    from gs_localization_b200 import localization as loc
+    from gs_localization_b200 import parallel
+    cfg = syn.CONFIGS["C3"]
+    iters = cfg["iters"]
+    m = syn.make_map(cfg["P"], cfg["deg"], cfg["sigma0"], cfg["box"], seed=0).to(device)
+    arm_C = __import__("gs_localization_b200.diff_gaussian_rasterization", fromlist=["_C"])._C
+    bg = torch.zeros(3, device=device)
+    mine = parallel.shard_queries(args.c3_queries, rank, world)
+    e = torch.Tensor([])
+
+    def target_of(q):
+        gt = syn.make_camera(cfg, 30_000 + q)
+        v, p_, _, c = gt.matrices(device)
+        with torch.no_grad():
+            img = arm_C.rasterize_gaussians(bg, m.means3D, e, m.opacities, m.scales, m.rotations, 1.0, e, v, p_, gt.tanfovx, gt.tanfovy,
+                                            gt.H, gt.W, m.shs, m.sh_degree, c, False, False)[1]
+        return gt, img
+
+    work = []
+    for q in mine:
+        gt, img = target_of(q)
+        work.append((q, gt, loc.PoseCamera(gt.perturbed(syn.initial_perturbation(q, trans_m=0.05, rot_deg=1.0)), device), img))
+    # warm-up query (graph capture) on a query that is not part of the set
+    gt_w, img_w = target_of(args.c3_queries + 7)
+    streams = [torch.cuda.Stream(device) for _ in range(2)]
+    refiners = []
+    for s_ in streams:
+        with torch.cuda.stream(s_):
+            cam_w = loc.PoseCamera(gt_w.perturbed(syn.initial_perturbation(1, trans_m=0.05, rot_deg=1.0)), device)
+            r_ = loc.GraphRefiner(m, cam_w, lr=1e-3)
+            r_.refine(cam_w, img_w, iters=iters)
+            refiners.append(r_)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    local = {}
+    todo = list(work)
+    while todo:
+        batch, todo = todo[:2], todo[2:]
+        for (q, gt, cam_q, img), r_, s_ in zip(batch, refiners, streams):
+            with torch.cuda.stream(s_):
+                r_.submit(cam_q, img, iters)
+        for (q, gt, cam_q, img), r_, s_ in zip(batch, refiners, streams):
+            with torch.cuda.stream(s_):
+                w2c = r_.collect()[0]
+            et, er = syn.pose_error(w2c.cpu(), gt.w2c)
+            local[q] = torch.tensor([et, er], dtype=torch.float64, device=device)
+    torch.cuda.synchronize()
+    t_rank = time.perf_counter() - t0
+    table = parallel.gather_query_results(local, args.c3_queries, 2)
+    t = torch.tensor([t_rank, -t_rank], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    if rank != 0:
+        return None
+    tmax, tmin = float(t[0]), -float(t[1])
+    errs = table.cpu()
+    done = int((~torch.isnan(errs[:, 0])).sum())
+    return {"workload": f"C3: {cfg['P']} Gaussians, {cfg['W']}x{cfg['H']}, SH degree {cfg['deg']}, {args.c3_queries} distinct queries, "
+                        f"{iters} pose-refinement iterations each from a 5 cm / 1 deg initial error",
+            "scaling": "strong", "queries": args.c3_queries, "queries_done": done, "n_gpus": world,
+            "queries_per_s": round(args.c3_queries / tmax, 2), "rank_time_s_min_max": [round(tmin, 3), round(tmax, 3)],
+            "tail_imbalance": round(tmax / max(tmin, 1e-9), 3),
+            "median_final_err_m_deg": [round(float(errs[:, 0].nanmedian()), 5), round(float(errs[:, 1].nanmedian()), 4)],
+            "refined_better_than_start": round(float((errs[:, 0] < 0.05).double().mean()), 3)}
+
+
+def run_train_dp(args, rank, world, device):
+    """BASELINE config 4: one data-parallel map-training step per rank-view (loop of gs/7scenes_gs_full_dslam.py:145-241) on the
+    3M-Gaussian map at 1297x840: fused render + L1/SSIM loss + backward, gradient exchange over NCCL (dense: one all-reduce
+    on the gradient arena; sparse: visible rows only, no host round trip), fused optimiser step.  Weak scaling over views."""
+    from gs_localization_b200 import gaussian_model as gm
+    from gs_localization_b200 import io as gio
+    from gs_localization_b200 import parallel
+    cfg = syn.CONFIGS["C4"]
+    raw = gio.deactivate(syn.make_map(cfg["P"], cfg["deg"], cfg["sigma0"], cfg["box"], seed=0))
+    gen = torch.Generator().manual_seed(0)
+    cams = [syn.make_camera(cfg, i) for i in range(16)]
+    gts = [torch.rand(3, cams[0].H, cams[0].W, generator=gen).to(device) for _ in range(16)]
+    bg = torch.zeros(3, device=device)
+    out = {"workload": f"C4: {cfg['P']} Gaussians, {cfg['W']}x{cfg['H']}, SH degree {cfg['deg']}, one view per rank and step, all parameter "
+                       "groups trained, densification statistics exchanged", "scaling": "weak", "n_gpus": world}
+    for mode in ("dense", "sparse"):
+        model = gm.GaussianModel(cfg["deg"], device=device)
+        model.from_raw(raw)
+        model.spatial_lr_scale = 1.0
+        opt = gm.default_training_args(densify_from_iter=10_000, densify_until_iter=15_000)   # statistics are exchanged, no densification inside the timed steps
+        model.training_setup(opt)
+        trainer = parallel.DataParallelTrainer(model, opt, mode=mode)
+        acc = [0.0, 0.0]
+
+        def one(it, timed):
+            vid = parallel.shard_views(16, it, rank, world)
+            torch.cuda.synchronize()
+            if world > 1:
+                torch.distributed.barrier()
+            t0 = time.perf_counter()
+            loss, g, g2d, o = model.compute_gradients(cams[vid], gts[vid], bg, opt, it, after_forward=trainer.after_forward)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            trainer.reduce(g, g2d, o["radii"], True)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            model.apply_gradients(g, None, None, opt, it, 1.0, stats_done=True)
+            torch.cuda.synchronize()
+            t3 = time.perf_counter()
+            if timed:
+                acc[0] += t3 - t0
+                acc[1] += t2 - t1
+
+        for it in range(1, 4):
+            one(it, False)
+        n = 8
+        for it in range(4, 4 + n):
+            one(it, True)
+        t = torch.tensor(acc, dtype=torch.float64, device=device) / n
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        # gradient-sum parity: exchanged gradient of one more step against the per-view gradients recomputed here
+        it = 4 + n
+        vid = parallel.shard_views(16, it, rank, world)
+        ref = None
+        for r in range(world):
+            v = parallel.shard_views(16, it, r, world)
+            _, gr, _, _ = model.compute_gradients(cams[v], gts[v], bg, opt, it)
+            ref = [x.clone() for x in gr] if ref is None else [a + b for a, b in zip(ref, gr)]
+        _, g, g2d, o = model.compute_gradients(cams[vid], gts[vid], bg, opt, it, after_forward=trainer.after_forward)
+        trainer.reduce(g, g2d, o["radii"], False)
+        err = max(float((a - b).norm() / (b.norm() + 1e-30)) for a, b in zip(g, ref))
+        step_s, ex_s = float(t[0]), float(t[1])
+        nbytes = trainer.exchange_bytes
+        bus = (2.0 * (world - 1) / world * nbytes if mode == "dense" else (world - 1) / world * nbytes) / max(ex_s, 1e-9) / 1e9 if world > 1 else None
+        out[mode] = {"views_per_s": round(world / step_s, 1), "step_ms": round(step_s * 1e3, 3), "exchange_ms": round(ex_s * 1e3, 3),
+                     "exchange_MB": round(nbytes / 1e6, 1), "bus_GBs": None if bus is None else round(bus, 1),
+                     "grad_sum_rel_err": err}
+        del model, trainer
+        torch.cuda.empty_cache()
+    return out if rank == 0 else None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -573,6 +721,13 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     st = run_gpu_arm(args, rank, world, local_rank)
 
+    scale_blocks = {}
+    if args.impl == "ours" and not args.no_scale_blocks:
+        dev_ = torch.device("cuda", local_rank)
+        torch.cuda.empty_cache()
+        scale_blocks["localization_c3"] = run_localization_c3(args, rank, world, dev_)
+        torch.cuda.empty_cache()
+        scale_blocks["train_dp"] = run_train_dp(args, rank, world, dev_)
     ms_total, e2e_s, queries_s = st["ms_total"], st["e2e_s"], st["queries_s"] or 0.0
     if world > 1:
         t = torch.tensor([ms_total, e2e_s, queries_s], device=f"cuda:{local_rank}", dtype=torch.float64)
@@ -597,6 +752,9 @@ def main():
                             "L1 loss+grad kernel, pose-only backward, Adam+SE3 kernel)",
                 "median_final_err_m_deg": [round(sorted(e[0] for e in errs)[len(errs) // 2], 5),
                                            round(sorted(e[1] for e in errs)[len(errs) // 2], 4)] if errs else None}
+        for k, v in scale_blocks.items():
+            if v:
+                line[k] = v
         if st["roofline"]:
             line["roofline"] = st["roofline"]
         if st["split"]:

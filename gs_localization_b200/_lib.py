@@ -62,7 +62,9 @@ SIGNATURES = {
     "gsr_l1_ssim_loss_grad": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P, _P]),
     "gsr_map_adam_step": (C.c_int, [C.c_int] * 4 + [_P, _P, C.c_float, C.c_float, C.c_float] + [_P] * 13),
     "gsr_pack_gradient_rows": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
-    "gsr_add_gradient_rows": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "gsr_add_gradient_rows": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "gsr_pack_visible_rows": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P, _P]),
+    "gsr_add_counted_rows": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P]),
     "gsr_knn_workspace_bytes": (C.c_size_t, [C.c_longlong]),
     "gsr_dist2_knn3": (C.c_int, [_P, C.c_longlong, _P, _P, _P]),
     "gsr_depth_loss_grad": (C.c_int, [_P, _P, _P, C.c_longlong, C.c_float, C.c_float, C.c_float, _P, _P, _P, _P]),
@@ -93,7 +95,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.gsr_abi_version() != 1:
+    if lib.gsr_abi_version() != 2:
         raise GsrError("libgsr_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

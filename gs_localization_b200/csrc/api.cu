@@ -811,14 +811,41 @@ int gsr_pack_gradient_rows(const long long* row_ids, int n_rows, int padded_rows
   return GSR_OK;
 }
 
-int gsr_add_gradient_rows(const float* table, int padded_rows, int M, float* const* grads, void* stream_) {
-  if (padded_rows < 0 || M < 1 || !grads || !table) return fail(GSR_ERR_INVALID_ARGUMENT, "bad arguments");
+int gsr_pack_visible_rows(const int* radii, int P, int M, float* const* grads, const float* dL_dmeans2D, float* table, int capacity_rows,
+                          unsigned int* count, void* stream_) {
+  if (P < 0 || M < 1 || capacity_rows < 1 || !radii || !grads || !table || !count) return fail(GSR_ERR_INVALID_ARGUMENT, "bad arguments");
   GradRowTensors t;
   for (int i = 0; i < 5; i++) {
     if (!grads[i]) return fail(GSR_ERR_INVALID_ARGUMENT, "null gradient tensor %d", i);
     t.g[i] = grads[i];
   }
-  launch_add_gradient_rows(table, padded_rows, M, t, (cudaStream_t)stream_);
+  launch_pack_visible_rows(radii, P, M, t, dL_dmeans2D, table, capacity_rows, count, (cudaStream_t)stream_);
+  GSR_STAGE("pack_visible_rows", 0, (cudaStream_t)stream_);
+  return GSR_OK;
+}
+
+int gsr_add_counted_rows(const float* table, int capacity_rows, int M, int P, float* const* grads, int add_gradients, float* max_radii2D,
+                         float* xyz_gradient_accum, float* denom, void* stream_) {
+  if (capacity_rows < 1 || M < 1 || P < 0 || !grads || !table) return fail(GSR_ERR_INVALID_ARGUMENT, "bad arguments");
+  if (max_radii2D && (!xyz_gradient_accum || !denom)) return fail(GSR_ERR_INVALID_ARGUMENT, "statistics need all three arrays");
+  GradRowTensors t;
+  for (int i = 0; i < 5; i++) {
+    if (!grads[i]) return fail(GSR_ERR_INVALID_ARGUMENT, "null gradient tensor %d", i);
+    t.g[i] = grads[i];
+  }
+  launch_add_counted_rows(table, capacity_rows, M, P, t, add_gradients, max_radii2D, xyz_gradient_accum, denom, (cudaStream_t)stream_);
+  GSR_STAGE("add_counted_rows", 0, (cudaStream_t)stream_);
+  return GSR_OK;
+}
+
+int gsr_add_gradient_rows(const float* table, int padded_rows, int M, int P, float* const* grads, void* stream_) {
+  if (padded_rows < 0 || M < 1 || P < 0 || !grads || !table) return fail(GSR_ERR_INVALID_ARGUMENT, "bad arguments");
+  GradRowTensors t;
+  for (int i = 0; i < 5; i++) {
+    if (!grads[i]) return fail(GSR_ERR_INVALID_ARGUMENT, "null gradient tensor %d", i);
+    t.g[i] = grads[i];
+  }
+  launch_add_gradient_rows(table, padded_rows, M, t, P, (cudaStream_t)stream_);
   GSR_STAGE("add_gradient_rows", 0, (cudaStream_t)stream_);
   return GSR_OK;
 }

@@ -198,7 +198,11 @@ struct MapStepParams {
 };
 struct GradRowTensors { float* g[5]; };   // xyz, features, opacity, scaling, rotation gradients
 void launch_pack_gradient_rows(const long long* idx, int k, int K, int M, const GradRowTensors& t, float* table, cudaStream_t stream);
-void launch_add_gradient_rows(const float* table, int K, int M, const GradRowTensors& t, cudaStream_t stream);
+void launch_add_gradient_rows(const float* table, int K, int M, const GradRowTensors& t, int P, cudaStream_t stream);
+void launch_pack_visible_rows(const int* radii, int P, int M, const GradRowTensors& t, const float* g_means2D, float* table, int capacity,
+                              unsigned int* count, cudaStream_t stream);
+void launch_add_counted_rows(const float* table, int capacity, int M, int P, const GradRowTensors& t, int add_grads, float* max_radii2D,
+                             float* xyz_gradient_accum, float* denom, cudaStream_t stream);
 void launch_map_step(const MapStepParams& s, float beta1, float beta2, float eps, const int* steps, cudaStream_t stream);
 
 // ---- simple-knn (knn.cu)

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) pack_gradient_rows_kernel(const long long
   }
 }
 
-__global__ void __launch_bounds__(256) add_gradient_rows_kernel(const float* __restrict__ table, int K, int M, GradRowTensors t) {
+__global__ void __launch_bounds__(256) add_gradient_rows_kernel(const float* __restrict__ table, int K, int M, GradRowTensors t, int P) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= K) return;
   const int F = 11 + 3 * M;
@@ -197,14 +197,99 @@ __global__ void __launch_bounds__(256) add_gradient_rows_kernel(const float* __r
   }
 }
 
+// ---- the same exchange without a host round trip: the visible rows (radii > 0) are appended through a device counter
+// into a table of fixed capacity; row `capacity` is the header (word 0: number of rows the view produced, which the
+// receivers clamp to the capacity and the host checks one step later).  Columns after the gradients: the screen-space
+// gradient (x, y) and the radius of the view, i.e. what the densification statistics of gaussian_model.py:405-407 need,
+// so that every replica accumulates the statistics of ALL views of the step and takes identical densification decisions.
+__global__ void __launch_bounds__(256) pack_visible_rows_kernel(const int* __restrict__ radii, int P, int M, GradRowTensors t,
+                                                                const float* __restrict__ g_means2D, float* __restrict__ table,
+                                                                int capacity, unsigned int* __restrict__ count) {
+  const int F = 11 + 3 * M, W = 1 + F + 3;
+  const int lane = threadIdx.x & 31;
+  const int warp_first = (blockIdx.x * blockDim.x + threadIdx.x) & ~31;
+  if (warp_first >= P) return;
+  const int i = warp_first + lane;
+  const bool vis = i < P && radii[i] > 0;
+  const unsigned int bal = __ballot_sync(0xffffffffu, vis);
+  if (!bal) return;
+  unsigned int base = 0;
+  if (lane == 0) base = atomicAdd(count, (unsigned int)__popc(bal));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  // the warp writes its visible rows one after the other, 32 columns at a time
+  const int width[5] = {3, 3 * M, 1, 3, 4};
+  unsigned int m = bal, k = 0;
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    const unsigned int row = base + k++;
+    if (row >= (unsigned int)capacity) continue;
+    const int g = warp_first + src;
+    float* out = table + (size_t)row * W;
+    if (lane == 0) out[0] = __int_as_float(g);
+    for (int c = lane; c < F; c += 32) {
+      int ten, w;
+      row_column(c, M, ten, w);
+      out[1 + c] = t.g[ten][(size_t)g * width[ten] + w];
+    }
+    if (lane < 2) out[1 + F + lane] = g_means2D ? g_means2D[3 * (size_t)g + lane] : 0.f;
+    if (lane == 2) out[1 + F + 2] = (float)radii[g];
+  }
+}
+__global__ void pack_visible_header_kernel(float* table, int capacity, int W, const unsigned int* count) {
+  table[(size_t)capacity * W] = __int_as_float((int)*count);
+}
+
+// adds a received table: gradients (unless it is this rank's own table, whose rows are already in place) and the
+// densification statistics; rows beyond the header's count or with ids outside [0, P) are ignored
+__global__ void __launch_bounds__(256) add_counted_rows_kernel(const float* __restrict__ table, int capacity, int M, int P, GradRowTensors t,
+                                                               int add_grads, float* __restrict__ max_radii2D,
+                                                               float* __restrict__ xyz_gradient_accum, float* __restrict__ denom) {
+  const int F = 11 + 3 * M, W = 1 + F + 3;
+  const int n = min(__float_as_int(table[(size_t)capacity * W]), capacity);
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* in = table + (size_t)row * W;
+  const int g = __float_as_int(in[0]);
+  if (g < 0 || g >= P) return;
+  if (add_grads) {
+    const int width[5] = {3, 3 * M, 1, 3, 4};
+    for (int c = lane; c < F; c += 32) {
+      int ten, w;
+      row_column(c, M, ten, w);
+      t.g[ten][(size_t)g * width[ten] + w] += in[1 + c];   // row ids are unique within one rank's table
+    }
+  }
+  if (lane == 0 && max_radii2D) {
+    const float gx = in[1 + F], gy = in[1 + F + 1], r = in[1 + F + 2];
+    max_radii2D[g] = fmaxf(max_radii2D[g], r);
+    xyz_gradient_accum[g] += sqrtf(gx * gx + gy * gy);
+    denom[g] += 1.f;
+  }
+}
+
+void launch_pack_visible_rows(const int* radii, int P, int M, const GradRowTensors& t, const float* g_means2D, float* table, int capacity,
+                              unsigned int* count, cudaStream_t stream) {
+  cudaMemsetAsync(count, 0, sizeof(unsigned int), stream);
+  if (P > 0) pack_visible_rows_kernel<<<(P + 255) / 256, 256, 0, stream>>>(radii, P, M, t, g_means2D, table, capacity, count);
+  pack_visible_header_kernel<<<1, 1, 0, stream>>>(table, capacity, 1 + 11 + 3 * M + 3, count);
+  count_launch(2);
+}
+void launch_add_counted_rows(const float* table, int capacity, int M, int P, const GradRowTensors& t, int add_grads, float* max_radii2D,
+                             float* xyz_gradient_accum, float* denom, cudaStream_t stream) {
+  if (capacity <= 0) return;
+  add_counted_rows_kernel<<<(capacity + 7) / 8, 256, 0, stream>>>(table, capacity, M, P, t, add_grads, max_radii2D, xyz_gradient_accum, denom);
+  count_launch();
+}
+
 void launch_pack_gradient_rows(const long long* idx, int k, int K, int M, const GradRowTensors& t, float* table, cudaStream_t stream) {
   if (K <= 0) return;
   pack_gradient_rows_kernel<<<(K + 7) / 8, 256, 0, stream>>>(idx, k, K, M, t, table);
   count_launch();
 }
-void launch_add_gradient_rows(const float* table, int K, int M, const GradRowTensors& t, cudaStream_t stream) {
+void launch_add_gradient_rows(const float* table, int K, int M, const GradRowTensors& t, int P, cudaStream_t stream) {
   if (K <= 0) return;
-  add_gradient_rows_kernel<<<(K + 7) / 8, 256, 0, stream>>>(table, K, M, t);
+  add_gradient_rows_kernel<<<(K + 7) / 8, 256, 0, stream>>>(table, K, M, t, P);
   count_launch();
 }
 

@@ -281,7 +281,7 @@ class GaussianModel:
         self.denom[update_filter] += 1
 
     # ------------------------------------------------------------------ one training iteration, no autograd
-    def compute_gradients(self, cam, gt_image, bg, opt, iteration: int, pseudo_depth=None, gt_depth=None):
+    def compute_gradients(self, cam, gt_image, bg, opt, iteration: int, pseudo_depth=None, gt_depth=None, after_forward=None):
         """Render + loss + backward of one view (7scenes_gs_full_dslam.py:128-190) without touching the parameters.
         Returns (loss[1], grads, dL_dmeans2D, outputs); grads = (dL_dxyz, dL_dfeatures, dL_dopacity_act, dL_dscaling_act,
         dL_drotation_act), dense over all Gaussians and exactly zero outside `outputs["radii"] > 0`."""
@@ -295,6 +295,8 @@ class GaussianModel:
         fwd = _rast._forward_impl(bg, self._xyz, e, self._opacity_act, self._scaling_act, self._rotation_act, 1.0, e, view, proj,
                                   cam.tanfovx, cam.tanfovy, cam.H, cam.W, self._features, self.active_sh_degree, campos, False, False)
         R, color, depth, alpha, radii, geom, binning, img, _ = fwd
+        if after_forward is not None:
+            after_forward(radii)        # e.g. the data-parallel exchange starts counting its rows while the backward runs
         stream = torch.cuda.current_stream(dev).cuda_stream
         p = lambda t: None if t is None else t.data_ptr()
         loss = torch.zeros(1, device=dev)
@@ -315,17 +317,21 @@ class GaussianModel:
         g = (dL_dmeans3D, dL_dsh, dL_dopacity, dL_dscales, dL_drotations)
         return loss, g, dL_dmeans2D, dict(render=color, depth=depth, alpha=alpha, radii=radii)
 
-    def apply_gradients(self, g, dL_dmeans2D, radii, opt, iteration: int, extent: float = 1.0):
+    def apply_gradients(self, g, dL_dmeans2D, radii, opt, iteration: int, extent: float = 1.0, stats_done: bool = False):
         """Statistics, densification / opacity reset on their schedule, and the optimiser step
-        (7scenes_gs_full_dslam.py:225-242).  Under data parallelism `g` is the sum over ranks (identical everywhere, so
-        every rank takes the same densification decisions given the same RNG seed) while dL_dmeans2D / radii stay local
-        unless the caller exchanged them too."""
+        (7scenes_gs_full_dslam.py:225-242).  Under data parallelism `g` is the sum over ranks and `stats_done=True` says
+        that the densification statistics of ALL views of the step have already been accumulated by the exchange
+        (parallel.DataParallelTrainer): every replica then holds the same statistics and takes the same densification
+        decisions.  Passing only the local dL_dmeans2D / radii in a data-parallel run would let the replicas diverge at
+        the first densification."""
         info = None
+        with_stats = not stats_done
         if iteration < opt.densify_until_iter:
             densify = iteration > opt.densify_from_iter and iteration % opt.densification_interval == 0
             reset = iteration % opt.opacity_reset_interval == 0
             if densify or reset:
-                self.optimizer_step(g, dL_dmeans2D, radii, stats=True, adam=False)
+                if with_stats:
+                    self.optimizer_step(g, dL_dmeans2D, radii, stats=True, adam=False)
                 if densify:
                     info = self.densify_and_prune(opt.densify_grad_threshold, 0.005, extent,
                                                   20 if iteration > opt.opacity_reset_interval else None)
@@ -335,8 +341,10 @@ class GaussianModel:
                     self.optimizer_step(g, adam=True)
                 else:
                     self._skip.clear()   # every parameter was replaced: optimizer.step() finds no gradients at all
-            else:
+            elif with_stats:
                 self.optimizer_step(g, dL_dmeans2D, radii, stats=True, adam=True)
+            else:
+                self.optimizer_step(g, adam=True)
         else:
             self.optimizer_step(g, adam=True)
         return info

@@ -58,6 +58,70 @@ def gather_query_results(local: Dict[int, torch.Tensor], num_queries: int, width
     return out
 
 
+def _backend() -> str:
+    return dist.get_backend() if dist.is_available() and dist.is_initialized() else ""
+
+
+def _all_reduce(t: torch.Tensor, op=None):
+    """dist.all_reduce; with the gloo backend (CPU tests, two processes sharing one GPU) CUDA tensors go through the host."""
+    op = dist.ReduceOp.SUM if op is None else op
+    if t.is_cuda and _backend() == "gloo":
+        h = t.cpu()
+        dist.all_reduce(h, op=op)
+        t.copy_(h)
+    else:
+        dist.all_reduce(t, op=op)
+    return t
+
+
+def _all_gather_into(out: torch.Tensor, t: torch.Tensor):
+    if t.is_cuda and _backend() == "gloo":
+        ho = torch.empty(out.shape, dtype=out.dtype)
+        dist.all_gather_into_tensor(ho, t.cpu())
+        out.copy_(ho)
+    else:
+        dist.all_gather_into_tensor(out, t)
+    return out
+
+
+def gradient_arena(grads: Sequence[torch.Tensor]):
+    """The single allocation the rasterizer's backward carved its gradient tensors from (binding/torch_binding.cpp: one
+    arena, 128-byte aligned slices, padding zero-filled), or None if the tensors do not share one."""
+    base = None
+    for g in grads:
+        if g is None:
+            continue
+        b = g._base if g._base is not None else g
+        if base is None:
+            base = b
+        elif b is not base:
+            return None
+    return base
+
+
+def allreduce_gradients(grads: Sequence[torch.Tensor], average: bool = False) -> int:
+    """Dense data-parallel exchange, in place and without a copy: the gradient tensors of one backward already live in
+    ONE arena, so the all-reduce runs on the arena itself (the pack into / unpack from a separate flat bucket that
+    GradientBucket does costs two extra passes over 59 floats per Gaussian).  Returns the bytes reduced."""
+    rank, ws = world()
+    arena = gradient_arena(grads)
+    if arena is None:                      # tensors from different allocations (ctypes binding): one collective each
+        n = 0
+        for g in grads:
+            if g is not None:
+                if ws > 1:
+                    _all_reduce(g)
+                    if average:
+                        g.div_(ws)
+                n += g.numel() * 4
+        return n
+    if ws > 1:
+        _all_reduce(arena)
+        if average:
+            arena.div_(ws)
+    return arena.numel() * arena.element_size()
+
+
 class GradientBucket:
     """Flat fp32 bucket for the map-training gradient exchange.
 
@@ -165,7 +229,7 @@ class SparseGradientExchange:
                 continue
             part = gathered[r * K:(r + 1) * K]
             if fused:
-                _lib.check(lib.gsr_add_gradient_rows(part.data_ptr(), K, M, tab, stream), "gsr_add_gradient_rows")
+                _lib.check(lib.gsr_add_gradient_rows(part.data_ptr(), K, M, int(grads[0].shape[0]), tab, stream), "gsr_add_gradient_rows")
                 continue
             rows = part[:, 0].contiguous().view(torch.int32).to(torch.int64)
             keep = rows >= 0
@@ -175,3 +239,143 @@ class SparseGradientExchange:
                 g.view(g.shape[0], -1).index_add_(0, rows, part[keep, off:off + w])
                 off += w
         return list(grads)
+
+
+class VisibleRowExchange:
+    """Visible-rows gradient exchange that never makes the host wait (SparseGradientExchange pays two round trips per step:
+    the row count for `nonzero`, and the MAX of the counts over ranks).
+
+    The number of visible rows of a view is known as soon as its FORWARD has run (`radii`), a whole backward before the
+    gradients exist.  `begin(radii)` — called right after the forward — counts them on the device, all-reduces the MAX
+    over ranks on a side stream and copies it to pinned memory, all while the backward runs; by the time `exchange()` is
+    called the count has long landed, so the table size is exact (no overflow case) and reading it costs no stall.
+    Every rank then appends the rows of its visible Gaussians through a device counter into its table
+    (gsr_pack_visible_rows), the tables are all-gathered and added on the device (gsr_add_counted_rows), which also
+    accumulates the densification statistics of ALL views of the step, so that the replicas take identical
+    densification decisions."""
+
+    def __init__(self, P: int, M: int, device, granularity: int = 4096):
+        self.P, self.M, self.dev = int(P), int(M), torch.device(device)
+        self.W = 1 + 11 + 3 * self.M + 3
+        self.granularity = int(granularity)
+        self.count = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._side = torch.cuda.Stream(self.dev) if self.dev.type == "cuda" else None
+        self._max_rows = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self._pinned = torch.zeros(1, dtype=torch.int32).pin_memory() if self.dev.type == "cuda" else torch.zeros(1, dtype=torch.int32)
+        self._ready = None
+        self.last_rows, self.last_bytes = 0, 0
+
+    def resize(self, P: int):
+        """After densification / pruning the map has a different number of rows."""
+        self.P = int(P)
+
+    def begin(self, radii: torch.Tensor):
+        """Start the (tiny) exchange of the row count; call right after the forward, before the backward is queued."""
+        rank, ws = world()
+        cur = torch.cuda.current_stream(self.dev)
+        self._max_rows.copy_((radii > 0).sum(dtype=torch.int32).reshape(1))
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(fork)
+            if ws > 1:
+                _all_reduce(self._max_rows, dist.ReduceOp.MAX)
+            self._pinned.copy_(self._max_rows, non_blocking=True)
+            self._ready = torch.cuda.Event()
+            self._ready.record(self._side)
+
+    def exchange(self, grads: Sequence[torch.Tensor], radii: torch.Tensor, dL_dmeans2D: torch.Tensor | None = None, stats=None):
+        """grads: (xyz [P,3], features [P,M,3], opacity [P,1], scaling [P,3], rotation [P,4]) dense fp32, summed over ranks in
+        place.  stats = (max_radii2D [P], xyz_gradient_accum [P,1], denom [P,1]) are updated with every rank's view."""
+        import ctypes as C
+
+        from . import _lib
+        lib = _lib.load()
+        rank, ws = world()
+        if self._ready is None:
+            self.begin(radii)                       # caller did not overlap the count exchange: do it now
+        self._ready.synchronize()
+        self._ready = None
+        g_ = self.granularity
+        cap = max(1, min(self.P, (int(self._pinned[0]) + g_ - 1) // g_ * g_))
+        W, dev = self.W, self.dev
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        tab = (C.c_void_p * 5)(*[g.data_ptr() for g in grads])
+        table = torch.empty((cap + 1) * W, dtype=torch.float32, device=dev)
+        _lib.check(lib.gsr_pack_visible_rows(radii.data_ptr(), self.P, self.M, tab, None if dL_dmeans2D is None else dL_dmeans2D.data_ptr(),
+                                             table.data_ptr(), cap, self.count.data_ptr(), stream), "gsr_pack_visible_rows")
+        if ws > 1:
+            gathered = torch.empty(ws * (cap + 1) * W, dtype=torch.float32, device=dev)
+            _all_gather_into(gathered, table)
+        else:
+            gathered = table
+        sp = [None, None, None] if stats is None else [t.data_ptr() for t in stats]
+        for r in range(ws):
+            part = gathered[r * (cap + 1) * W:(r + 1) * (cap + 1) * W]
+            if r == rank and stats is None:
+                continue
+            _lib.check(lib.gsr_add_counted_rows(part.data_ptr(), cap, self.M, self.P, tab, int(r != rank), sp[0], sp[1], sp[2], stream),
+                       "gsr_add_counted_rows")
+        self.last_rows, self.last_bytes = cap, int(gathered.numel() * 4)
+        return list(grads)
+
+
+class DataParallelTrainer:
+    """Synchronous data-parallel map training over views (loop of gs/7scenes_gs_full_dslam.py:145-241):
+    every rank renders its own view of the step on its replica of the map, the per-Gaussian gradients are summed over
+    ranks — `mode="dense"`: one all-reduce on the gradient arena; `mode="sparse"`: VisibleRowExchange — together with the
+    inputs of the densification statistics, and every rank applies the same fused optimiser / densification step, so
+    the replicas stay identical (same torch.manual_seed on every rank for the split samples).  The all-reduce of step t
+    cannot overlap the forward of step t+1: that forward reads the parameters the optimiser step of t writes."""
+
+    def __init__(self, model, opt, mode: str = "sparse", extent: float = 1.0):
+        assert mode in ("dense", "sparse")
+        self.model, self.opt, self.mode, self.extent = model, opt, mode, float(extent)
+        self.exchange = None
+        self.exchange_bytes = 0
+
+    def _sparse(self):
+        m = self.model
+        P, M = int(m._xyz.shape[0]), int(m._features.shape[1])
+        if self.exchange is None:
+            self.exchange = VisibleRowExchange(P, M, m.device)
+        elif self.exchange.P != P:
+            self.exchange.resize(P)
+        return self.exchange
+
+    def reduce(self, g, dL_dmeans2D, radii, want_stats: bool):
+        """Sum the gradients over ranks and (if the step updates them) the densification statistics of all views."""
+        m = self.model
+        rank, ws = world()
+        stats = (m.max_radii2D, m.xyz_gradient_accum, m.denom) if want_stats else None
+        if self.mode == "sparse":
+            ex = self._sparse()
+            ex.exchange(list(g), radii, dL_dmeans2D, stats)
+            self.exchange_bytes = ex.last_bytes
+        else:
+            self.exchange_bytes = allreduce_gradients(g)
+            if want_stats:
+                # no boolean indexing (it would make the host wait for the visible count): masked dense increments
+                vis = (radii > 0).to(torch.float32)
+                inc = torch.stack([torch.linalg.vector_norm(dL_dmeans2D[:, :2], dim=-1) * vis, vis], dim=1)
+                rad = radii.clamp_min(0).to(torch.float32)
+                if ws > 1:
+                    _all_reduce(inc)
+                    _all_reduce(rad, dist.ReduceOp.MAX)
+                torch.maximum(m.max_radii2D, rad, out=m.max_radii2D)
+                m.xyz_gradient_accum[:, 0] += inc[:, 0]
+                m.denom[:, 0] += inc[:, 1]
+        return g
+
+    def after_forward(self, radii):
+        """Hook for GaussianModel.compute_gradients: the sparse exchange starts its row-count collective under the backward."""
+        if self.mode == "sparse":
+            self._sparse().begin(radii)
+
+    def step(self, cam, gt_image, bg, iteration: int, pseudo_depth=None, gt_depth=None):
+        m, opt = self.model, self.opt
+        loss, g, g2d, out = m.compute_gradients(cam, gt_image, bg, opt, iteration, pseudo_depth, gt_depth, after_forward=self.after_forward)
+        want_stats = iteration < opt.densify_until_iter
+        self.reduce(g, g2d, out["radii"], want_stats)
+        out["densify"] = m.apply_gradients(g, None, None, opt, iteration, self.extent, stats_done=True)
+        return loss, out

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define GSR_ABI_VERSION 1
+#define GSR_ABI_VERSION 2
 
 /* error codes (negative return values) */
 #define GSR_OK 0
@@ -231,7 +231,19 @@ GSR_API int gsr_map_adam_step(int P, int M, int do_stats, int do_adam, const int
  * adds a (received) table back into dense gradients; ids must be unique within a table.  Host tables of device pointers. */
 GSR_API int gsr_pack_gradient_rows(const long long* row_ids, int n_rows, int padded_rows, int M, float* const* grads,
                                    float* table, void* stream);
-GSR_API int gsr_add_gradient_rows(const float* table, int padded_rows, int M, float* const* grads, void* stream);
+GSR_API int gsr_add_gradient_rows(const float* table, int padded_rows, int M, int P, float* const* grads, void* stream);
+/* The same exchange without any host round trip.  gsr_pack_visible_rows appends the rows with radii[i] > 0 through the
+ * device counter `count` (zeroed by the call) into table[capacity_rows + 1][1 + 11 + 3M + 3]: columns = row id (int bits),
+ * the gradients as above, then dL_dmeans2D x, y and the radius of the view (the inputs of the densification statistics,
+ * gaussian_model.py:405-407).  Row `capacity_rows` is a header whose word 0 holds the number of visible rows of the view
+ * (it may exceed capacity_rows: the surplus rows were dropped and the caller must treat the step as failed).
+ * gsr_add_counted_rows applies a (received) table: adds the gradient rows when add_gradients != 0 (a rank passes 0 for its
+ * own table), and, when max_radii2D / xyz_gradient_accum / denom are given, updates the statistics for the table's rows.
+ * Row ids outside [0, P) are ignored. */
+GSR_API int gsr_pack_visible_rows(const int* radii, int P, int M, float* const* grads, const float* dL_dmeans2D, float* table,
+                                  int capacity_rows, unsigned int* count, void* stream);
+GSR_API int gsr_add_counted_rows(const float* table, int capacity_rows, int M, int P, float* const* grads, int add_gradients,
+                                 float* max_radii2D, float* xyz_gradient_accum, float* denom, void* stream);
 /* distCUDA2 of simple-knn (gaussian_splatting/submodules/simple-knn/spatial.cu:15-26, simple_knn.cu:185-221):
  * mean_dists[i] = mean of the squared distances from points[i] to its three nearest other points (exact search;
  * FLT_MAX stands in for missing neighbours when n_points < 4, as in the reference).  points: [n,3] float32.

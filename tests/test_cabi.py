@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s)
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(declared_symbols())
-    assert lib.gsr_abi_version() == 1
+    assert lib.gsr_abi_version() == 2
 
 
 def test_scratch_size_queries_need_no_gpu():
