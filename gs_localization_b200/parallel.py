@@ -263,6 +263,7 @@ class VisibleRowExchange:
         self._max_rows = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._pinned = torch.zeros(1, dtype=torch.int32).pin_memory() if self.dev.type == "cuda" else torch.zeros(1, dtype=torch.int32)
         self._ready = None
+        self._buf = None
         self.last_rows, self.last_bytes = 0, 0
 
     def resize(self, P: int):
@@ -301,11 +302,16 @@ class VisibleRowExchange:
         W, dev = self.W, self.dev
         stream = torch.cuda.current_stream(dev).cuda_stream
         tab = (C.c_void_p * 5)(*[g.data_ptr() for g in grads])
-        table = torch.empty((cap + 1) * W, dtype=torch.float32, device=dev)
+        # persistent buffers that only grow: a table whose size follows the view would otherwise ask the allocator for a new
+        # block (a cudaMalloc, i.e. a device synchronisation) almost every step
+        need = (cap + 1) * W
+        if self._buf is None or self._buf.numel() < need * (ws + 1):
+            self._buf = torch.empty(int(need * (ws + 1) * 1.25), dtype=torch.float32, device=dev)
+        table = self._buf[:need]
         _lib.check(lib.gsr_pack_visible_rows(radii.data_ptr(), self.P, self.M, tab, None if dL_dmeans2D is None else dL_dmeans2D.data_ptr(),
                                              table.data_ptr(), cap, self.count.data_ptr(), stream), "gsr_pack_visible_rows")
         if ws > 1:
-            gathered = torch.empty(ws * (cap + 1) * W, dtype=torch.float32, device=dev)
+            gathered = self._buf[need:need * (ws + 1)]
             _all_gather_into(gathered, table)
         else:
             gathered = table
