@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--workload", default="headline", choices=list(syn.CONFIGS))
     ap.add_argument("--queries", type=int, default=12, help="pose-refinement queries per rank for the queries/s figure (ours only)")
     ap.add_argument("--query-iters", type=int, default=50)
+    ap.add_argument("--query-batch", type=int, default=4, help="queries per CUDA-graph launch (localization.BatchedGraphRefiner)")
     ap.add_argument("--c3-queries", type=int, default=512, help="queries of the localization_c3 block (BASELINE config 3), sharded over ranks")
     ap.add_argument("--no-scale-blocks", action="store_true", help="skip the localization_c3 and train_dp blocks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -355,16 +356,12 @@ def run_gpu_arm(args, rank, world, local_rank):
             with torch.no_grad():
                 target = arm.c_forward(m, bg, v, p_, c, gt)[1].clone()
             qs.append((loc.PoseCamera(gt.perturbed(syn.initial_perturbation(gq, trans_m=0.02, rot_deg=1.0)), device), target, gt))
-        # two graph refiners on two streams per GPU: the latency-bound binning kernels of one query overlap the blend
-        # kernels of the other
-        streams = [torch.cuda.Stream(device) for _ in range(2)]
-        refiners = []
-        for s_ in streams:
-            with torch.cuda.stream(s_):
-                r_ = loc.GraphRefiner(m, qs[0][0], lr=1e-3)
-                warm = loc.PoseCamera(qs[0][2].perturbed(syn.initial_perturbation(0, trans_m=0.02, rot_deg=1.0)), device)
-                r_.refine(warm, qs[0][1], iters=args.query_iters)      # warm-up query: includes the graph capture
-                refiners.append(r_)
+        # B queries per CUDA-graph launch (parallel branches of one graph): the latency-bound binning kernels of one query
+        # overlap the blend kernels of the others, one graph launch per iteration for the whole batch
+        B = args.query_batch
+        refiner = loc.BatchedGraphRefiner(m, qs[0][0], batch=B, lr=1e-3)
+        warm = [loc.PoseCamera(qs[0][2].perturbed(syn.initial_perturbation(0, trans_m=0.02, rot_deg=1.0)), device) for _ in range(B)]
+        refiner.refine_batch(warm, [qs[0][1]] * B, iters=args.query_iters)      # warm-up batch: includes the graph capture
         torch.cuda.synchronize()
         if world > 1:
             torch.distributed.barrier()
@@ -372,13 +369,9 @@ def run_gpu_arm(args, rank, world, local_rank):
         errs = []
         todo = list(qs[1:])
         while todo:
-            batch, todo = todo[:2], todo[2:]
-            for (cam_q, target, gt), r_, s_ in zip(batch, refiners, streams):
-                with torch.cuda.stream(s_):
-                    r_.submit(cam_q, target, args.query_iters)
-            for (cam_q, target, gt), r_, s_ in zip(batch, refiners, streams):
-                with torch.cuda.stream(s_):
-                    errs.append(r_.collect()[0])
+            batch, todo = todo[:B], todo[B:]
+            res_ = refiner.refine_batch([b_[0] for b_ in batch], [b_[1] for b_ in batch], iters=args.query_iters)
+            errs += [r_[0] for r_ in res_]
         torch.cuda.synchronize()
         queries_s = time.perf_counter() - t0
         if world > 1:
@@ -416,16 +409,12 @@ def run_localization_c3(args, rank, world, device):
     for q in mine:
         gt, img = target_of(q)
         work.append((q, gt, loc.PoseCamera(gt.perturbed(syn.initial_perturbation(q, trans_m=0.05, rot_deg=1.0)), device), img))
-    # warm-up query (graph capture) on a query that is not part of the set
+    # warm-up batch (graph capture) on a query that is not part of the set
+    B = args.query_batch
     gt_w, img_w = target_of(args.c3_queries + 7)
-    streams = [torch.cuda.Stream(device) for _ in range(2)]
-    refiners = []
-    for s_ in streams:
-        with torch.cuda.stream(s_):
-            cam_w = loc.PoseCamera(gt_w.perturbed(syn.initial_perturbation(1, trans_m=0.05, rot_deg=1.0)), device)
-            r_ = loc.GraphRefiner(m, cam_w, lr=1e-3)
-            r_.refine(cam_w, img_w, iters=iters)
-            refiners.append(r_)
+    warm = [loc.PoseCamera(gt_w.perturbed(syn.initial_perturbation(1, trans_m=0.05, rot_deg=1.0)), device) for _ in range(B)]
+    refiner = loc.BatchedGraphRefiner(m, warm[0], batch=B, lr=1e-3)
+    refiner.refine_batch(warm, [img_w] * B, iters=iters)
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
@@ -433,13 +422,9 @@ def run_localization_c3(args, rank, world, device):
     local = {}
     todo = list(work)
     while todo:
-        batch, todo = todo[:2], todo[2:]
-        for (q, gt, cam_q, img), r_, s_ in zip(batch, refiners, streams):
-            with torch.cuda.stream(s_):
-                r_.submit(cam_q, img, iters)
-        for (q, gt, cam_q, img), r_, s_ in zip(batch, refiners, streams):
-            with torch.cuda.stream(s_):
-                w2c = r_.collect()[0]
+        batch, todo = todo[:B], todo[B:]
+        res_ = refiner.refine_batch([b_[2] for b_ in batch], [b_[3] for b_ in batch], iters=iters)
+        for (q, gt, cam_q, img), (w2c, _) in zip(batch, res_):
             et, er = syn.pose_error(w2c.cpu(), gt.w2c)
             local[q] = torch.tensor([et, er], dtype=torch.float64, device=device)
     torch.cuda.synchronize()
@@ -748,8 +733,8 @@ def main():
             errs = st.get("final_pose_err") or []
             line["localization"] = {
                 "queries_per_s": round(world * args.queries / queries_s, 3), "iters_per_query": args.query_iters,
-                "queries": world * args.queries, "workload": f"{args.workload} map, pose-only refinement from a 2 cm / 1 deg initial error (2 queries in flight per GPU, one CUDA graph per iteration: sync-free forward, "
-                            "L1 loss+grad kernel, pose-only backward, Adam+SE3 kernel)",
+                "queries": world * args.queries, "workload": f"{args.workload} map, pose-only refinement from a 2 cm / 1 deg initial error ({args.query_batch} queries per CUDA-graph launch, one launch per iteration: "
+                            "sync-free forward, L1 loss+grad kernel, pose-only backward, Adam+SE3 kernel per query)",
                 "median_final_err_m_deg": [round(sorted(e[0] for e in errs)[len(errs) // 2], 5),
                                            round(sorted(e[1] for e in errs)[len(errs) // 2], 4)] if errs else None}
         for k, v in scale_blocks.items():

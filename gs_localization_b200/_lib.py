@@ -38,7 +38,8 @@ SIGNATURES = {
         _P, C.c_float, _P, _P,
         _P, _P, _P,
         C.c_float, C.c_float,
-        _P, _P, _P, _P, _P, _P]),
+        _P, _P, _P, _P, _P, _P, _P]),
+    "gsr_build_cull_records": (C.c_int, [C.c_int, _P, _P, _P, _P, _P]),
     "gsr_read_counters": (C.c_int, [_P, C.c_int, _P, _P]),
     "gsr_clear_overflow": (C.c_int, [_P, C.c_int, _P]),
     "gsr_rasterize_backward": (C.c_int, [

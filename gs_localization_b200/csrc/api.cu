@@ -457,7 +457,7 @@ int gsr_rasterize_forward_async(char* geometry_buffer, char* binning_buffer, lon
                                 const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
                                 const float* viewmatrix, const float* projmatrix, const float* cam_pos, float tan_fovx,
                                 float tan_fovy, float* out_color, float* out_depth, float* out_alpha, int* radii, int* n_touched,
-                                void* stream_) {
+                                const float* cull_records, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (P <= 0 || width <= 0 || height <= 0 || binning_capacity <= 0 || binning_capacity >= (1ll << 30))
     return fail(GSR_ERR_INVALID_ARGUMENT, "bad sizes");
@@ -482,6 +482,7 @@ int gsr_rasterize_forward_async(char* geometry_buffer, char* binning_buffer, lon
   pp.scale_modifier = scale_modifier, pp.tan_fovx = tan_fovx, pp.tan_fovy = tan_fovy;
   pp.focal_y = height / (2.0f * tan_fovy), pp.focal_x = width / (2.0f * tan_fovx);
   pp.prefiltered = 0;
+  pp.cull_rec = cov3D_precomp ? nullptr : reinterpret_cast<const float4*>(cull_records);
   pp.sh_vec4 = shs && (M % 4 == 0) && ((uintptr_t)shs % 16 == 0);
   pp.radii = radii, pp.n_touched = n_touched, pp.tile_diff = im.tile_diff, pp.geom = g;
   launch_preprocess_fwd(pp, stream);
@@ -643,6 +644,16 @@ int gsr_rasterize_backward(int P, int D, int M, long long R, const float* backgr
   }
   GSR_STAGE("preprocess_backward", debug, stream);
   stage_collect(stream);
+  return GSR_OK;
+}
+
+int gsr_build_cull_records(int P, const float* means3D, const float* scales, const float* rotations, float* records, void* stream_) {
+  if (P < 0) return fail(GSR_ERR_INVALID_ARGUMENT, "P < 0");
+  if (P == 0) return GSR_OK;
+  if (!means3D || !scales || !rotations || !records) return fail(GSR_ERR_INVALID_ARGUMENT, "null pointer");
+  if ((uintptr_t)records % 16 || (uintptr_t)rotations % 16) return fail(GSR_ERR_INVALID_ARGUMENT, "records and rotations must be 16-byte aligned");
+  launch_build_cull_records(P, means3D, scales, rotations, reinterpret_cast<float4*>(records), (cudaStream_t)stream_);
+  GSR_STAGE("build_cull_records", 0, (cudaStream_t)stream_);
   return GSR_OK;
 }
 

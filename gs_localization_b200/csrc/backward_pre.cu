@@ -178,13 +178,11 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
       const char* sh_row = reinterpret_cast<const char*>(p.shs + idx * row);
       for (int b = 0; b < row * 4; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(sh_row + b));
     }
-    const float3 mean = {__ldg(p.means3D + 3 * idx), __ldg(p.means3D + 3 * idx + 1), __ldg(p.means3D + 3 * idx + 2)};
-    float3 sc_in = {0, 0, 0};
-    float4 q_in = {0, 0, 0, 0};
-    if (p.scales) {
-      sc_in = make_float3(__ldg(p.scales + 3 * idx), __ldg(p.scales + 3 * idx + 1), __ldg(p.scales + 3 * idx + 2));
-      q_in = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
-    }
+    // mean, scale and rotation were left in the slot by the forward: three coalesced 16-byte loads, no second gather by id
+    const float4 m0 = __ldg(p.geom.msr + 3 * (size_t)k), m1 = __ldg(p.geom.msr + 3 * (size_t)k + 1), m2 = __ldg(p.geom.msr + 3 * (size_t)k + 2);
+    const float3 mean = {m0.x, m0.y, m0.z};
+    const float3 sc_in = {m0.w, m1.x, m1.y};
+    const float4 q_in = {m1.z, m1.w, m2.x, m2.y};
     const uint8_t cm = p.shs ? __ldg(p.geom.clamped + k) : (uint8_t)0;
     const float* c3 = p.cov3D_precomp ? p.cov3D_precomp + 6 * idx : p.geom.cov3D + 6 * (size_t)k;
     float cov3D[6];

@@ -33,6 +33,8 @@ struct GeometryView {           // replaces GeometryState (reference rasterizer_
   float4* mean_tau;             // [slots] (pixel-space centre x, y, 2 ln(255 o) inflated: the opacity-aware culling bound, unused)
   float4* conic_opacity;        // [slots] (conic.x, conic.y, conic.z, opacity)
   float4* rgbd;                 // [slots] (r, g, b, depth): one 16-byte gather for the blend kernels
+  float4* msr;                  // [3 slots] (mean xyz, scale x) (scale y z, rot w x) (rot y z, -, -): what the preprocess backward needs
+                                //           of the map, kept per visible slot so that it does not gather it by Gaussian id again
   float* cov3D;                 // [6 slots]
   uint2* rect;                  // [slots] tile rectangle: x = minx | maxx<<16, y = miny | maxy<<16
   uint8_t* clamped;             // [slots] bit c set <=> channel c was clamped at 0
@@ -121,6 +123,7 @@ inline char* carve_geometry(char* base, int P, GeometryView& g) {
   carve(p, g.mean_tau, S);
   carve(p, g.conic_opacity, S);
   carve(p, g.rgbd, S);
+  carve(p, g.msr, 3 * S);
   carve(p, g.cov3D, 6 * S);
   carve(p, g.rect, S);
   carve(p, g.clamped, S);

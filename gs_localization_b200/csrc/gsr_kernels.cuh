@@ -19,6 +19,7 @@ struct PreprocessParams {
   const float* shs;
   const float* cov3D_precomp;
   const float* colors_precomp;
+  const float4* cull_rec;       // optional: packed static map (mean, static radius-bound factor) for the cull pass
   const float* viewmatrix;
   const float* projmatrix;
   const float* campos;
@@ -34,6 +35,7 @@ struct PreprocessParams {
 void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream);
 // colours of the visible slots (needs preprocess; only the blend needs it)
 void launch_color_fwd(const PreprocessParams& p, cudaStream_t stream);
+void launch_build_cull_records(int P, const float* means3D, const float* scales, const float* rotations, float4* rec, cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t stream);
 
 // ---- binning (binning.cu)

@@ -134,6 +134,31 @@ __device__ __forceinline__ float3 color_from_sh(int deg, float3 pos, float3 camp
   return make_float3(fmaxf(r0, 0.f), fmaxf(r1, 0.f), fmaxf(r2, 0.f));
 }
 
+// static factor of the conservative radius bound: s_max^2 |R|_F^2 with |R|_F^2 = 1 + 2 (1 - 2|v|^2)^2 + 8 w^2 |v|^2 for the
+// reference's unnormalised-quaternion matrix (forward.cu:127-140)
+__device__ __forceinline__ float cull_static_factor(float3 sc, float4 q) {
+  const float smax = fmaxf(fmaxf(fabsf(sc.x), fabsf(sc.y)), fabsf(sc.z));
+  const float v2 = q.y * q.y + q.z * q.z + q.w * q.w;
+  const float r2 = 1.0f + 2.0f * (1.0f - 2.0f * v2) * (1.0f - 2.0f * v2) + 8.0f * q.x * q.x * v2;
+  return smax * smax * r2;
+}
+
+// Static map packed once at load (LoGS localizes hundreds of queries against one read-only map,
+// scene/gaussian_model.py:215-256 load_ply): 16 bytes per Gaussian = mean + the static factor of the radius bound.
+__global__ void __launch_bounds__(256) build_cull_records_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ scales,
+                                                                 const float* __restrict__ rotations, float4* __restrict__ rec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const float3 sc = make_float3(scales[3 * (size_t)i], scales[3 * (size_t)i + 1], scales[3 * (size_t)i + 2]);
+  const float4 q = reinterpret_cast<const float4*>(rotations)[i];
+  rec[i] = make_float4(means3D[3 * (size_t)i], means3D[3 * (size_t)i + 1], means3D[3 * (size_t)i + 2], cull_static_factor(sc, q));
+}
+void launch_build_cull_records(int P, const float* means3D, const float* scales, const float* rotations, float4* rec, cudaStream_t stream) {
+  if (P <= 0) return;
+  build_cull_records_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, scales, rotations, rec);
+  count_launch();
+}
+
 // Pass 1, one thread per Gaussian: depth cull + conservative screen-radius bound; the survivors ("candidates") of
 // each 256-Gaussian segment are compacted, in order, into the segment's candidate list.
 __global__ void __launch_bounds__(PRE_THREADS) preprocess_cull_kernel(const PreprocessParams p) {
@@ -167,11 +192,19 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_cull_kernel(const Prep
     float px = 0.f, py = 0.f, pz = 0.f;
     float3 sc = {0, 0, 0};
     float4 q = {0, 0, 0, 0};
+    float s2r2 = 0.f;          // (largest scale)^2 x squared Frobenius norm of the rotation matrix: the static factor of the radius bound
     if (idx < P) {
-      px = __ldg(p.means3D + 3 * (size_t)idx), py = __ldg(p.means3D + 3 * (size_t)idx + 1), pz = __ldg(p.means3D + 3 * (size_t)idx + 2);
-      if (!p.cov3D_precomp) {
-        sc = make_float3(__ldg(p.scales + 3 * (size_t)idx), __ldg(p.scales + 3 * (size_t)idx + 1), __ldg(p.scales + 3 * (size_t)idx + 2));
-        q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+      if (p.cull_rec) {
+        // static map, packed once at load (gsr_build_cull_records): one 16-byte load instead of 40 bytes in three streams
+        const float4 r = __ldg(p.cull_rec + idx);
+        px = r.x, py = r.y, pz = r.z, s2r2 = r.w;
+      } else {
+        px = __ldg(p.means3D + 3 * (size_t)idx), py = __ldg(p.means3D + 3 * (size_t)idx + 1), pz = __ldg(p.means3D + 3 * (size_t)idx + 2);
+        if (!p.cov3D_precomp) {
+          sc = make_float3(__ldg(p.scales + 3 * (size_t)idx), __ldg(p.scales + 3 * (size_t)idx + 1), __ldg(p.scales + 3 * (size_t)idx + 2));
+          q = __ldg(reinterpret_cast<const float4*>(p.rotations) + idx);
+          s2r2 = cull_static_factor(sc, q);
+        }
       }
     }
     if (tid < 16) s_cam[tid] = p.viewmatrix[tid];
@@ -198,10 +231,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_cull_kernel(const Prep
           const float limx = 1.3f * p.tan_fovx, limy = 1.3f * p.tan_fovy;
           const float iz = 1.0f / vz;
           const float j2 = (p.focal_x * iz) * (p.focal_x * iz) * (1.0f + limx * limx) + (p.focal_y * iz) * (p.focal_y * iz) * (1.0f + limy * limy);
-          const float smax = fmaxf(fmaxf(fabsf(sc.x), fabsf(sc.y)), fabsf(sc.z)) * fabsf(p.scale_modifier);
-          const float v2 = q.y * q.y + q.z * q.z + q.w * q.w;
-          const float r2 = 1.0f + 2.0f * (1.0f - 2.0f * v2) * (1.0f - 2.0f * v2) + 8.0f * q.x * q.x * v2;
-          const float lam = w2 * j2 * smax * smax * r2 * 1.02f + 0.3f + 0.32f;
+          const float lam = w2 * j2 * (s2r2 * p.scale_modifier * p.scale_modifier) * 1.02f + 0.3f + 0.32f;
           const float rb = 3.0f * sqrtf(lam) * 1.01f + 2.0f;
           // outside for sure: the whole [c - rb, c + rb + 15] interval maps to tile index <= 0 or >= grid on one axis
           const bool outside = (cx + rb + 15.0f < 0.0f) || (cx - rb >= 16.0f * (float)p.grid_x) || (cy + rb + 15.0f < 0.0f) ||
@@ -323,6 +353,9 @@ __global__ void __launch_bounds__(PRE2_WARPS * 32) preprocess_fwd_kernel(const P
       p.geom.conic_opacity[k] = make_float4(conic.x, conic.y, conic.z, opacity);
       p.geom.rect[k] = rect;
       p.geom.gid[k] = (uint32_t)idx;
+      p.geom.msr[3 * (size_t)k] = make_float4(px, py, pz, sc.x);
+      p.geom.msr[3 * (size_t)k + 1] = make_float4(sc.y, sc.z, q.x, q.y);
+      p.geom.msr[3 * (size_t)k + 2] = make_float4(q.z, q.w, 0.f, 0.f);
       if (!p.cov3D_precomp) {
 #pragma unroll
         for (int i = 0; i < 6; i++) p.geom.cov3D[6 * (size_t)k + i] = cov3D[i];

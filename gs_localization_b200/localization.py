@@ -292,6 +292,10 @@ class GraphRefiner:
         self.grad_mask = torch.ones(1, H, W, **f32)
         self.exposure, self.dL_dexposure = torch.zeros(2, **f32), torch.zeros(2, **f32)
         self.exp_m, self.exp_v, self.exp_step = torch.zeros(2, **f32), torch.zeros(2, **f32), torch.zeros(1, **f32)
+        # the map is read-only for the whole run: pack the cull pass's inputs once (16 bytes per Gaussian)
+        self.cull_records = torch.empty(P, 4, **f32)
+        _lib.check(lib.gsr_build_cull_records(P, gmap.means3D.data_ptr(), gmap.scales.data_ptr(), gmap.rotations.data_ptr(),
+                                              self.cull_records.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "gsr_build_cull_records")
         self.graph = None
 
     def _iteration(self):
@@ -303,7 +307,7 @@ class GraphRefiner:
             p(self.geom), p(self.binning), self.capacity, self.global_sort, p(self.img), self.P, g.sh_degree, self.M,
             p(self.bg), W, H, p(g.means3D), p(g.shs), None, p(g.opacities), p(g.scales), 1.0, p(g.rotations), None,
             p(self.view), p(self.proj), p(self.campos), self.tanfovx, self.tanfovy,
-            p(self.color), p(self.depth), p(self.alpha), p(self.radii), None, stream), "gsr_rasterize_forward_async")
+            p(self.color), p(self.depth), p(self.alpha), p(self.radii), None, p(self.cull_records), stream), "gsr_rasterize_forward_async")
         self.loss.zero_()
         gD = self.zeros1
         tr = self.tracking
@@ -369,7 +373,7 @@ class GraphRefiner:
             p(self.geom), p(self.binning), self.capacity, self.global_sort, p(self.img), self.P, g.sh_degree, self.M,
             p(self.bg), self.W, self.H, p(g.means3D), p(g.shs), None, p(g.opacities), p(g.scales), 1.0, p(g.rotations), None,
             p(self.view), p(self.proj), p(self.campos), self.tanfovx, self.tanfovy,
-            p(self.color), p(self.depth), p(self.alpha), p(self.radii), None,
+            p(self.color), p(self.depth), p(self.alpha), p(self.radii), None, p(self.cull_records),
             torch.cuda.current_stream(self.dev).cuda_stream), "gsr_rasterize_forward_async")
         R, overflow, longest = self._counters()
         need_global = int(longest * 1.5 > 4096)
@@ -414,3 +418,67 @@ class GraphRefiner:
             self._load_query(cam, target, target_depth, grad_mask)   # capture does not execute, but keep the state explicit
         for _ in range(iters):
             self.graph.replay()
+
+
+class BatchedGraphRefiner:
+    """B independent queries against one map per CUDA-graph launch (queries are independent, the map
+    is read-only).  One graph holds the refinement iteration of B `GraphRefiner`s as B parallel branches; replaying it
+    `iters` times refines B queries at once.  The latency-bound kernels of a small frame (C1: fourteen launches of a
+    few microseconds each per iteration) run side by side instead of one after the other, and the host pays one graph
+    launch per iteration for the whole batch; a large frame's blend kernels, which fill the GPU on their own, overlap
+    with the other branches' binning kernels.  Every branch runs exactly the kernels of the unbatched loop on its own
+    scratch, so the refined poses are those of `GraphRefiner`."""
+
+    def __init__(self, gmap: syn.GaussianMap, cam: PoseCamera, batch: int = 4, **kw):
+        self.dev = cam.device
+        self.refiners = [GraphRefiner(gmap, cam, **kw) for _ in range(int(batch))]
+        self.streams = [torch.cuda.Stream(self.dev) for _ in range(int(batch))]
+        self.graph = None
+        self._captured_with = None
+
+    @property
+    def batch(self) -> int:
+        return len(self.refiners)
+
+    def _capture(self):
+        main = torch.cuda.current_stream(self.dev)
+        for r in self.refiners:                 # warm-up outside capture (lazy CUDA state, side streams)
+            r._iteration()
+        torch.cuda.synchronize(self.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            main_c = torch.cuda.current_stream(self.dev)
+            for r, s_ in zip(self.refiners, self.streams):
+                s_.wait_stream(main_c)
+                with torch.cuda.stream(s_):
+                    r._iteration()
+            for s_ in self.streams:
+                main_c.wait_stream(s_)
+        self._captured_with = [(r.capacity, r.global_sort) for r in self.refiners]
+        del main
+
+    def refine_batch(self, cams, targets, iters: int = 50, target_depths=None, grad_masks=None):
+        """Refine len(cams) <= batch queries; returns [(w2c, loss), ...].  A partial batch repeats its last query in the idle
+        branches (their results are discarded)."""
+        n = len(cams)
+        assert 1 <= n <= self.batch
+        td = list(target_depths) if target_depths is not None else [None] * n
+        gm = list(grad_masks) if grad_masks is not None else [None] * n
+        for i, r in enumerate(self.refiners):
+            j = min(i, n - 1)
+            r._pending = (cams[j], targets[j], iters, td[j], gm[j])
+            r._load_query(cams[j], targets[j], td[j], gm[j])
+            r._ensure_capacity()                # may grow this branch's binning buffer
+        if self.graph is None or self._captured_with != [(r.capacity, r.global_sort) for r in self.refiners]:
+            self._capture()
+            for i, r in enumerate(self.refiners):
+                j = min(i, n - 1)
+                r._load_query(cams[j], targets[j], td[j], gm[j])
+        for _ in range(iters):
+            self.graph.replay()
+        out = []
+        for i in range(n):
+            r = self.refiners[i]
+            r.graph = None                      # collect()'s eager fallback must not reuse a stale single-query graph
+            out.append(r.collect())
+        return out

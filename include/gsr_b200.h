@@ -108,8 +108,14 @@ GSR_API int gsr_rasterize_forward_async(
     const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
     const float* viewmatrix, const float* projmatrix, const float* cam_pos,
     float tan_fovx, float tan_fovy,
-    float* out_color, float* out_depth, float* out_alpha, int* radii, int* n_touched, void* stream);
+    float* out_color, float* out_depth, float* out_alpha, int* radii, int* n_touched,
+    const float* cull_records /* gsr_build_cull_records output for these means3D / scales / rotations, or NULL */, void* stream);
 GSR_API int gsr_read_counters(const char* geometry_buffer, int P, unsigned int* out3, void* stream);
+/* Static map, packed once at load (LoGS localizes every query of a scene against one read-only map loaded by
+ * scene/gaussian_model.py:215-256): records[P][4] = mean x, y, z and the static factor of the conservative screen-radius
+ * bound.  Passed as `cull_records` to gsr_rasterize_forward_async, the cull pass streams 16 bytes per Gaussian instead
+ * of 40 from three arrays; results are identical.  Rebuild after any change of means3D / scales / rotations. */
+GSR_API int gsr_build_cull_records(int P, const float* means3D, const float* scales, const float* rotations, float* records, void* stream);
 /* The overflow flag reported by gsr_read_counters is STICKY: it stays set until cleared, however many forwards ran on the
  * geometry buffer in between (a CUDA graph replays many forwards between two reads).  Clear it once after allocating the
  * buffer (its contents are otherwise undefined) and whenever a new query starts. */

@@ -216,3 +216,24 @@ def test_refined_pose_matches_oracle_loop_c2():
         assert dt <= 1e-3 and dr <= 0.01, (dt, dr)
     e0, e1 = syn.pose_error(start.w2c, gt.w2c), syn.pose_error(w2c_cuda.cpu(), gt.w2c)
     assert e1[0] < e0[0] and e1[1] < e0[1], (e0, e1)
+
+
+def test_batched_graph_refiner_matches_single_query_refiner():
+    """B queries per graph launch (parallel branches of one CUDA graph) give the poses of the one-query-at-a-time refiner."""
+    cfg = dict(P=20_000, W=160, H=128, deg=2, f=120.0, box=1.0, sigma0=0.06)
+    m = syn.make_map(cfg["P"], cfg["deg"], cfg["sigma0"], 1.0, seed=0).to(DEV)
+    qs = []
+    for q in (2, 5, 7):
+        gt = syn.make_camera(cfg, q)
+        target = loc.render_pose(m, loc.PoseCamera(gt, DEV), torch.zeros(3, device=DEV))[0].detach()
+        qs.append((gt, target, gt.perturbed(syn.initial_perturbation(q, trans_m=0.02, rot_deg=1.0))))
+    single = loc.GraphRefiner(m, loc.PoseCamera(qs[0][2], DEV), lr=1e-3)
+    want = [single.refine(loc.PoseCamera(start, DEV), tgt, iters=25) for _, tgt, start in qs]
+    batched = loc.BatchedGraphRefiner(m, loc.PoseCamera(qs[0][2], DEV), batch=4, lr=1e-3)
+    for rounds in range(2):                                  # second round re-uses the captured graph
+        got = batched.refine_batch([loc.PoseCamera(start, DEV) for _, _, start in qs], [tgt for _, tgt, _ in qs], iters=25)
+        assert len(got) == 3
+        for (w_b, l_b), (w_s, l_s) in zip(got, want):
+            dt, dr = syn.pose_error(w_b.cpu(), w_s.cpu())
+            assert dt <= 1e-5 and dr <= 1e-3, (rounds, dt, dr)
+            assert abs(float(l_b) - float(l_s)) <= 1e-5

@@ -400,10 +400,14 @@ def test_async_forward_long_lists_match_default_forward():
     c2, d2, a2 = torch.empty_like(color), torch.empty_like(depth), torch.empty_like(alpha)
     r2 = torch.empty_like(radii)
     p = lambda t: C.c_void_p(t.data_ptr())
-    for global_sort in (1, 0):       # 0: tile lists beyond the shared-memory limit fall to the in-place network, same result
+    # packed static map for the cull pass (gsr_build_cull_records): with and without, the results must be identical
+    rec = torch.empty(P, 4, device=DEV)
+    assert lib.gsr_build_cull_records(P, p(means3D), p(scales), p(rots), p(rec), C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+    for global_sort, records in ((1, None), (0, None), (1, rec)):   # 0: long buckets fall to the in-place network, same result
         rc = lib.gsr_rasterize_forward_async(p(g2), p(b2), cap, global_sort, p(i2), P, deg, int(sh.shape[1]), p(bgt), W, H, p(means3D), p(sh),
                                              None, p(opac), p(scales), 1.0, p(rots), None, p(view), p(proj), p(campos), tfx, tfy,
-                                             p(c2), p(d2), p(a2), p(r2), None, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                             p(c2), p(d2), p(a2), p(r2), None, None if records is None else p(records),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream))
         assert rc == 0, lib.gsr_last_error()
         torch.cuda.synchronize()
         cnt = (C.c_uint * 3)()
@@ -411,5 +415,5 @@ def test_async_forward_long_lists_match_default_forward():
         assert cnt[0] == R and cnt[2] > 4096
         st2 = ours.export_state(P, R, W, H, g2, b2, i2)
         for k in ("keys", "list", "ranges", "n_contrib"):
-            assert torch.equal(st[k], st2[k]), (global_sort, k)
+            assert torch.equal(st[k], st2[k]), (global_sort, records is not None, k)
         assert torch.equal(color, c2) and torch.equal(alpha, a2) and torch.equal(depth, d2) and torch.equal(radii, r2)

@@ -60,6 +60,23 @@ for name in sys.argv[1:] or ["C1", "C2", "headline", "C3"]:
         res[f"graph_x{nstreams}"] = {"queries_per_s": round(6 / dt, 2), "ms_per_iter": round(dt / 6 / iters * 1e3, 4),
                                      "median_err_m": round(sorted(e[0] for e in errs)[3], 5)}
         del refs
+    # B queries per graph launch (parallel branches of one graph)
+    for B in (4, 8):
+        cams_q = [loc.PoseCamera(gt.perturbed(syn.initial_perturbation(q, 0.02, 1.0)), dev) for q, (gt, _) in enumerate(qs)]
+        br = loc.BatchedGraphRefiner(m, cams_q[0], batch=B)
+        warm = [loc.PoseCamera(qs[0][0].perturbed(syn.initial_perturbation(0, 0.02, 1.0)), dev) for _ in range(B)]
+        br.refine_batch(warm, [qs[0][1]] * B, iters=iters)
+        nq = 2 * B
+        batch_cams = [loc.PoseCamera(qs[1 + i % 6][0].perturbed(syn.initial_perturbation(1 + i % 6, 0.02, 1.0)), dev) for i in range(nq)]
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for b0 in range(0, nq, B):
+            br.refine_batch(batch_cams[b0:b0 + B], [qs[1 + i % 6][1] for i in range(b0, b0 + B)], iters=iters)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        errs = [syn.pose_error(c.w2c.cpu(), qs[1 + i % 6][0].w2c) for i, c in enumerate(batch_cams)]
+        res[f"batched_graph_B{B}"] = {"queries_per_s": round(nq / dt, 2), "ms_per_query_iter": round(dt / nq / iters * 1e3, 4),
+                                      "median_err_m": round(sorted(e[0] for e in errs)[nq // 2], 5)}
+        del br
+        torch.cuda.empty_cache()
     print(json.dumps(res), flush=True)
     del m, gmap
     torch.cuda.empty_cache()
