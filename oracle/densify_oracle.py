@@ -1,9 +1,9 @@
 """TEST INFRASTRUCTURE ONLY — sequential torch restatement of the reference's densification
 (gaussian_splatting/scene/gaussian_model.py:258-402) on a plain dict of tensors + Adam state, step by step as the
 reference performs it: densify_and_clone (append) -> densification_postfix (statistics reset) -> densify_and_split
-(append two children per parent, prune the parents) -> opacity / size prune.  "parity unpinned": the reference's own
-GaussianModel cannot be imported here (it needs plyfile and a CUDA build of simple_knn at import time), so this file
-is pinned only by reading; the product's single-gather implementation is compared against it row for row."""
+(append two children per parent, prune the parents) -> opacity / size prune.  Pinned on tests/golden/ref_densify.npz,
+the output of the reference's own GaussianModel class (tests/golden/make_densify_golden.py runs it in the build
+container); the product's single-gather implementation is compared with both, row for row."""
 import torch
 
 
@@ -37,7 +37,7 @@ def _prune(S, mask):          # prune_points (:285-301)
     S["accum"], S["denom"], S["max_radii2D"] = S["accum"][valid], S["denom"][valid], S["max_radii2D"][valid]
 
 
-def densify_and_prune(S, max_grad, min_opacity, extent, max_screen_size, percent_dense):
+def densify_and_prune(S, max_grad, min_opacity, extent, max_screen_size, percent_dense, samples=None):
     """S = {"p": {name: tensor}, "m": {...}, "v": {...}, "accum": [N,1], "denom": [N,1], "max_radii2D": [N]} (CPU)."""
     grads = S["accum"] / S["denom"]
     grads[grads.isnan()] = 0.0
@@ -51,7 +51,8 @@ def densify_and_prune(S, max_grad, min_opacity, extent, max_screen_size, percent
     padded[:grads.shape[0]] = grads.squeeze()
     sel = (padded >= max_grad) & (torch.max(scaling(), dim=1).values > percent_dense * extent)
     stds = scaling()[sel].repeat(2, 1)
-    samples = torch.normal(mean=torch.zeros((stds.size(0), 3)), std=stds)
+    if samples is None:          # the goldens carry the reference's own draw (CPU and CUDA generators differ)
+        samples = torch.normal(mean=torch.zeros((stds.size(0), 3)), std=stds)
     rots = _rotmat(S["p"]["rotation"][sel]).repeat(2, 1, 1)
     new = {"xyz": torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1) + S["p"]["xyz"][sel].repeat(2, 1),
            "scaling": torch.log(scaling()[sel].repeat(2, 1) / (0.8 * 2)), "rotation": S["p"]["rotation"][sel].repeat(2, 1),
