@@ -36,70 +36,30 @@ __device__ __forceinline__ float3 dnormvdv(float3 v, float3 dv) {
   return o;
 }
 
-// SH backward (reference backward.cu:20-139).  Writes this Gaussian's dL_dsh row to `out`
-// (may be null) and returns dL_dmean through the view direction.  Processed in groups of four
-// coefficients (three 16-byte loads + three 16-byte stores) to keep register pressure low;
-// w is the basis value, wx/wy/wz its derivative w.r.t. the (normalised) direction components.
-__device__ __forceinline__ float3 sh_backward(int deg, float3 pos, float3 campos, const float* __restrict__ sh,
-                                              float3 dL_dRGB, float* out, bool vec4) {
+// SH backward (reference backward.cu:20-139).  Writes this Gaussian's dL_dsh row to `out` (may be null) and returns
+// dL_dmean through the view direction.  The coefficients themselves are not read: dL_dsh_k = basis_k * dL_dRGB needs
+// only the direction, and the direction gradient needs them only through the nine sums d(rgb)/d(dir) that the
+// forward's colour kernel left in the slot (`dcol`).  Rows are written in groups of four coefficients (three 16-byte
+// stores).
+__device__ __forceinline__ float3 sh_backward(int deg, float3 pos, float3 campos, const float (&dcol)[9], float3 dL_dRGB, float* out,
+                                              bool vec4) {
   const float3 dir_orig = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
   const float inv_len = 1.0f / sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
   const float x = dir_orig.x * inv_len, y = dir_orig.y * inv_len, z = dir_orig.z * inv_len;
-  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
   const int ncoef = (deg + 1) * (deg + 1);
   const int ngroups = (ncoef + 3) / 4;
-  float3 dRGBdx = {0, 0, 0}, dRGBdy = {0, 0, 0}, dRGBdz = {0, 0, 0};
+  if (out) {
 #pragma unroll
-  for (int g = 0; g < 4; g++) {
-    if (g < ngroups) {
-      float w[4], wx[4], wy[4], wz[4];
-      if (g == 0) {
-        w[0] = SH_C0;       wx[0] = 0.f;    wy[0] = 0.f;    wz[0] = 0.f;
-        w[1] = -SH_C1 * y;  wx[1] = 0.f;    wy[1] = -SH_C1; wz[1] = 0.f;
-        w[2] = SH_C1 * z;   wx[2] = 0.f;    wy[2] = 0.f;    wz[2] = SH_C1;
-        w[3] = -SH_C1 * x;  wx[3] = -SH_C1; wy[3] = 0.f;    wz[3] = 0.f;
-      } else if (g == 1) {
-        w[0] = SH_C2[0] * xy;                     wx[0] = SH_C2[0] * y;        wy[0] = SH_C2[0] * x;        wz[0] = 0.f;
-        w[1] = SH_C2[1] * yz;                     wx[1] = 0.f;                 wy[1] = SH_C2[1] * z;        wz[1] = SH_C2[1] * y;
-        w[2] = SH_C2[2] * (2.f * zz - xx - yy);   wx[2] = SH_C2[2] * -2.f * x; wy[2] = SH_C2[2] * -2.f * y; wz[2] = SH_C2[2] * 4.f * z;
-        w[3] = SH_C2[3] * xz;                     wx[3] = SH_C2[3] * z;        wy[3] = 0.f;                 wz[3] = SH_C2[3] * x;
-      } else if (g == 2) {
-        w[0] = SH_C2[4] * (xx - yy);              wx[0] = SH_C2[4] * 2.f * x;  wy[0] = SH_C2[4] * -2.f * y; wz[0] = 0.f;
-        w[1] = SH_C3[0] * y * (3.f * xx - yy);    wx[1] = SH_C3[0] * 6.f * xy; wy[1] = SH_C3[0] * 3.f * (xx - yy); wz[1] = 0.f;
-        w[2] = SH_C3[1] * xy * z;                 wx[2] = SH_C3[1] * yz;       wy[2] = SH_C3[1] * xz;       wz[2] = SH_C3[1] * xy;
-        w[3] = SH_C3[2] * y * (4.f * zz - xx - yy);
-        wx[3] = SH_C3[2] * -2.f * xy; wy[3] = SH_C3[2] * (-3.f * yy + 4.f * zz - xx); wz[3] = SH_C3[2] * 8.f * yz;
-      } else {
-        w[0] = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
-        wx[0] = SH_C3[3] * -6.f * xz; wy[0] = SH_C3[3] * -6.f * yz; wz[0] = SH_C3[3] * 3.f * (2.f * zz - xx - yy);
-        w[1] = SH_C3[4] * x * (4.f * zz - xx - yy);
-        wx[1] = SH_C3[4] * (-3.f * xx + 4.f * zz - yy); wy[1] = SH_C3[4] * -2.f * xy; wz[1] = SH_C3[4] * 8.f * xz;
-        w[2] = SH_C3[5] * z * (xx - yy);          wx[2] = SH_C3[5] * 2.f * xz; wy[2] = SH_C3[5] * -2.f * yz; wz[2] = SH_C3[5] * (xx - yy);
-        w[3] = SH_C3[6] * x * (xx - 3.f * yy);    wx[3] = SH_C3[6] * 3.f * (xx - yy); wy[3] = SH_C3[6] * -6.f * xy; wz[3] = 0.f;
-      }
-      float c[12];
-      if (vec4) {
-        const float4* s4 = reinterpret_cast<const float4*>(sh + 12 * g);
-        const float4 v0 = __ldg(s4), v1 = __ldg(s4 + 1), v2 = __ldg(s4 + 2);
-        c[0] = v0.x, c[1] = v0.y, c[2] = v0.z, c[3] = v0.w, c[4] = v1.x, c[5] = v1.y, c[6] = v1.z, c[7] = v1.w;
-        c[8] = v2.x, c[9] = v2.y, c[10] = v2.z, c[11] = v2.w;
-      } else {
+    for (int g = 0; g < 4; g++) {
+      if (g < ngroups) {
+        float w[4], wx[4], wy[4], wz[4];
+        sh_basis_group(g, x, y, z, w, wx, wy, wz);
+        float o[12];
 #pragma unroll
-        for (int q = 0; q < 12; q++) c[q] = (4 * g + q / 3 < ncoef) ? __ldg(sh + 12 * g + q) : 0.f;
-      }
-      float o[12];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const bool on = 4 * g + k < ncoef;
-        const float wk = on ? w[k] : 0.f;
-        o[3 * k] = wk * dL_dRGB.x, o[3 * k + 1] = wk * dL_dRGB.y, o[3 * k + 2] = wk * dL_dRGB.z;
-        if (on) {
-          dRGBdx.x += wx[k] * c[3 * k]; dRGBdx.y += wx[k] * c[3 * k + 1]; dRGBdx.z += wx[k] * c[3 * k + 2];
-          dRGBdy.x += wy[k] * c[3 * k]; dRGBdy.y += wy[k] * c[3 * k + 1]; dRGBdy.z += wy[k] * c[3 * k + 2];
-          dRGBdz.x += wz[k] * c[3 * k]; dRGBdz.y += wz[k] * c[3 * k + 1]; dRGBdz.z += wz[k] * c[3 * k + 2];
+        for (int k = 0; k < 4; k++) {
+          const float wk = 4 * g + k < ncoef ? w[k] : 0.f;
+          o[3 * k] = wk * dL_dRGB.x, o[3 * k + 1] = wk * dL_dRGB.y, o[3 * k + 2] = wk * dL_dRGB.z;
         }
-      }
-      if (out) {
         if (vec4) {
           float4* o4 = reinterpret_cast<float4*>(out + 12 * g);
           o4[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -113,9 +73,9 @@ __device__ __forceinline__ float3 sh_backward(int deg, float3 pos, float3 campos
       }
     }
   }
-  const float3 dL_ddir = {dRGBdx.x * dL_dRGB.x + dRGBdx.y * dL_dRGB.y + dRGBdx.z * dL_dRGB.z,
-                          dRGBdy.x * dL_dRGB.x + dRGBdy.y * dL_dRGB.y + dRGBdy.z * dL_dRGB.z,
-                          dRGBdz.x * dL_dRGB.x + dRGBdz.y * dL_dRGB.y + dRGBdz.z * dL_dRGB.z};
+  const float3 dL_ddir = {dcol[0] * dL_dRGB.x + dcol[1] * dL_dRGB.y + dcol[2] * dL_dRGB.z,
+                          dcol[3] * dL_dRGB.x + dcol[4] * dL_dRGB.y + dcol[5] * dL_dRGB.z,
+                          dcol[6] * dL_dRGB.x + dcol[7] * dL_dRGB.y + dcol[8] * dL_dRGB.z};
   return dnormvdv(dir_orig, dL_ddir);
 }
 
@@ -172,11 +132,12 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
     g_color = make_float3(a1.z, a1.w, a2.x);
     const float g_depth = a2.y;
 
-    // everything this Gaussian needs from the map is requested here, in one round trip: the SH row (two or more
-    // cache lines) as L1 prefetches, the rest into registers
+    // everything this Gaussian needs is in its slot (the forward left mean / scale / rotation and the SH direction
+    // derivatives there): coalesced loads, one round trip; the map itself is not read
+    float dcol[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (p.shs) {
-      const char* sh_row = reinterpret_cast<const char*>(p.shs + idx * row);
-      for (int b = 0; b < row * 4; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(sh_row + b));
+      const float4 d0 = __ldg(p.geom.shd + 3 * (size_t)k), d1 = __ldg(p.geom.shd + 3 * (size_t)k + 1), d2 = __ldg(p.geom.shd + 3 * (size_t)k + 2);
+      dcol[0] = d0.x, dcol[1] = d0.y, dcol[2] = d0.z, dcol[3] = d0.w, dcol[4] = d1.x, dcol[5] = d1.y, dcol[6] = d1.z, dcol[7] = d1.w, dcol[8] = d2.x;
     }
     // mean, scale and rotation were left in the slot by the forward: three coalesced 16-byte loads, no second gather by id
     const float4 m0 = __ldg(p.geom.msr + 3 * (size_t)k), m1 = __ldg(p.geom.msr + 3 * (size_t)k + 1), m2 = __ldg(p.geom.msr + 3 * (size_t)k + 2);
@@ -268,8 +229,8 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
       const float3 dL_dRGB = {(cm & 1) ? 0.f : g_color.x, (cm & 2) ? 0.f : g_color.y, (cm & 4) ? 0.f : g_color.z};
       const float3 cp = {s_cam[48], s_cam[49], s_cam[50]};
       // rows of the SH gradient were zero-filled; coefficients above the active degree stay zero
-      const bool vec4 = (M % 4 == 0) && (((uintptr_t)p.shs | (uintptr_t)p.dL_dsh) % 16 == 0);
-      g_sh_mean = sh_backward(p.D, mean, cp, p.shs + idx * row, dL_dRGB, p.dL_dsh ? p.dL_dsh + idx * row : nullptr, vec4);
+      const bool vec4 = (M % 4 == 0) && ((uintptr_t)p.dL_dsh % 16 == 0);
+      g_sh_mean = sh_backward(p.D, mean, cp, dcol, dL_dRGB, p.dL_dsh ? p.dL_dsh + idx * row : nullptr, vec4);
       g_mean.x += g_sh_mean.x; g_mean.y += g_sh_mean.y; g_mean.z += g_sh_mean.z;
     }
 

@@ -35,6 +35,8 @@ struct GeometryView {           // replaces GeometryState (reference rasterizer_
   float4* rgbd;                 // [slots] (r, g, b, depth): one 16-byte gather for the blend kernels
   float4* msr;                  // [3 slots] (mean xyz, scale x) (scale y z, rot w x) (rot y z, -, -): what the preprocess backward needs
                                 //           of the map, kept per visible slot so that it does not gather it by Gaussian id again
+  float4* shd;                  // [3 slots] d(rgb before clamping)/d(unit view direction): (dr/dx dg/dx db/dx dr/dy) (dg/dy db/dy dr/dz dg/dz) (db/dz - - -),
+                                //           left by the forward's colour kernel so that the backward never reads the SH rows again
   float* cov3D;                 // [6 slots]
   uint2* rect;                  // [slots] tile rectangle: x = minx | maxx<<16, y = miny | maxy<<16
   uint8_t* clamped;             // [slots] bit c set <=> channel c was clamped at 0
@@ -124,6 +126,7 @@ inline char* carve_geometry(char* base, int P, GeometryView& g) {
   carve(p, g.conic_opacity, S);
   carve(p, g.rgbd, S);
   carve(p, g.msr, 3 * S);
+  carve(p, g.shd, 3 * S);
   carve(p, g.cov3D, 6 * S);
   carve(p, g.rect, S);
   carve(p, g.clamped, S);
@@ -185,6 +188,36 @@ __device__ __forceinline__ float splat_two_tau(float a, float b, float c, float 
   if (!(o255 >= 1.0f)) return -1.0f;
   if (!(a * c - b * b > 0.f) || !(a > 0.f) || !(c > 0.f)) return __int_as_float(0x7f800000);
   return 2.0f * __logf(o255) * 1.001f + 1e-3f;
+}
+
+// Real SH basis of group g (coefficients 4g .. 4g+3) at the unit direction (x, y, z): values w and their derivatives
+// wx, wy, wz with respect to the direction components (reference forward.cu:20-71, backward.cu:20-139).
+__device__ __forceinline__ void sh_basis_group(int g, float x, float y, float z, float (&w)[4], float (&wx)[4], float (&wy)[4], float (&wz)[4]) {
+  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+  if (g == 0) {
+    w[0] = SH_C0;       wx[0] = 0.f;    wy[0] = 0.f;    wz[0] = 0.f;
+    w[1] = -SH_C1 * y;  wx[1] = 0.f;    wy[1] = -SH_C1; wz[1] = 0.f;
+    w[2] = SH_C1 * z;   wx[2] = 0.f;    wy[2] = 0.f;    wz[2] = SH_C1;
+    w[3] = -SH_C1 * x;  wx[3] = -SH_C1; wy[3] = 0.f;    wz[3] = 0.f;
+  } else if (g == 1) {
+    w[0] = SH_C2[0] * xy;                     wx[0] = SH_C2[0] * y;        wy[0] = SH_C2[0] * x;        wz[0] = 0.f;
+    w[1] = SH_C2[1] * yz;                     wx[1] = 0.f;                 wy[1] = SH_C2[1] * z;        wz[1] = SH_C2[1] * y;
+    w[2] = SH_C2[2] * (2.f * zz - xx - yy);   wx[2] = SH_C2[2] * -2.f * x; wy[2] = SH_C2[2] * -2.f * y; wz[2] = SH_C2[2] * 4.f * z;
+    w[3] = SH_C2[3] * xz;                     wx[3] = SH_C2[3] * z;        wy[3] = 0.f;                 wz[3] = SH_C2[3] * x;
+  } else if (g == 2) {
+    w[0] = SH_C2[4] * (xx - yy);              wx[0] = SH_C2[4] * 2.f * x;  wy[0] = SH_C2[4] * -2.f * y; wz[0] = 0.f;
+    w[1] = SH_C3[0] * y * (3.f * xx - yy);    wx[1] = SH_C3[0] * 6.f * xy; wy[1] = SH_C3[0] * 3.f * (xx - yy); wz[1] = 0.f;
+    w[2] = SH_C3[1] * xy * z;                 wx[2] = SH_C3[1] * yz;       wy[2] = SH_C3[1] * xz;       wz[2] = SH_C3[1] * xy;
+    w[3] = SH_C3[2] * y * (4.f * zz - xx - yy);
+    wx[3] = SH_C3[2] * -2.f * xy; wy[3] = SH_C3[2] * (-3.f * yy + 4.f * zz - xx); wz[3] = SH_C3[2] * 8.f * yz;
+  } else {
+    w[0] = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+    wx[0] = SH_C3[3] * -6.f * xz; wy[0] = SH_C3[3] * -6.f * yz; wz[0] = SH_C3[3] * 3.f * (2.f * zz - xx - yy);
+    w[1] = SH_C3[4] * x * (4.f * zz - xx - yy);
+    wx[1] = SH_C3[4] * (-3.f * xx + 4.f * zz - yy); wy[1] = SH_C3[4] * -2.f * xy; wz[1] = SH_C3[4] * 8.f * xz;
+    w[2] = SH_C3[5] * z * (xx - yy);          wx[2] = SH_C3[5] * 2.f * xz; wy[2] = SH_C3[5] * -2.f * yz; wz[2] = SH_C3[5] * (xx - yy);
+    w[3] = SH_C3[6] * x * (xx - 3.f * yy);    wx[3] = SH_C3[6] * 3.f * (xx - yy); wy[3] = SH_C3[6] * -6.f * xy; wz[3] = 0.f;
+  }
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }

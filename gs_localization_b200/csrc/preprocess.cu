@@ -87,26 +87,24 @@ __device__ __forceinline__ float3 compute_cov2D(float tx, float ty, float tz, fl
 }
 
 // reference forward.cu:20-71.  `sh` points at this Gaussian's M*3 coefficients.  Evaluated in
-// groups of four coefficients (= three 16-byte loads) to keep register pressure low.
+// groups of four coefficients (= three 16-byte loads) to keep register pressure low.  Also returns
+// d(rgb before clamping)/d(unit view direction) (dcol[0..2] = d/dx of r, g, b; [3..5] d/dy; [6..8] d/dz): the SH part of
+// the backward (reference backward.cu:20-139) needs the coefficients only through these nine sums.
 template <bool VEC4>
 __device__ __forceinline__ float3 color_from_sh(int deg, float3 pos, float3 campos, const float* __restrict__ sh,
-                                                uint8_t& clamp_mask) {
+                                                uint8_t& clamp_mask, float (&dcol)[9]) {
   float3 dir = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
   const float len = sqrtf(__fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.x, dir.x, dir.y * dir.y)));
   const float x = dir.x / len, y = dir.y / len, z = dir.z / len;
-  const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
   float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 9; i++) dcol[i] = 0.f;
   const int ngroups = deg == 0 ? 1 : deg == 1 ? 1 : deg == 2 ? 3 : 4;   // groups of 4 coefficients
 #pragma unroll
   for (int g = 0; g < 4; g++) {
     if (g < ngroups) {
-      float w[4];
-      if (g == 0) { w[0] = SH_C0; w[1] = -SH_C1 * y; w[2] = SH_C1 * z; w[3] = -SH_C1 * x; }
-      else if (g == 1) { w[0] = SH_C2[0] * xy; w[1] = SH_C2[1] * yz; w[2] = SH_C2[2] * (2.0f * zz - xx - yy); w[3] = SH_C2[3] * xz; }
-      else if (g == 2) { w[0] = SH_C2[4] * (xx - yy); w[1] = SH_C3[0] * y * (3.0f * xx - yy); w[2] = SH_C3[1] * xy * z;
-                         w[3] = SH_C3[2] * y * (4.0f * zz - xx - yy); }
-      else { w[0] = SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy); w[1] = SH_C3[4] * x * (4.0f * zz - xx - yy);
-             w[2] = SH_C3[5] * z * (xx - yy); w[3] = SH_C3[6] * x * (xx - 3.0f * yy); }
+      float w[4], wx[4], wy[4], wz[4];
+      sh_basis_group(g, x, y, z, w, wx, wy, wz);
       // number of valid coefficients in this group for the active degree
       const int ncoef = (deg + 1) * (deg + 1);
       float c[12];
@@ -125,6 +123,9 @@ __device__ __forceinline__ float3 color_from_sh(int deg, float3 pos, float3 camp
           r0 += w[k] * c[3 * k];
           r1 += w[k] * c[3 * k + 1];
           r2 += w[k] * c[3 * k + 2];
+          dcol[0] += wx[k] * c[3 * k]; dcol[1] += wx[k] * c[3 * k + 1]; dcol[2] += wx[k] * c[3 * k + 2];
+          dcol[3] += wy[k] * c[3 * k]; dcol[4] += wy[k] * c[3 * k + 1]; dcol[5] += wy[k] * c[3 * k + 2];
+          dcol[6] += wz[k] * c[3 * k]; dcol[7] += wz[k] * c[3 * k + 1]; dcol[8] += wz[k] * c[3 * k + 2];
         }
       }
     }
@@ -393,13 +394,17 @@ __global__ void __launch_bounds__(COLOR_THREADS) color_fwd_kernel(const Preproce
     const size_t g = __ldg(p.geom.gid + k);
     float3 rgb;
     uint8_t cm = 0;
+    float dcol[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (p.colors_precomp) {
       rgb = make_float3(__ldg(p.colors_precomp + 3 * g), __ldg(p.colors_precomp + 3 * g + 1), __ldg(p.colors_precomp + 3 * g + 2));
     } else {
       const float3 pos = {__ldg(p.means3D + 3 * g), __ldg(p.means3D + 3 * g + 1), __ldg(p.means3D + 3 * g + 2)};
       const float* sh = p.shs + g * p.M * 3;
-      if (p.sh_vec4) rgb = color_from_sh<true>(p.D, pos, cp, sh, cm);
-      else rgb = color_from_sh<false>(p.D, pos, cp, sh, cm);
+      if (p.sh_vec4) rgb = color_from_sh<true>(p.D, pos, cp, sh, cm, dcol);
+      else rgb = color_from_sh<false>(p.D, pos, cp, sh, cm, dcol);
+      p.geom.shd[3 * (size_t)k] = make_float4(dcol[0], dcol[1], dcol[2], dcol[3]);
+      p.geom.shd[3 * (size_t)k + 1] = make_float4(dcol[4], dcol[5], dcol[6], dcol[7]);
+      p.geom.shd[3 * (size_t)k + 2] = make_float4(dcol[8], 0.f, 0.f, 0.f);
     }
     p.geom.rgbd[k] = make_float4(rgb.x, rgb.y, rgb.z, p.geom.depths[k]);
     p.geom.clamped[k] = cm;
