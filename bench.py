@@ -462,7 +462,7 @@ def run_train_dp(args, rank, world, device):
     bg = torch.zeros(3, device=device)
     out = {"workload": f"C4: {cfg['P']} Gaussians, {cfg['W']}x{cfg['H']}, SH degree {cfg['deg']}, one view per rank and step, all parameter "
                        "groups trained, densification statistics exchanged", "scaling": "weak", "n_gpus": world}
-    for mode in ("dense", "sparse"):
+    for mode in ("dense", "sparse", "auto"):
         model = gm.GaussianModel(cfg["deg"], device=device)
         model.from_raw(raw)
         model.spatial_lr_scale = 1.0
@@ -511,10 +511,11 @@ def run_train_dp(args, rank, world, device):
         err = max(float((a - b).norm() / (b.norm() + 1e-30)) for a, b in zip(g, ref))
         step_s, ex_s = float(t[0]), float(t[1])
         nbytes = trainer.exchange_bytes
-        bus = (2.0 * (world - 1) / world * nbytes if mode == "dense" else (world - 1) / world * nbytes) / max(ex_s, 1e-9) / 1e9 if world > 1 else None
+        used = trainer.last_choice
+        bus = (2.0 * (world - 1) / world * nbytes if used == "dense" else (world - 1) / world * nbytes) / max(ex_s, 1e-9) / 1e9 if world > 1 else None
         out[mode] = {"views_per_s": round(world / step_s, 1), "step_ms": round(step_s * 1e3, 3), "exchange_ms": round(ex_s * 1e3, 3),
                      "exchange_MB": round(nbytes / 1e6, 1), "bus_GBs": None if bus is None else round(bus, 1),
-                     "grad_sum_rel_err": err}
+                     "grad_sum_rel_err": err, "exchange_used_last_step": used}
         del model, trainer
         torch.cuda.empty_cache()
     return out if rank == 0 else None

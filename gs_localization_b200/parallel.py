@@ -285,6 +285,13 @@ class VisibleRowExchange:
             self._ready = torch.cuda.Event()
             self._ready.record(self._side)
 
+    def max_rows(self, radii: torch.Tensor) -> int:
+        """Largest visible-row count of this step over the ranks (waits for begin()'s copy, which has long landed)."""
+        if self._ready is None:
+            self.begin(radii)                       # caller did not overlap the count exchange: do it now
+        self._ready.synchronize()
+        return int(self._pinned[0])
+
     def exchange(self, grads: Sequence[torch.Tensor], radii: torch.Tensor, dL_dmeans2D: torch.Tensor | None = None, stats=None):
         """grads: (xyz [P,3], features [P,M,3], opacity [P,1], scaling [P,3], rotation [P,4]) dense fp32, summed over ranks in
         place.  stats = (max_radii2D [P], xyz_gradient_accum [P,1], denom [P,1]) are updated with every rank's view."""
@@ -293,12 +300,10 @@ class VisibleRowExchange:
         from . import _lib
         lib = _lib.load()
         rank, ws = world()
-        if self._ready is None:
-            self.begin(radii)                       # caller did not overlap the count exchange: do it now
-        self._ready.synchronize()
+        rows = self.max_rows(radii)
         self._ready = None
         g_ = self.granularity
-        cap = max(1, min(self.P, (int(self._pinned[0]) + g_ - 1) // g_ * g_))
+        cap = max(1, min(self.P, (rows + g_ - 1) // g_ * g_))
         W, dev = self.W, self.dev
         stream = torch.cuda.current_stream(dev).cuda_stream
         tab = (C.c_void_p * 5)(*[g.data_ptr() for g in grads])
@@ -334,11 +339,19 @@ class DataParallelTrainer:
     the replicas stay identical (same torch.manual_seed on every rank for the split samples).  The all-reduce of step t
     cannot overlap the forward of step t+1: that forward reads the parameters the optimiser step of t writes."""
 
-    def __init__(self, model, opt, mode: str = "sparse", extent: float = 1.0):
-        assert mode in ("dense", "sparse")
+    # An all-reduce moves 2 (N-1)/N x the arena whatever the views see, and on NVSwitch it is reduced inside the switch
+    # (measured 8 x B200: 744 MB in 2.6 ms, 507 GB/s bus); the visible-row all-gather moves (N-1) x the LARGEST view's table
+    # into every GPU at about 0.4 of that rate (182 GB/s bus).  "auto" compares the two per step, with the row count that
+    # is known before the exchange starts: sparse wins while N x visible fraction is small (2 GPUs at C4: 1.0 ms vs 2.2 ms),
+    # dense once the views of a step cover most of the map (8 GPUs at C4: 2.6 ms vs 5.6 ms).
+    ALLGATHER_RATE_VS_ALLREDUCE = 0.4
+
+    def __init__(self, model, opt, mode: str = "auto", extent: float = 1.0):
+        assert mode in ("dense", "sparse", "auto")
         self.model, self.opt, self.mode, self.extent = model, opt, mode, float(extent)
         self.exchange = None
         self.exchange_bytes = 0
+        self.last_choice = None
 
     def _sparse(self):
         m = self.model
@@ -354,11 +367,21 @@ class DataParallelTrainer:
         m = self.model
         rank, ws = world()
         stats = (m.max_radii2D, m.xyz_gradient_accum, m.denom) if want_stats else None
-        if self.mode == "sparse":
+        mode = self.mode
+        if mode == "auto":
+            ex = self._sparse()
+            rows = ex.max_rows(radii)                  # exact, already on the host (exchanged under the backward)
+            sparse_bytes = (ws - 1) * rows * ex.W * 4
+            dense_bytes = 2.0 * (ws - 1) / max(ws, 1) * sum(t.numel() for t in g) * 4
+            mode = "sparse" if ws == 1 or sparse_bytes < dense_bytes * self.ALLGATHER_RATE_VS_ALLREDUCE else "dense"
+        self.last_choice = mode
+        if mode == "sparse":
             ex = self._sparse()
             ex.exchange(list(g), radii, dL_dmeans2D, stats)
             self.exchange_bytes = ex.last_bytes
         else:
+            if self.exchange is not None:
+                self.exchange._ready = None            # the row count of this step was not consumed by an exchange
             self.exchange_bytes = allreduce_gradients(g)
             if want_stats:
                 # no boolean indexing (it would make the host wait for the visible count): masked dense increments
@@ -375,7 +398,7 @@ class DataParallelTrainer:
 
     def after_forward(self, radii):
         """Hook for GaussianModel.compute_gradients: the sparse exchange starts its row-count collective under the backward."""
-        if self.mode == "sparse":
+        if self.mode in ("sparse", "auto"):
             self._sparse().begin(radii)
 
     def step(self, cam, gt_image, bg, iteration: int, pseudo_depth=None, gt_depth=None):

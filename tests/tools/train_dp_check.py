@@ -24,7 +24,7 @@ gen = torch.Generator().manual_seed(0)
 gts = [torch.rand(3, cfg["H"], cfg["W"], generator=gen).to(dev) for _ in range(8)]
 bg = torch.zeros(3, device=dev)
 ok_all = True
-for mode in ("sparse", "dense"):
+for mode in ("sparse", "dense", "auto"):
     raw = gio.deactivate(syn.make_map(cfg["P"], cfg["deg"], cfg["sigma0"], cfg["box"], seed=0))
     model = gm.GaussianModel(cfg["deg"], device=dev)
     model.from_raw(raw)
