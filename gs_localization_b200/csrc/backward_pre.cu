@@ -81,6 +81,8 @@ __device__ __forceinline__ float3 sh_backward(int deg, float3 pos, float3 campos
 
 __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwdParams p) {
   __shared__ float s_tau[BW_THREADS / 32][6];
+  pdl_trigger();
+  pdl_wait();
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t seg = blockIdx.x * (BW_THREADS / 32) + warp;
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
 
 void launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream) {
   if (p.P <= 0) return;
-  preprocess_bwd_kernel<<<(num_pre_blocks(p.P) + BW_THREADS / 32 - 1) / (BW_THREADS / 32), BW_THREADS, 0, stream>>>(p);
+  launch_pdl(preprocess_bwd_kernel, dim3((num_pre_blocks(p.P) + BW_THREADS / 32 - 1) / (BW_THREADS / 32)), dim3(BW_THREADS), 0, stream, p);
   count_launch();
 }
 

@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(ST_THREADS) scan_tiles_kernel(int* __restrict_
                                                                 uint32_t* __restrict__ counters, uint32_t capacity) {
   __shared__ int s_grid[IN_SMEM ? ST_SMEM_CELLS : 1];
   __shared__ uint32_t s_part[ST_THREADS];
+  pdl_trigger();
+  pdl_wait();
   __shared__ uint32_t s_max[32];
   __shared__ uint32_t s_bucket[ST_BUCKETS];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -206,9 +208,9 @@ __global__ void __launch_bounds__(ST_THREADS) scan_tiles_kernel(int* __restrict_
 void launch_scan_tiles(int* tile_diff, uint32_t gx, uint32_t gy, uint2* ranges, uint32_t* cursor, uint32_t* tile_order,
                        uint32_t* counters, uint32_t capacity, cudaStream_t stream) {
   if ((gx + 1) * (gy + 1) <= ST_SMEM_CELLS)
-    scan_tiles_kernel<true><<<1, ST_THREADS, 0, stream>>>(tile_diff, gx, gy, ranges, cursor, tile_order, counters, capacity);
+    launch_pdl(scan_tiles_kernel<true>, dim3(1), dim3(ST_THREADS), 0, stream, tile_diff, gx, gy, ranges, cursor, tile_order, counters, capacity);
   else
-    scan_tiles_kernel<false><<<1, ST_THREADS, 0, stream>>>(tile_diff, gx, gy, ranges, cursor, tile_order, counters, capacity);
+    launch_pdl(scan_tiles_kernel<false>, dim3(1), dim3(ST_THREADS), 0, stream, tile_diff, gx, gy, ranges, cursor, tile_order, counters, capacity);
   count_launch();
 }
 
@@ -239,6 +241,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint32_t* __restrict
   __shared__ uint2 s_rect[256];
   __shared__ uint32_t s_depth[256];
   __shared__ uint32_t s_wsum[8];
+  pdl_trigger();
+  pdl_wait();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (header) *header = hv;
     unit_count[0] = 0;   // the forward blend appends the backward's work units ...
@@ -316,8 +320,8 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(const uint32_t* __res
 void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* comp, uint32_t grid_x, BinHeader hv,
                     BinHeader* header, cudaStream_t stream) {
   if (P <= 0) return;
-  scatter_kernel<<<num_pre_blocks(P), 256, 0, stream>>>(g.block_vis, g.rect, g.depths, cursor, comp, g.grad_acc, grid_x, hv, header,
-                                                       g.counters + 5);
+  launch_pdl(scatter_kernel, dim3(num_pre_blocks(P)), dim3(256), 0, stream, (const uint32_t*)g.block_vis, (const uint2*)g.rect,
+             (const float*)g.depths, cursor, comp, g.grad_acc, grid_x, hv, header, g.counters + 5);
   count_launch();
 }
 
@@ -448,6 +452,8 @@ __global__ void __launch_bounds__(TS_THREADS) tile_sort_kernel(const uint2* __re
                                                                uint32_t* __restrict__ point_list, uint32_t capacity,
                                                                const uint32_t* __restrict__ tile_order) {
   __shared__ uint64_t s_keys[TS_SMEM_KEYS];
+  pdl_trigger();
+  pdl_wait();
   // longest lists first (the blend kernels' launch order): a 4096-key network takes many times longer than the median
   // tile's, and started late it finishes the kernel alone
   const uint2 rg = ranges[tile_order ? tile_order[blockIdx.x] : blockIdx.x];
@@ -478,7 +484,7 @@ __global__ void __launch_bounds__(TS_THREADS) tile_sort_kernel(const uint2* __re
 void launch_tile_sort(int num_tiles, const uint2* ranges, uint64_t* comp, uint32_t* point_list, uint32_t capacity,
                       const uint32_t* tile_order, cudaStream_t stream) {
   if (num_tiles <= 0) return;
-  tile_sort_kernel<<<num_tiles, TS_THREADS, 0, stream>>>(ranges, comp, point_list, capacity, tile_order);
+  launch_pdl(tile_sort_kernel, dim3(num_tiles), dim3(TS_THREADS), 0, stream, ranges, comp, point_list, capacity, tile_order);
   count_launch();
 }
 

@@ -9,6 +9,47 @@ namespace gsr {
 extern std::atomic<unsigned long long> g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
+// ---- programmatic dependent launch (griddepcontrol): a kernel launched through launch_pdl may be scheduled while its
+// predecessor in the stream is still draining; it must call pdl_wait() before it touches anything the predecessor
+// wrote (or anything the predecessor still reads), after which the predecessor has completed and its writes are visible.
+// pdl_trigger() at the top lets the NEXT kernel's CTAs be scheduled as soon as this grid's last CTAs are resident.
+// -DGSR_AB_NO_PDL builds the plain <<<>>> launches for measurements.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() {
+#ifndef GSR_AB_NO_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_trigger() {
+#ifndef GSR_AB_NO_PDL
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+#ifdef GSR_AB_NO_PDL
+  kernel<<<grid, block, smem, stream>>>(args...);
+#else
+  // Inside a CUDA-graph capture the programmatic edges measured SLOWER than plain ones (headline pose iteration 0.451 vs
+  // 0.384 ms, profiles/r2_pdl_ab.txt): graph launches already have no per-kernel launch latency to hide, and early-scheduled
+  // dependents only take SM resources from the running kernel.  Eager launches gain 5.8 % per fwd+bwd.
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &capturing);
+  if (capturing != cudaStreamCaptureStatusNone) {
+    kernel<<<grid, block, smem, stream>>>(args...);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
+#endif
+}
+#endif
+
 struct PreprocessParams {
   int P, D, M, W, H;
   uint32_t grid_x, grid_y;

@@ -165,6 +165,8 @@ void launch_build_cull_records(int P, const float* means3D, const float* scales,
 __global__ void __launch_bounds__(PRE_THREADS) preprocess_cull_kernel(const PreprocessParams p) {
   __shared__ uint32_t s_warp_near[PRE_THREADS / 32];
   __shared__ float s_cam[16 + 16];
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
   const uint32_t block = blockIdx.x;
@@ -268,6 +270,8 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_cull_kernel(const Prep
 constexpr int PRE2_WARPS = 8;
 __global__ void __launch_bounds__(PRE2_WARPS * 32) preprocess_fwd_kernel(const PreprocessParams p) {
   __shared__ float s_cam[16 + 16];
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
   if (tid < 16) s_cam[tid] = p.viewmatrix[tid];
@@ -376,8 +380,8 @@ __global__ void __launch_bounds__(PRE2_WARPS * 32) preprocess_fwd_kernel(const P
 
 void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream) {
   const int nb = num_pre_blocks(p.P);
-  preprocess_cull_kernel<<<nb, PRE_THREADS, 0, stream>>>(p);
-  preprocess_fwd_kernel<<<(nb + PRE2_WARPS - 1) / PRE2_WARPS, PRE2_WARPS * 32, 0, stream>>>(p);
+  launch_pdl(preprocess_cull_kernel, dim3(nb), dim3(PRE_THREADS), 0, stream, p);
+  launch_pdl(preprocess_fwd_kernel, dim3((nb + PRE2_WARPS - 1) / PRE2_WARPS), dim3(PRE2_WARPS * 32), 0, stream, p);
   count_launch(2);
 }
 
