@@ -594,7 +594,7 @@ def make_roofline(split, ws, cfg, ms_per_step):
         "radix_sort": 8 * R + 4 * R,                               # tile-local sort: read the composites once, write the sorted slots
         "render": 52 * R + 24 * N + 48 * R + 20 * N,               # gather (4 + 48 B) per instance, images, + the record stream and the checkpoints it leaves for the backward (>= 1 per 64 entries blended)
         "render_backward": 48 * R + 28 * N + 36 * Pv,              # record stream back in, per-pixel reads, accumulator rows
-        "preprocess_backward": 4 * P + (107 + 12 * M) * Pv + (64 + 12 * M) * Pv,
+        "preprocess_backward": 189 * Pv + (156 + 12 * M) * Pv,   # slot records in (no map rows are read), accumulator re-zero + gradient rows out
     }
     peak, how, sm_mhz = measured_peaks()
     prof, prof_note = load_profile()
