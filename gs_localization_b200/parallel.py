@@ -382,12 +382,17 @@ class DataParallelTrainer:
         else:
             if self.exchange is not None:
                 self.exchange._ready = None            # the row count of this step was not consumed by an exchange
-            self.exchange_bytes = allreduce_gradients(g)
+            inc = rad = None
             if want_stats:
-                # no boolean indexing (it would make the host wait for the visible count): masked dense increments
+                # The per-view increments are taken BEFORE the all-reduce: dL_dmeans2D lives in the same arena as the
+                # parameter gradients and is summed over ranks with them, and the statistic is the sum over views of the
+                # per-view norms (gaussian_model.py:405-407), not the norm of the summed gradient.
+                # No boolean indexing (it would make the host wait for the visible count): masked dense increments.
                 vis = (radii > 0).to(torch.float32)
                 inc = torch.stack([torch.linalg.vector_norm(dL_dmeans2D[:, :2], dim=-1) * vis, vis], dim=1)
                 rad = radii.clamp_min(0).to(torch.float32)
+            self.exchange_bytes = allreduce_gradients(g)
+            if want_stats:
                 if ws > 1:
                     _all_reduce(inc)
                     _all_reduce(rad, dist.ReduceOp.MAX)

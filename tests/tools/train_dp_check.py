@@ -24,6 +24,7 @@ gen = torch.Generator().manual_seed(0)
 gts = [torch.rand(3, cfg["H"], cfg["W"], generator=gen).to(dev) for _ in range(8)]
 bg = torch.zeros(3, device=dev)
 ok_all = True
+events_by_mode = {}
 for mode in ("sparse", "dense", "auto"):
     raw = gio.deactivate(syn.make_map(cfg["P"], cfg["deg"], cfg["sigma0"], cfg["box"], seed=0))
     model = gm.GaussianModel(cfg["deg"], device=dev)
@@ -67,8 +68,16 @@ for mode in ("sparse", "dense", "auto"):
                 print(json.dumps({"mode": mode, "iteration": it, "error": "replicas differ", "lo": lo.tolist()[:3], "hi": hi.tolist()[:3]}))
             break
     ok = worst_sum < 1e-4 and len(events) >= 2 and len(set(sizes)) > 1
+    events_by_mode[mode] = events
     ok_all &= ok
     if rank == 0:
         print(json.dumps({"mode": mode, "world": world, "grad_sum_rel_err": worst_sum, "densify_events": events, "final_P": sizes[-1], "ok": ok}))
+# the exchange mode must not change what is densified: same statistics (sum over views of per-view norms) in every mode.
+# The first event is decided by identical inputs; later ones may differ by a few rows (float addition order of the exchange).
+same_first = len({tuple(ev[0]) for ev in events_by_mode.values()}) == 1
+if rank == 0:
+    print(json.dumps({"check": "first densification identical across exchange modes", "ok": same_first,
+                      "first_events": {k: v[0] for k, v in events_by_mode.items()}}))
+ok_all &= same_first
 dist.destroy_process_group()
 sys.exit(0 if ok_all else 1)
