@@ -328,66 +328,68 @@ void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* co
 // ------------------------------------------------------------------ tile-local sort (kernel)
 constexpr int TS_THREADS = 256;
 constexpr uint32_t TS_SMEM_KEYS = 4096;   // 32 KB of composite keys in shared memory
+constexpr int TS_RUN_SCAN = 16;           // longest run of equal quantised depths that is ranked in place
 
-__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int mask) {
+__device__ __forceinline__ uint64_t shfl_xor_key(uint64_t v, int mask) {
   const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, mask);
   const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), mask);
   return ((uint64_t)hi << 32) | lo;
 }
+__device__ __forceinline__ uint32_t shfl_xor_key(uint32_t v, int mask) { return __shfl_xor_sync(0xffffffffu, v, mask); }
 
 // Register-resident bitonic sort of N2 = 256*E keys held E per thread (thread t owns indices [tE, tE+E)).
 // Same network as bitonic_sort_block (mirror step, then half-cleaners, always ascending), but a
 // compare-exchange whose partner lives in the same thread is a register swap, one whose partner lives in
-// the same warp is two shuffles, and only the few steps that cross warps go through shared memory.
+// the same warp is a shuffle, and only the few steps that cross warps go through shared memory.
 // For N2 = 1024 that is 6 shared-memory steps out of 55.  Padding is real +inf keys in registers.
 // The k / j loops stay rolled (the fully unrolled network is ~30k instructions and thrashes the
 // instruction cache); only the per-thread element loops are unrolled.
-template <int E, int J>
-__device__ __forceinline__ void cx_in_thread(uint64_t (&v)[E]) {   // partner r ^ J, J < E
+template <typename K, int E, int J>
+__device__ __forceinline__ void cx_in_thread(K (&v)[E]) {   // partner r ^ J, J < E
 #pragma unroll
   for (int r = 0; r < E; r++) {
     if ((r & J) == 0 && (r | J) < E) {
-      const uint64_t a = v[r], b = v[r | J];
+      const K a = v[r], b = v[r | J];
       v[r] = min(a, b);
       v[r | J] = max(a, b);
     }
   }
 }
-template <int E, int K>
-__device__ __forceinline__ void mirror_in_thread(uint64_t (&v)[E]) {   // partner r ^ (K-1), K <= E
+template <typename K, int E, int KK>
+__device__ __forceinline__ void mirror_in_thread(K (&v)[E]) {   // partner r ^ (KK-1), KK <= E
 #pragma unroll
   for (int r = 0; r < E; r++) {
-    const int rp = r ^ (K - 1);
+    const int rp = r ^ (KK - 1);
     if (r < rp && rp < E) {
-      const uint64_t a = v[r], b = v[rp];
+      const K a = v[r], b = v[rp];
       v[r] = min(a, b);
       v[rp] = max(a, b);
     }
   }
 }
 
-template <int E>
-__device__ __forceinline__ void bitonic_sort_regs(uint64_t (&v)[E], uint64_t* s) {
+template <typename K, int E>
+__device__ __forceinline__ void bitonic_sort_regs(K (&v)[E], K* s) {
   constexpr int N2 = TS_THREADS * E;
   const uint32_t t = threadIdx.x;
   for (int k = 2; k <= N2; k <<= 1) {
     // ---- mirror step: i <-> i ^ (k-1)
     if (k <= E) {
       switch (k) {
-        case 2: mirror_in_thread<E, 2>(v); break;
-        case 4: mirror_in_thread<E, 4>(v); break;
-        case 8: mirror_in_thread<E, 8>(v); break;
-        default: mirror_in_thread<E, 16>(v); break;
+        case 2: mirror_in_thread<K, E, 2>(v); break;
+        case 4: mirror_in_thread<K, E, 4>(v); break;
+        case 8: mirror_in_thread<K, E, 8>(v); break;
+        default: mirror_in_thread<K, E, 16>(v); break;
       }
     } else if (k <= 32 * E) {
       const int m = k / E - 1;
       const bool lower = (t & (k / (2 * E))) == 0;
-      uint64_t w[E];
+      K w[E];
 #pragma unroll
       for (int r = 0; r < E; r++) w[r] = v[r];
 #pragma unroll
       for (int r = 0; r < E; r++) {
-        const uint64_t pv = shfl_xor_u64(w[E - 1 - r], m);
+        const K pv = shfl_xor_key(w[E - 1 - r], m);
         v[r] = lower ? min(w[r], pv) : max(w[r], pv);
       }
     } else {
@@ -398,7 +400,7 @@ __device__ __forceinline__ void bitonic_sort_regs(uint64_t (&v)[E], uint64_t* s)
 #pragma unroll
       for (int r = 0; r < E; r++) {
         const uint32_t i = t * E + r, ip = i ^ (uint32_t)(k - 1);
-        const uint64_t pv = s[ip];
+        const K pv = s[ip];
         v[r] = (i < ip) ? min(v[r], pv) : max(v[r], pv);
       }
     }
@@ -406,17 +408,17 @@ __device__ __forceinline__ void bitonic_sort_regs(uint64_t (&v)[E], uint64_t* s)
     for (int j = k >> 2; j > 0; j >>= 1) {
       if (j < E) {
         switch (j) {
-          case 1: cx_in_thread<E, 1>(v); break;
-          case 2: cx_in_thread<E, 2>(v); break;
-          case 4: cx_in_thread<E, 4>(v); break;
-          default: cx_in_thread<E, 8>(v); break;
+          case 1: cx_in_thread<K, E, 1>(v); break;
+          case 2: cx_in_thread<K, E, 2>(v); break;
+          case 4: cx_in_thread<K, E, 4>(v); break;
+          default: cx_in_thread<K, E, 8>(v); break;
         }
       } else if (j < 32 * E) {
         const int m = j / E;
         const bool lower = (t & m) == 0;
 #pragma unroll
         for (int r = 0; r < E; r++) {
-          const uint64_t pv = shfl_xor_u64(v[r], m);
+          const K pv = shfl_xor_key(v[r], m);
           v[r] = lower ? min(v[r], pv) : max(v[r], pv);
         }
       } else {
@@ -427,7 +429,7 @@ __device__ __forceinline__ void bitonic_sort_regs(uint64_t (&v)[E], uint64_t* s)
 #pragma unroll
         for (int r = 0; r < E; r++) {
           const uint32_t i = t * E + r, ip = i ^ (uint32_t)j;
-          const uint64_t pv = s[ip];
+          const K pv = s[ip];
           v[r] = (i < ip) ? min(v[r], pv) : max(v[r], pv);
         }
       }
@@ -435,17 +437,98 @@ __device__ __forceinline__ void bitonic_sort_regs(uint64_t (&v)[E], uint64_t* s)
   }
 }
 
+// Sort a bucket of n <= 256 E composites (depth bits << 32 | slot) and write the slots in that order.
+// The network runs on 32-bit words, a third of the 64-bit network's instructions (one shuffle and one VIMNMX per
+// compare-exchange instead of two shuffles, two compares and two selects): word = quantised depth << b | index in the
+// bucket, b = log2(256 E).  The quantisation is a shift of (depth bits - smallest depth bits of the bucket) chosen so that
+// the bucket's depth range fills the 31 - b bits that are left — an integer, monotone map of the composite's upper half,
+// so the words order the bucket exactly except inside runs of equal quantised depth (a handful of pairs per frame).  Those
+// are found by comparing neighbours after the sort and resolved exactly: every member of a run counts the members whose
+// full composite is smaller than its own and takes that place in the run.  The result is the ascending order of the
+// 64-bit composites — the reference's stable (depth, Gaussian id) order — for any input; a bucket with a run longer
+// than TS_RUN_SCAN (many equal depths: nothing a camera produces) is handed to the generic 64-bit network in place
+// (register-light, so the rare path does not set the kernel's register count).
 template <int E>
-__device__ __forceinline__ void tile_sort_small(const uint64_t* __restrict__ comp, uint32_t* __restrict__ point_list,
-                                                uint32_t start, uint32_t n, uint64_t* s) {
-  uint64_t v[E];
-  const uint32_t base = threadIdx.x * E;
+__device__ __forceinline__ void tile_sort_small(uint64_t* __restrict__ comp, uint32_t* __restrict__ point_list,
+                                                uint32_t start, uint32_t n, uint64_t* s64) {
+  constexpr uint32_t N2 = TS_THREADS * E;
+  constexpr int B = (E == 1 ? 8 : E == 2 ? 9 : E == 4 ? 10 : E == 8 ? 11 : 12);
+  constexpr uint32_t IDX_MASK = N2 - 1u;
+  uint32_t* s32 = reinterpret_cast<uint32_t*>(s64);
+  __shared__ uint32_t s_red[2][TS_THREADS / 32];
+  const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const uint32_t base = t * E;
+  uint32_t d[E];
+  uint32_t dmin = 0xffffffffu, dmax = 0u;
 #pragma unroll
-  for (int r = 0; r < E; r++) v[r] = (base + r < n) ? __ldg(comp + start + base + r) : ~0ull;
-  bitonic_sort_regs<E>(v, s);
+  for (int r = 0; r < E; r++) {
+    const bool ok = base + r < n;
+    d[r] = ok ? (uint32_t)(__ldg(comp + start + base + r) >> 32) : 0u;
+    if (ok) dmin = min(dmin, d[r]), dmax = max(dmax, d[r]);
+  }
+  dmin = __reduce_min_sync(0xffffffffu, dmin), dmax = __reduce_max_sync(0xffffffffu, dmax);
+  if (lane == 0) s_red[0][warp] = dmin, s_red[1][warp] = dmax;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < TS_THREADS / 32; w++) dmin = min(dmin, s_red[0][w]), dmax = max(dmax, s_red[1][w]);
+  // (dmax - dmin) >> sh < 2^(31 - B): the top bit stays clear, so the all-ones padding word sorts behind every key
+  const int sh = max(0, (32 - __clz(dmax - dmin)) - (31 - B));
+  uint32_t v[E];
+#pragma unroll
+  for (int r = 0; r < E; r++) v[r] = (base + r < n) ? (((d[r] - dmin) >> sh) << B) | (base + r) : 0xffffffffu;
+  bitonic_sort_regs<uint32_t, E>(v, s32);
+  // publish the sorted words; pair (p, p+1) with equal quantised depth = a run
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < E; r++) s32[base + r] = v[r];
+  __syncthreads();
+  bool run = false;
+#pragma unroll
+  for (int r = 0; r < E; r++) {
+    const uint32_t p = base + r;
+    if (p + 1 < n) {
+      const uint32_t nx = (r + 1 < E) ? v[(r + 1) % E] : s32[p + 1];
+      run |= (nx >> B) == (v[r] >> B);
+    }
+  }
+  if (!__syncthreads_or(run)) {
+    // the common case: the words are distinct in their depth part, position p takes the slot of bucket entry (word & mask)
+#pragma unroll
+    for (int r = 0; r < E; r++)
+      if (base + r < n) point_list[start + base + r] = __ldg(reinterpret_cast<const uint32_t*>(comp + start + (v[r] & IDX_MASK)));
+    return;
+  }
+  bool too_long = false;
+  uint32_t dst[E], slot[E];
+#pragma unroll
+  for (int r = 0; r < E; r++) {
+    const uint32_t p = base + r;
+    dst[r] = p, slot[r] = 0;
+    if (p < n) {
+      const uint32_t q = v[r] >> B;
+      const uint64_t f = __ldg(comp + start + (v[r] & IDX_MASK));
+      slot[r] = (uint32_t)f;
+      int steps = 0;
+      for (uint32_t j = p; j > 0 && (s32[j - 1] >> B) == q; j--) {        // members in front of p that belong behind it
+        if (++steps > TS_RUN_SCAN) { too_long = true; break; }
+        if (__ldg(comp + start + (s32[j - 1] & IDX_MASK)) > f) dst[r]--;
+      }
+      steps = 0;
+      for (uint32_t j = p + 1; j < n && (s32[j] >> B) == q; j++) {        // members behind p that belong in front of it
+        if (++steps > TS_RUN_SCAN) { too_long = true; break; }
+        if (__ldg(comp + start + (s32[j] & IDX_MASK)) < f) dst[r]++;
+      }
+    }
+  }
+  if (__syncthreads_or(too_long)) {
+    uint64_t* a = comp + start;
+    bitonic_sort_block<uint64_t>(a, n, N2);
+    for (uint32_t i = t; i < n; i += TS_THREADS) point_list[start + i] = (uint32_t)a[i];
+    return;
+  }
 #pragma unroll
   for (int r = 0; r < E; r++)
-    if (base + r < n) point_list[start + base + r] = (uint32_t)v[r];
+    if (base + r < n) point_list[start + dst[r]] = slot[r];
 }
 
 __global__ void __launch_bounds__(TS_THREADS) tile_sort_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ comp,
