@@ -329,6 +329,10 @@ void launch_scatter(int P, const GeometryView& g, uint32_t* cursor, uint64_t* co
 constexpr int TS_THREADS = 256;
 constexpr uint32_t TS_SMEM_KEYS = 4096;   // 32 KB of composite keys in shared memory
 constexpr int TS_RUN_SCAN = 16;           // longest run of equal quantised depths that is ranked in place
+#ifndef GSR_TS_CTAS_PER_SM
+#define GSR_TS_CTAS_PER_SM 5
+#endif
+constexpr int TS_CTAS_PER_SM = GSR_TS_CTAS_PER_SM;
 
 __device__ __forceinline__ uint64_t shfl_xor_key(uint64_t v, int mask) {
   const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, mask);
@@ -531,7 +535,7 @@ __device__ __forceinline__ void tile_sort_small(uint64_t* __restrict__ comp, uin
     if (base + r < n) point_list[start + dst[r]] = slot[r];
 }
 
-__global__ void __launch_bounds__(TS_THREADS) tile_sort_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ comp,
+__global__ void __launch_bounds__(TS_THREADS, TS_CTAS_PER_SM) tile_sort_kernel(const uint2* __restrict__ ranges, uint64_t* __restrict__ comp,
                                                                uint32_t* __restrict__ point_list, uint32_t capacity,
                                                                const uint32_t* __restrict__ tile_order) {
   __shared__ uint64_t s_keys[TS_SMEM_KEYS];
