@@ -271,7 +271,7 @@ class GraphRefiner:
                                gmap.sh_degree, cam.camera_center, False, False)
         cnt = (C.c_uint * 3)()
         _lib.check(self.lib.gsr_read_counters(fwd[5].data_ptr(), P, cnt, torch.cuda.current_stream(dev).cuda_stream), "gsr_read_counters")
-        self.capacity = int(cnt[0] * 1.5) + 65536
+        self.capacity = int(cnt[0] * 2.0) + 65536     # headroom for the other views of the run: growing means re-capturing
         self.global_sort = int(cnt[2] * 1.5 > 4096)
         lib = self.lib
         self.geom = torch.empty(lib.gsr_geometry_bytes(P), **byte)
@@ -378,10 +378,18 @@ class GraphRefiner:
         R, overflow, longest = self._counters()
         need_global = int(longest * 1.5 > 4096)
         if R * 1.25 > self.capacity or need_global > self.global_sort:
-            self.capacity = int(R * 1.5) + 65536
-            self.global_sort = max(self.global_sort, need_global)
-            self.binning = torch.empty(self.lib.gsr_binning_bytes(self.capacity, self.W, self.H), dtype=torch.uint8, device=self.dev)
-            self.graph = None
+            # twice the view's instances: every growth drops the captured graph, so grow rarely
+            self._resize(max(self.capacity, int(R * 2.0) + 65536), max(self.global_sort, need_global))
+            return True
+        return False
+
+    def _resize(self, capacity: int, global_sort: int):
+        """New binning buffer of `capacity` instances (and sort path); the captured graph holds the old pointers and is dropped."""
+        if capacity == self.capacity and global_sort == self.global_sort:
+            return
+        self.capacity, self.global_sort = int(capacity), int(global_sort)
+        self.binning = torch.empty(self.lib.gsr_binning_bytes(self.capacity, self.W, self.H), dtype=torch.uint8, device=self.dev)
+        self.graph = None
 
     def refine(self, cam: PoseCamera, target: torch.Tensor, iters: int = 50, target_depth: torch.Tensor | None = None,
                grad_mask: torch.Tensor | None = None):
@@ -469,6 +477,11 @@ class BatchedGraphRefiner:
             r._pending = (cams[j], targets[j], iters, td[j], gm[j])
             r._load_query(cams[j], targets[j], td[j], gm[j])
             r._ensure_capacity()                # may grow this branch's binning buffer
+        # one branch grew: bring every branch to the same size now, so that a similar view landing in another branch later
+        # does not cost another capture of the whole batch graph
+        cap, gs = max(r.capacity for r in self.refiners), max(r.global_sort for r in self.refiners)
+        for r in self.refiners:
+            r._resize(cap, gs)
         if self.graph is None or self._captured_with != [(r.capacity, r.global_sort) for r in self.refiners]:
             self._capture()
             for i, r in enumerate(self.refiners):

@@ -169,6 +169,32 @@ def test_equal_depths_are_ordered_like_the_reference(kind):
     assert (alpha - ralpha).abs().max().item() == 0.0
 
 
+def test_packed_expf_is_expf_bit_for_bit():
+    """The forward's alpha decides n_contrib, and it comes from expf_pair (render.cu): CUDA's accurate expf with the four
+    roundings that have a packed form issued once for two values.  Every bit must be expf()'s: swept on the device over the
+    exponent's whole useful range (the blend only evaluates power <= 0), around zero, and at the special values."""
+    import ctypes as C
+    from gs_localization_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    n = 1 << 23
+    x = torch.empty(n)
+    x[: n // 2] = torch.rand(n // 2, generator=g) * -110.0                      # the blend's domain
+    x[n // 2: 3 * n // 4] = (torch.rand(n // 4, generator=g) - 0.5) * 200.0     # both signs, overflow and underflow ends
+    x[3 * n // 4:] = torch.randn(n // 4, generator=g) * torch.logspace(-30, 1, n // 4)
+    x[:12] = torch.tensor([0.0, -0.0, float("inf"), float("-inf"), float("nan"), -87.33655, -88.0, -103.97, -104.0, 88.72, 88.73, -1e-45])
+    xd = x.to(DEV)
+    ref, fast = torch.empty_like(xd), torch.empty_like(xd)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    lib.gsr_selftest_expf.restype = C.c_int
+    rc = lib.gsr_selftest_expf(p(xd), p(ref), p(fast), C.c_int(n), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert rc == 0
+    bad = ref.view(torch.int32) != fast.view(torch.int32)
+    assert not bool(bad.any()), (int(bad.sum()), x[bad.cpu()][:8], ref[bad][:8], fast[bad][:8])
+    assert torch.equal(ref[:2].cpu(), torch.ones(2)) and float(ref[3]) == 0.0
+
+
 def _grads_ours(m, cam, bg, wc, wd, wa):
     args, (R, color, depth, alpha, radii, geom, binning, img) = run_ours(m, cam, bg)
     (bgt, means3D, colors, opac, scales, rots, smod, cov, view, proj, tfx, tfy, H, W, sh, deg, campos, pf, dbg) = args
