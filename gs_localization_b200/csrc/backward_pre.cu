@@ -79,6 +79,60 @@ __device__ __forceinline__ float3 sh_backward(int deg, float3 pos, float3 campos
   return dnormvdv(dir_orig, dL_ddir);
 }
 
+// Rows of one gradient tensor ([P, R] floats) for the warp's visible Gaussians, written as FULL 32-byte sectors.
+// A row is 4-24 bytes at stride 4R: written on its own it is a partial sector, which L2 has to complete from DRAM before
+// it can merge the bytes (the zero rows around it were streamed out long ago) — those read-modify-writes were 16 us of
+// this kernel's 37 at the headline.  The rest of a row's sector is known, though: rows of culled Gaussians are zero, and the
+// visible neighbours are in the adjacent lanes (slot order is Gaussian order).  The lanes stage their rows in a
+// shared-memory window of the segment (256 rows, zeroed around the rows only), and every lane then writes the one or two
+// sectors its row touches, complete.  Lanes whose rows share a sector write the same bytes.  Sectors that hold a row of
+// another iteration of the warp's loop over the segment (`taint`), that reach behind the tensor's end, or a tensor that is
+// not 32-byte aligned take the plain element stores.
+#ifndef GSR_PBW_GRAN
+#define GSR_PBW_GRAN 8
+#endif
+constexpr int PBW_GRAN = GSR_PBW_GRAN;          // floats per completed block: 8 = one 32-byte sector
+template <int R>
+__device__ __forceinline__ void store_rows(float* __restrict__ out, float* __restrict__ stage, uint32_t seg_row0, uint32_t l, bool visible,
+                                           const float (&v)[R], int taint_lo_row, int taint_hi_row, uint32_t P) {
+  constexpr int G = PBW_GRAN, G4 = G / 4;
+  const bool sectors = ((uintptr_t)out & (4u * G - 1u)) == 0;
+  const uint32_t f0 = l * R, s0 = f0 / G, s1 = (f0 + R - 1) / G;           // floats / sectors of the row inside the window
+  // sectors <= taint_lo or >= taint_hi hold (part of) a row that another iteration of the loop writes
+  const int taint_lo = taint_lo_row < 0 ? -1 : (int)(((uint32_t)taint_lo_row * R + R - 1) / G);
+  const int taint_hi = taint_hi_row < 0 ? 0x7fffffff : (int)(((uint32_t)taint_hi_row * R) / G);
+  const size_t base = (size_t)seg_row0 * R, total = (size_t)P * R;
+  auto plain = [&](uint32_t sct) { return !sectors || (int)sct <= taint_lo || (int)sct >= taint_hi || base + (size_t)sct * G + G > total; };
+  float4* st4 = reinterpret_cast<float4*>(stage);
+  if (visible) {
+#pragma unroll
+    for (int i = 0; i < G4; i++) st4[G4 * s0 + i] = make_float4(0.f, 0.f, 0.f, 0.f), st4[G4 * s1 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncwarp();
+  if (visible) {
+#pragma unroll
+    for (int c = 0; c < R; c++) stage[f0 + c] = v[c];
+  }
+  __syncwarp();
+  if (visible) {
+#pragma unroll
+    for (int w = 0; w < 2; w++) {
+      const uint32_t sct = w ? s1 : s0;
+      if (w && s1 == s0) break;
+      if (plain(sct)) {
+#pragma unroll
+        for (int c = 0; c < R; c++)
+          if ((f0 + c) / G == sct) out[base + f0 + c] = v[c];
+      } else {
+        float4* dst = reinterpret_cast<float4*>(out + base + (size_t)sct * G);
+#pragma unroll
+        for (int i = 0; i < G4; i++) dst[i] = st4[G4 * sct + i];
+      }
+    }
+  }
+  __syncwarp();      // the window is reused by the next tensor
+}
+
 __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwdParams p) {
   __shared__ float s_tau[BW_THREADS / 32][6];
   pdl_trigger();
@@ -101,9 +155,15 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
   const float* proj = s_cam + 16;
   float tau[6] = {0, 0, 0, 0, 0, 0};
 
-  for (uint32_t t_in_seg = lane; t_in_seg < nvis; t_in_seg += 32) {
-  const uint32_t k = seg * PRE_THREADS + t_in_seg;     // slot
-  const bool visible = true;
+  __shared__ __align__(16) float s_stage[BW_THREADS / 32][PRE_THREADS * 6];     // per warp: a segment's rows of the widest small tensor
+  float* const stage = s_stage[warp];
+  int prev_last_row = -1;                                // segment-local row of the previous iteration's last Gaussian
+  for (uint32_t t0 = 0; t0 < nvis; t0 += 32) {          // warp-uniform trip count: the row stores below are warp-cooperative
+  const uint32_t t_in_seg = t0 + lane;
+  const bool visible = t_in_seg < nvis;
+  const uint32_t k = seg * PRE_THREADS + (visible ? t_in_seg : 0u);     // slot
+  // first Gaussian of the next iteration, if there is one (its sectors are left to the plain stores, like the previous one's)
+  const int next_first_row = t0 + 32 < nvis ? (int)(__ldg(p.geom.gid + seg * PRE_THREADS + t0 + 32) - seg * PRE_THREADS) : -1;
   float3 g_mean2D = {0, 0, 0};
   float4 g_conic = {0, 0, 0, 0};
   float g_opacity = 0.f;
@@ -308,20 +368,19 @@ __global__ void __launch_bounds__(BW_THREADS) preprocess_bwd_kernel(const PreBwd
     }
   }
 
-  // ---------------- rows of the visible Gaussians (culled rows were zero-filled by memset)
-  if (visible) {
-    if (p.dL_dmean2D) { float* o = p.dL_dmean2D + 3 * idx; o[0] = g_mean2D.x; o[1] = g_mean2D.y; o[2] = 0.f; }
-    if (p.dL_dconic) reinterpret_cast<float4*>(p.dL_dconic)[idx] = g_conic;
-    if (p.dL_dopacity) p.dL_dopacity[idx] = g_opacity;
-    if (p.dL_dcolor) { float* o = p.dL_dcolor + 3 * idx; o[0] = g_color.x; o[1] = g_color.y; o[2] = g_color.z; }
-    if (p.dL_dmean3D) { float* o = p.dL_dmean3D + 3 * idx; o[0] = g_mean.x; o[1] = g_mean.y; o[2] = g_mean.z; }
-    if (p.dL_dcov3D) {
-      float* o = p.dL_dcov3D + 6 * idx;
-#pragma unroll
-      for (int q = 0; q < 6; q++) o[q] = g_cov[q];
-    }
-    if (p.dL_dscale) { float* o = p.dL_dscale + 3 * idx; o[0] = g_scale.x; o[1] = g_scale.y; o[2] = g_scale.z; }
-    if (p.dL_drot) reinterpret_cast<float4*>(p.dL_drot)[idx] = g_rot;
+  // ---------------- rows of the visible Gaussians (culled rows were zero-filled by the blend backward)
+  {
+    const uint32_t row0 = seg * PRE_THREADS, l = visible ? (uint32_t)idx - row0 : 0u;
+    const uint32_t Pn = (uint32_t)p.P;
+    if (p.dL_dmean2D) { const float v[3] = {g_mean2D.x, g_mean2D.y, 0.f}; store_rows<3>(p.dL_dmean2D, stage, row0, l, visible, v, prev_last_row, next_first_row, Pn); }
+    if (p.dL_dconic) { const float v[4] = {g_conic.x, g_conic.y, g_conic.z, g_conic.w}; store_rows<4>(p.dL_dconic, stage, row0, l, visible, v, prev_last_row, next_first_row, Pn); }
+    if (p.dL_dopacity) { const float v[1] = {g_opacity}; store_rows<1>(p.dL_dopacity, stage, row0, l, visible, v, prev_last_row, next_first_row, Pn); }
+    if (p.dL_dcolor) { const float v[3] = {g_color.x, g_color.y, g_color.z}; store_rows<3>(p.dL_dcolor, stage, row0, l, visible, v, prev_last_row, next_first_row, Pn); }
+    if (p.dL_dmean3D) { const float v[3] = {g_mean.x, g_mean.y, g_mean.z}; store_rows<3>(p.dL_dmean3D, stage, row0, l, visible, v, prev_last_row, next_first_row, Pn); }
+    if (p.dL_dcov3D) { const float v[6] = {g_cov[0], g_cov[1], g_cov[2], g_cov[3], g_cov[4], g_cov[5]}; store_rows<6>(p.dL_dcov3D, stage, row0, l, visible, v, prev_last_row, next_first_row, Pn); }
+    if (p.dL_dscale) { const float v[3] = {g_scale.x, g_scale.y, g_scale.z}; store_rows<3>(p.dL_dscale, stage, row0, l, visible, v, prev_last_row, next_first_row, Pn); }
+    if (p.dL_drot) { const float v[4] = {g_rot.x, g_rot.y, g_rot.z, g_rot.w}; store_rows<4>(p.dL_drot, stage, row0, l, visible, v, prev_last_row, next_first_row, Pn); }
+    prev_last_row = (int)__shfl_sync(0xffffffffu, l, 31);      // only used when there is a next iteration (lane 31 is then visible)
   }
   }  // loop over the segment's visible slots
 
