@@ -11,8 +11,9 @@
 // segment's first slots, so each CTA here runs only ceil(visible/32) dense warps (the reference
 // launches P threads, most of which exit at once); the two reference kernels are fused, so dL_dcov3D / dL_dmean3D never
 // round-trip through HBM between them; the dense zero rows the API promises for culled
-// Gaussians are produced by plain memsets at copy-engine bandwidth, and each visible row is
-// then written exactly once.  With dL_dtau != nullptr the SE(3) chain rule is fused in: each
+// Gaussians are written by the blend backward (render.cu), and the rows of the visible ones here, as
+// complete 32-byte sectors (store_rows).  Nothing of the map is read: the forward left mean / scale /
+// rotation and the SH direction derivatives in the slot.  With dL_dtau != nullptr the SE(3) chain rule is fused in: each
 // thread forms its 6-vector contribution to dL/d(rho, theta) for the left perturbation
 // T_w2c <- exp(tau) T_w2c (gs_localization/pipelines/tools/pose_utils.py:90-122), the CTA
 // reduces it with shuffles and issues 6 atomics.

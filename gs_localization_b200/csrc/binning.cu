@@ -17,11 +17,13 @@
 //      binary search over CTA-local prefix sums, so a Gaussian covering thousands of tiles
 //      costs no more per instance than one covering four) and drop each instance into its
 //      tile's bucket through an atomic cursor, as the composite depth_bits << 32 | slot.
-//   3. tile_sort: one CTA per tile sorts its bucket in shared memory with a bitonic network on
-//      the composite key.  Slot order is Gaussian order, so ascending (depth bits, slot) is
-//      exactly the order the reference's stable LSD sort produces — ties included — while each
-//      instance crosses HBM once instead of 12 times.  Buckets larger than the shared-memory
-//      budget are sorted by the same network directly in global memory (L2).
+//   3. tile_sort: one CTA per tile sorts its bucket with a register / shuffle bitonic network.
+//      Slot order is Gaussian order, so ascending (depth bits, slot) is exactly the order the
+//      reference's stable LSD sort produces — ties included — while each instance crosses HBM
+//      once instead of 12 times.  The network runs on 32-bit words (quantised depth | index in
+//      the bucket: a third of the 64-bit network's instructions); runs of equal quantised depth
+//      are resolved exactly afterwards (tile_sort_small).  Buckets larger than the shared-memory
+//      budget are sorted by the generic 64-bit network directly in global memory (L2).
 // The onesweep radix sort (Adinets & Merrill) that replaces cub::DeviceRadixSort as a library
 // primitive is kept below and exported as gsr_sort_pairs.
 #include <cstdlib>
