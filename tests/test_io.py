@@ -99,3 +99,45 @@ def test_pose_results_round_trip(tmp_path):
     R = gio.quat_to_rotmat([np.sqrt(0.5), 0, 0, np.sqrt(0.5)])
     assert np.allclose(R, [[0, -1, 0], [1, 0, 0], [0, 0, 1]])
     assert np.allclose(gio.rotmat_to_quat(R), [np.sqrt(0.5), 0, 0, np.sqrt(0.5)])
+
+
+# ---------------------------------------------------------------------------------------------------- reference goldens
+# tests/golden/ref_map.ply is what the REFERENCE's GaussianModel.save_ply wrote for the parameters stored in ref_map.npz,
+# and ref_map.npz also holds what its load_ply / getters returned for that file (tests/golden/make_ply_golden.py).
+import os
+
+_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _golden_raw():
+    z = np.load(os.path.join(_GOLD, "ref_map.npz"))
+    return z, gio.RawGaussians(z["in_xyz"], z["in_f_dc"], z["in_f_rest"], z["in_opacity"], z["in_scaling"], z["in_rotation"])
+
+
+def test_save_ply_writes_the_reference_bytes(tmp_path):
+    """Same parameters -> the file the reference's save_ply wrote, byte for byte (gaussian_model.py:192-208)."""
+    _, raw = _golden_raw()
+    path = str(tmp_path / "ours.ply")
+    gio.save_ply(path, raw)
+    assert open(path, "rb").read() == open(os.path.join(_GOLD, "ref_map.ply"), "rb").read()
+
+
+def test_load_ply_matches_the_reference_loader():
+    """The reference-written file read by load_ply_raw / activate equals what the reference's load_ply and getters gave."""
+    z, _ = _golden_raw()
+    raw = gio.load_ply_raw(os.path.join(_GOLD, "ref_map.ply"), max_sh_degree=int(z["sh_degree"]))
+    for ours, key in ((raw.xyz, "ld_xyz"), (raw.features_dc, "ld_f_dc"), (raw.features_rest, "ld_f_rest"), (raw.opacity, "ld_opacity"),
+                      (raw.scaling, "ld_scaling"), (raw.rotation, "ld_rotation")):
+        assert ours.dtype == np.float32 and ours.shape == z[key].shape, key
+        assert np.array_equal(ours, z[key]), key
+    g = gio.activate(raw)
+    assert g.sh_degree == int(z["sh_degree"])
+    assert np.array_equal(g.shs.numpy(), z["get_features"])
+    # sigmoid / exp / normalize are torch's own ops in both; allow for vectorisation differences of one ulp
+    np.testing.assert_allclose(g.opacities.numpy(), z["get_opacity"], rtol=2e-7, atol=0)
+    np.testing.assert_allclose(g.scales.numpy(), z["get_scaling"], rtol=2e-7, atol=0)
+    np.testing.assert_allclose(g.rotations.numpy(), z["get_rotation"], rtol=0, atol=2e-7)
+    # the reference asserts on the f_rest count for a different SH degree (gaussian_model.py:230)
+    import pytest
+    with pytest.raises(AssertionError):
+        gio.load_ply_raw(os.path.join(_GOLD, "ref_map.ply"), max_sh_degree=2)
