@@ -30,7 +30,7 @@ __device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f,
 // slot order == Gaussian order, so ties keep the reference's order.  No CTA depends on another.
 struct GeometryView {           // replaces GeometryState (reference rasterizer_impl.h:29-44)
   float* depths;                // [slots] view-space z
-  float4* mean_tau;             // [slots] (pixel-space centre x, y, 2 ln(255 o) inflated: the opacity-aware culling bound, unused)
+  float4* mean_tau;             // [slots] (pixel-space centre x, y, 2 ln(255 o) inflated: the opacity-aware culling bound, slot bits)
   float4* conic_opacity;        // [slots] (conic.x, conic.y, conic.z, opacity)
   float4* rgbd;                 // [slots] (r, g, b, depth): one 16-byte gather for the blend kernels
   float4* msr;                  // [3 slots] (mean xyz, scale x) (scale y z, rot w x) (rot y z, -, -): what the preprocess backward needs

@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(PRE2_WARPS * 32) preprocess_fwd_kernel(const P
     if (vis) {
       const uint32_t k = (uint32_t)base + nvis + __popc(vis_mask & lt);   // slot: segment start + rank inside the segment
       p.geom.depths[k] = vz;
-      p.geom.mean_tau[k] = make_float4(pix_x, pix_y, splat_two_tau(conic.x, conic.y, conic.z, opacity), 0.f);
+      p.geom.mean_tau[k] = make_float4(pix_x, pix_y, splat_two_tau(conic.x, conic.y, conic.z, opacity), __uint_as_float(k));   // w: the slot itself, so a staged record is three plain 16-byte copies
       p.geom.conic_opacity[k] = make_float4(conic.x, conic.y, conic.z, opacity);
       p.geom.rect[k] = rect;
       p.geom.gid[k] = (uint32_t)idx;
