@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(ST_THREADS) scan_tiles_kernel(int* __restrict_
   }
   __syncthreads();
   const uint32_t longest = s_max[0];
+  const float bucket_scale = (float)ST_BUCKETS / (float)(longest + 1u);
   // ranges + bucket cursors + launch order of the blend CTAs (longest lists first: counting sort on 64 length classes)
   uint32_t run = s_part[warp] + incl - sum;
   uint32_t my_bucket[(8192 + ST_THREADS - 1) / ST_THREADS + 1];
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(ST_THREADS) scan_tiles_kernel(int* __restrict_
       cursor[(size_t)t * CURSOR_STRIDE] = run;
       run += c;
       if (order_ok) {
-        const uint32_t bk = (ST_BUCKETS - 1) - min((uint32_t)(ST_BUCKETS - 1), (uint32_t)(((unsigned long long)c * ST_BUCKETS) / (longest + 1)));
+        const uint32_t bk = (ST_BUCKETS - 1) - min((uint32_t)(ST_BUCKETS - 1), (uint32_t)((float)c * bucket_scale));   // a launch-order heuristic: float is exact enough
         my_bucket[i] = bk;
         atomicAdd(&s_bucket[bk], 1u);
       }

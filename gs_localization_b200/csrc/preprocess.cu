@@ -135,6 +135,17 @@ __device__ __forceinline__ float3 color_from_sh(int deg, float3 pos, float3 camp
   return make_float3(fmaxf(r0, 0.f), fmaxf(r1, 0.f), fmaxf(r2, 0.f));
 }
 
+__device__ __forceinline__ float rcp_mufu(float x) {
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sqrt_mufu(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // static factor of the conservative radius bound: s_max^2 |R|_F^2 with |R|_F^2 = 1 + 2 (1 - 2|v|^2)^2 + 8 w^2 |v|^2 for the
 // reference's unnormalised-quaternion matrix (forward.cu:127-140)
 __device__ __forceinline__ float cull_static_factor(float3 sc, float4 q) {
@@ -165,6 +176,7 @@ void launch_build_cull_records(int P, const float* means3D, const float* scales,
 __global__ void __launch_bounds__(PRE_THREADS) preprocess_cull_kernel(const PreprocessParams p) {
   __shared__ uint32_t s_warp_near[PRE_THREADS / 32];
   __shared__ float s_cam[16 + 16];
+  __shared__ float s_w2;
   pdl_trigger();
   pdl_wait();
   const int tid = threadIdx.x;
@@ -212,6 +224,14 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_cull_kernel(const Prep
     }
     if (tid < 16) s_cam[tid] = p.viewmatrix[tid];
     else if (tid < 32) s_cam[tid] = p.projmatrix[tid - 16];
+    else if (tid == 32) {       // squared Frobenius norm of the view rotation: the same for every Gaussian of the launch
+      float w2 = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) { const float v = p.viewmatrix[4 * c + r]; w2 += v * v; }
+      s_w2 = w2;
+    }
     __syncthreads();
     if (idx < P) {
       const float* vm = s_cam;
@@ -224,18 +244,16 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_cull_kernel(const Prep
           const float hx = __fadd_rn(dot3c(px, pm[0], py, pm[4], pz, pm[8]), pm[12]);
           const float hy = __fadd_rn(dot3c(px, pm[1], py, pm[5], pz, pm[9]), pm[13]);
           const float hw = __fadd_rn(dot3c(px, pm[3], py, pm[7], pz, pm[11]), pm[15]);
-          const float p_w = 1.0f / (hw + 0.0000001f);
+          // bare MUFU reciprocals / square root (1-2 ulp): this is a BOUND with 1 % / 2 % / 2 px of slack built in, the exact
+          // pipeline runs in pass 2 for everything that survives
+          const float p_w = rcp_mufu(hw + 0.0000001f);
           const float cx = ((hx * p_w + 1.0f) * (float)p.W - 1.0f) * 0.5f, cy = ((hy * p_w + 1.0f) * (float)p.H - 1.0f) * 0.5f;
-          float w2 = 0.f;
-#pragma unroll
-          for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) w2 += vm[4 * c + r] * vm[4 * c + r];
+          const float w2 = s_w2;
           const float limx = 1.3f * p.tan_fovx, limy = 1.3f * p.tan_fovy;
-          const float iz = 1.0f / vz;
+          const float iz = rcp_mufu(vz);
           const float j2 = (p.focal_x * iz) * (p.focal_x * iz) * (1.0f + limx * limx) + (p.focal_y * iz) * (p.focal_y * iz) * (1.0f + limy * limy);
           const float lam = w2 * j2 * (s2r2 * p.scale_modifier * p.scale_modifier) * 1.02f + 0.3f + 0.32f;
-          const float rb = 3.0f * sqrtf(lam) * 1.01f + 2.0f;
+          const float rb = 3.0f * sqrt_mufu(lam) * 1.01f + 2.0f;
           // outside for sure: the whole [c - rb, c + rb + 15] interval maps to tile index <= 0 or >= grid on one axis
           const bool outside = (cx + rb + 15.0f < 0.0f) || (cx - rb >= 16.0f * (float)p.grid_x) || (cy + rb + 15.0f < 0.0f) ||
                                (cy - rb >= 16.0f * (float)p.grid_y);
