@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_cull_kernel(const Prep
 // block barrier after the camera constants are staged.  Visible Gaussians are packed into the segment's slots in order
 // (ballot ranks + a running count over the warp's iterations).
 constexpr int PRE2_WARPS = 8;
-__global__ void __launch_bounds__(PRE2_WARPS * 32) preprocess_fwd_kernel(const PreprocessParams p) {
+__global__ void __launch_bounds__(PRE2_WARPS * 32, 4) preprocess_fwd_kernel(const PreprocessParams p) {
   __shared__ float s_cam[16 + 16];
   pdl_trigger();
   pdl_wait();
