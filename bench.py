@@ -469,7 +469,7 @@ def run_train_dp(args, rank, world, device):
         opt = gm.default_training_args(densify_from_iter=10_000, densify_until_iter=15_000)   # statistics are exchanged, no densification inside the timed steps
         model.training_setup(opt)
         trainer = parallel.DataParallelTrainer(model, opt, mode=mode)
-        acc = [0.0, 0.0]
+        acc = [[], []]
 
         def one(it, timed):
             vid = parallel.shard_views(16, it, rank, world)
@@ -487,19 +487,21 @@ def run_train_dp(args, rank, world, device):
             torch.cuda.synchronize()
             t3 = time.perf_counter()
             if timed:
-                acc[0] += t3 - t0
-                acc[1] += t2 - t1
+                acc[0].append(t3 - t0)
+                acc[1].append(t2 - t1)
 
-        for it in range(1, 4):
+        # warm-up: every view once (allocator, speculative binning capacity and NCCL buffers in steady state), then the
+        # median step over another pass through the views
+        n_warm, n = 16, 16
+        for it in range(1, 1 + n_warm):
             one(it, False)
-        n = 8
-        for it in range(4, 4 + n):
+        for it in range(1 + n_warm, 1 + n_warm + n):
             one(it, True)
-        t = torch.tensor(acc, dtype=torch.float64, device=device) / n
+        t = torch.tensor([sorted(a)[len(a) // 2] for a in acc], dtype=torch.float64, device=device)
         if world > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         # gradient-sum parity: exchanged gradient of one more step against the per-view gradients recomputed here
-        it = 4 + n
+        it = 1 + n_warm + n
         vid = parallel.shard_views(16, it, rank, world)
         ref = None
         for r in range(world):
