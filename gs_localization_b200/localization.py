@@ -468,6 +468,12 @@ class BatchedGraphRefiner:
     def refine_batch(self, cams, targets, iters: int = 50, target_depths=None, grad_masks=None):
         """Refine len(cams) <= batch queries; returns [(w2c, loss), ...].  A partial batch repeats its last query in the idle
         branches (their results are discarded)."""
+        self.submit_batch(cams, targets, iters, target_depths, grad_masks)
+        return self.collect_batch()
+
+    def submit_batch(self, cams, targets, iters: int = 50, target_depths=None, grad_masks=None):
+        """Queue the refinement of len(cams) <= batch queries on the current stream without waiting for it
+        (`collect_batch` does); the only host wait in here is the capacity check of each query's starting view."""
         n = len(cams)
         assert 1 <= n <= self.batch
         td = list(target_depths) if target_depths is not None else [None] * n
@@ -489,9 +495,63 @@ class BatchedGraphRefiner:
                 r._load_query(cams[j], targets[j], td[j], gm[j])
         for _ in range(iters):
             self.graph.replay()
+        self._submitted = n
+
+    def collect_batch(self):
+        """Wait for the batch submitted last; [(w2c, loss), ...] in the order of its queries."""
         out = []
-        for i in range(n):
+        for i in range(self._submitted):
             r = self.refiners[i]
             r.graph = None                      # collect()'s eager fallback must not reuse a stale single-query graph
             out.append(r.collect())
+        self._submitted = 0
         return out
+
+
+class PipelinedBatchRefiner:
+    """A stream of queries against one map through `depth` BatchedGraphRefiners that take turns, each on its own CUDA
+    stream: while one set's graph replays run, the host loads the next batch into the other set (pose / target copies,
+    the capacity check of each starting view, which is a forward plus a host read) and queues its replays, and collects
+    the first set only when it needs it again.  The GPU never waits for the host between batches; every query still runs
+    exactly the kernels of `GraphRefiner`, so the refined poses are unchanged (queries are independent: loop of
+    gs_localization/pipelines/7scenes_localize_full_dslam.py:352-365)."""
+
+    def __init__(self, gmap: syn.GaussianMap, cam: PoseCamera, batch: int = 4, depth: int = 2, **kw):
+        self.dev = cam.device
+        self.sets = [BatchedGraphRefiner(gmap, cam, batch=batch, **kw) for _ in range(int(depth))]
+        self.streams = [torch.cuda.Stream(self.dev) for _ in range(int(depth))]
+
+    @property
+    def batch(self) -> int:
+        return self.sets[0].batch
+
+    def refine_all(self, cams, targets, iters: int = 50, target_depths=None, grad_masks=None):
+        """Refine all queries; returns [(w2c, loss), ...] in query order."""
+        n, B, D = len(cams), self.batch, len(self.sets)
+        td = list(target_depths) if target_depths is not None else [None] * n
+        gm = list(grad_masks) if grad_masks is not None else [None] * n
+        main = torch.cuda.current_stream(self.dev)
+        for s_ in self.streams:
+            s_.wait_stream(main)                  # the targets were produced on the caller's stream
+        results = [None] * n
+        pending = [None] * D                      # per set: (first, last) of the batch in flight
+
+        def collect(k):
+            if pending[k] is None:
+                return
+            a, b = pending[k]
+            with torch.cuda.stream(self.streams[k]):
+                results[a:b] = self.sets[k].collect_batch()
+            pending[k] = None
+
+        for j, a in enumerate(range(0, n, B)):
+            k, b = j % D, min(n, a + B)
+            collect(k)
+            with torch.cuda.stream(self.streams[k]):
+                self.sets[k].submit_batch(cams[a:b], targets[a:b], iters, td[a:b], gm[a:b])
+            pending[k] = (a, b)
+        for k in range(D):
+            collect(k)
+        for s_ in self.streams:
+            main.wait_stream(s_)
+        return results

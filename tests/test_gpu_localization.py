@@ -237,3 +237,32 @@ def test_batched_graph_refiner_matches_single_query_refiner():
             dt, dr = syn.pose_error(w_b.cpu(), w_s.cpu())
             assert dt <= 1e-5 and dr <= 1e-3, (rounds, dt, dr)
             assert abs(float(l_b) - float(l_s)) <= 1e-5
+
+
+def test_pipelined_refiner_matches_batched_refiner():
+    """Two sets of graph branches taking turns on their own streams (host work of one batch under the replays of the other)
+    return, query by query, what the one-set refiner returns — partial last batch included."""
+    cfg = dict(P=20_000, W=160, H=128, deg=2, f=120.0, box=1.0, sigma0=0.06)
+    m = syn.make_map(cfg["P"], cfg["deg"], cfg["sigma0"], 1.0, seed=0).to(DEV)
+    qs = []
+    for q in range(11):                                      # 11 queries, batches of 2: six batches, the last one partial
+        gt = syn.make_camera(cfg, 40 + q)
+        target = loc.render_pose(m, loc.PoseCamera(gt, DEV), torch.zeros(3, device=DEV))[0].detach()
+        qs.append((gt, target, gt.perturbed(syn.initial_perturbation(q, trans_m=0.02, rot_deg=1.0))))
+    one = loc.BatchedGraphRefiner(m, loc.PoseCamera(qs[0][2], DEV), batch=2, lr=1e-3)
+    want = []
+    for a in range(0, len(qs), 2):
+        part = qs[a:a + 2]
+        want += one.refine_batch([loc.PoseCamera(s, DEV) for _, _, s in part], [t for _, t, _ in part], iters=15)
+    piped = loc.PipelinedBatchRefiner(m, loc.PoseCamera(qs[0][2], DEV), batch=2, depth=2, lr=1e-3)
+    for rounds in range(2):
+        got = piped.refine_all([loc.PoseCamera(s, DEV) for _, _, s in qs], [t for _, t, _ in qs], iters=15)
+        assert len(got) == len(qs) and all(g is not None for g in got)
+        for i, ((w_p, l_p), (w_b, l_b)) in enumerate(zip(got, want)):
+            dt, dr = syn.pose_error(w_p.cpu(), w_b.cpu())
+            assert dt <= 1e-5 and dr <= 1e-3, (rounds, i, dt, dr)
+            assert abs(float(l_p) - float(l_b)) <= 1e-5
+    # the refined poses moved towards the ground truth
+    e0 = syn.pose_error(qs[3][2].w2c, qs[3][0].w2c)
+    e1 = syn.pose_error(got[3][0].cpu(), qs[3][0].w2c)
+    assert e1[0] < e0[0]
