@@ -260,8 +260,10 @@ def test_pipelined_refiner_matches_batched_refiner():
         assert len(got) == len(qs) and all(g is not None for g in got)
         for i, ((w_p, l_p), (w_b, l_b)) in enumerate(zip(got, want)):
             dt, dr = syn.pose_error(w_p.cpu(), w_b.cpu())
-            assert dt <= 1e-5 and dr <= 1e-3, (rounds, i, dt, dr)
-            assert abs(float(l_p) - float(l_b)) <= 1e-5
+            # two runs of the SAME refiner differ by the order of the backward's float32 atomics, carried through 15 Adam
+            # steps (observed up to 2e-6 m / 1.2e-3 deg); the budget of north_star is 1 mm / 0.01 deg
+            assert dt <= 1e-4 and dr <= 5e-3, (rounds, i, dt, dr)
+            assert abs(float(l_p) - float(l_b)) <= 1e-4
     # the refined poses moved towards the ground truth
     e0 = syn.pose_error(qs[3][2].w2c, qs[3][0].w2c)
     e1 = syn.pose_error(got[3][0].cpu(), qs[3][0].w2c)
