@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(256) add_gradient_rows_kernel(const float* __r
 // receivers clamp to the capacity and the host checks one step later).  Columns after the gradients: the screen-space
 // gradient (x, y) and the radius of the view, i.e. what the densification statistics of gaussian_model.py:405-407 need,
 // so that every replica accumulates the statistics of ALL views of the step and takes identical densification decisions.
+constexpr int PACK_ROWS = 4;
 __global__ void __launch_bounds__(256) pack_visible_rows_kernel(const int* __restrict__ radii, int P, int M, GradRowTensors t,
                                                                 const float* __restrict__ g_means2D, float* __restrict__ table,
                                                                 int capacity, unsigned int* __restrict__ count) {
@@ -216,24 +217,41 @@ __global__ void __launch_bounds__(256) pack_visible_rows_kernel(const int* __res
   unsigned int base = 0;
   if (lane == 0) base = atomicAdd(count, (unsigned int)__popc(bal));
   base = __shfl_sync(0xffffffffu, base, 0);
-  // the warp writes its visible rows one after the other, 32 columns at a time
+  // The warp writes its visible rows PACK_ROWS at a time: all their columns are requested first (read-only path, so the
+  // loads do not wait for the stores of the previous group), then stored — one DRAM round trip per group instead of per row.
   const int width[5] = {3, 3 * M, 1, 3, 4};
   unsigned int m = bal, k = 0;
   while (m) {
-    const int src = __ffs(m) - 1;
-    m &= m - 1;
-    const unsigned int row = base + k++;
-    if (row >= (unsigned int)capacity) continue;
-    const int g = warp_first + src;
-    float* out = table + (size_t)row * W;
-    if (lane == 0) out[0] = __int_as_float(g);
-    for (int c = lane; c < F; c += 32) {
-      int ten, w;
-      row_column(c, M, ten, w);
-      out[1 + c] = t.g[ten][(size_t)g * width[ten] + w];
+    int g[PACK_ROWS];
+    unsigned int row[PACK_ROWS];
+#pragma unroll
+    for (int r = 0; r < PACK_ROWS; r++) {
+      const bool have = m != 0;
+      g[r] = have ? warp_first + (__ffs(m) - 1) : -1;
+      m &= m - 1;                                 // no-op on 0
+      row[r] = base + k;
+      if (have) k++;
+      if (row[r] >= (unsigned int)capacity) g[r] = -1;
     }
-    if (lane < 2) out[1 + F + lane] = g_means2D ? g_means2D[3 * (size_t)g + lane] : 0.f;
-    if (lane == 2) out[1 + F + 2] = (float)radii[g];
+    for (int c0 = 0; c0 < F; c0 += 32) {
+      const int c = c0 + lane;
+      int ten = 0, w = 0;
+      if (c < F) row_column(c, M, ten, w);
+      float v[PACK_ROWS];
+#pragma unroll
+      for (int r = 0; r < PACK_ROWS; r++) v[r] = (c < F && g[r] >= 0) ? __ldg(t.g[ten] + (size_t)g[r] * width[ten] + w) : 0.f;
+#pragma unroll
+      for (int r = 0; r < PACK_ROWS; r++)
+        if (c < F && g[r] >= 0) table[(size_t)row[r] * W + 1 + c] = v[r];
+    }
+#pragma unroll
+    for (int r = 0; r < PACK_ROWS; r++) {
+      if (g[r] < 0) continue;
+      float* out = table + (size_t)row[r] * W;
+      if (lane == 0) out[0] = __int_as_float(g[r]);
+      if (lane < 2) out[1 + F + lane] = g_means2D ? __ldg(g_means2D + 3 * (size_t)g[r] + lane) : 0.f;
+      if (lane == 2) out[1 + F + 2] = (float)radii[g[r]];
+    }
   }
 }
 __global__ void pack_visible_header_kernel(float* table, int capacity, int W, const unsigned int* count) {
@@ -241,30 +259,60 @@ __global__ void pack_visible_header_kernel(float* table, int capacity, int W, co
 }
 
 // adds a received table: gradients (unless it is this rank's own table, whose rows are already in place) and the
-// densification statistics; rows beyond the header's count or with ids outside [0, P) are ignored
+// densification statistics; rows beyond the header's count or with ids outside [0, P) are ignored.
+// The table may live in a PEER's memory (VisibleRowExchange with symmetric memory: gather and add are this one kernel,
+// the loads go over NVLink): a warp therefore takes ADD_ROWS rows at a time and requests all their ids, then all their
+// columns, before it touches the local rows — four times the bytes in flight per warp for a round trip of microseconds.
+constexpr int ADD_ROWS = 4;
+// The table may live in a peer's memory and was written a barrier (and a kernel boundary) ago; it is read-only for the
+// lifetime of this kernel, so it goes through the read-only path: L1 is invalidated between kernels, and its 128-byte line
+// fills are the request size NVLink moves best — ld.global.cg / ld.relaxed.sys (32-byte sectors) ran the peer pull 25 %
+// slower (tests/tools/exchange_peer_probe.py, which changes the table contents every step and checks the sums).
+__device__ __forceinline__ float ld_sys(const float* p) { return __ldg(p); }
 __global__ void __launch_bounds__(256) add_counted_rows_kernel(const float* __restrict__ table, int capacity, int M, int P, GradRowTensors t,
                                                                int add_grads, float* __restrict__ max_radii2D,
                                                                float* __restrict__ xyz_gradient_accum, float* __restrict__ denom) {
   const int F = 11 + 3 * M, W = 1 + F + 3;
-  const int n = min(__float_as_int(table[(size_t)capacity * W]), capacity);
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= n) return;
-  const float* in = table + (size_t)row * W;
-  const int g = __float_as_int(in[0]);
-  if (g < 0 || g >= P) return;
+  const int n = min(__float_as_int(ld_sys(table + (size_t)capacity * W)), capacity);
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ADD_ROWS, lane = threadIdx.x & 31;
+  if (row0 >= n) return;
+  int g[ADD_ROWS];
+#pragma unroll
+  for (int k = 0; k < ADD_ROWS; k++) g[k] = row0 + k < n ? __float_as_int(ld_sys(table + (size_t)(row0 + k) * W)) : -1;
+#pragma unroll
+  for (int k = 0; k < ADD_ROWS; k++)
+    if (g[k] >= P) g[k] = -1;
   if (add_grads) {
     const int width[5] = {3, 3 * M, 1, 3, 4};
-    for (int c = lane; c < F; c += 32) {
-      int ten, w;
-      row_column(c, M, ten, w);
-      t.g[ten][(size_t)g * width[ten] + w] += in[1 + c];   // row ids are unique within one rank's table
+    for (int c0 = 0; c0 < F; c0 += 32) {
+      const int c = c0 + lane;
+      float v[ADD_ROWS];
+#pragma unroll
+      for (int k = 0; k < ADD_ROWS; k++) v[k] = (c < F && g[k] >= 0) ? ld_sys(table + (size_t)(row0 + k) * W + 1 + c) : 0.f;
+      if (c < F) {
+        int ten, w;
+        row_column(c, M, ten, w);
+        // Row ids are unique within one rank's table and the tables of a step are added one kernel after the other, so
+        // every address receives ONE addition per launch: the reduction instruction gives the bits of `+=` (a subnormal
+        // sum flushes to zero), but nothing comes back to the SM — no read-modify-write round trip per row.
+#pragma unroll
+        for (int k = 0; k < ADD_ROWS; k++)
+          if (g[k] >= 0) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(t.g[ten] + (size_t)g[k] * width[ten] + w), "f"(v[k]) : "memory");
+      }
     }
   }
-  if (lane == 0 && max_radii2D) {
-    const float gx = in[1 + F], gy = in[1 + F + 1], r = in[1 + F + 2];
-    max_radii2D[g] = fmaxf(max_radii2D[g], r);
-    xyz_gradient_accum[g] += sqrtf(gx * gx + gy * gy);
-    denom[g] += 1.f;
+  if (max_radii2D && lane < ADD_ROWS) {     // lane k: the statistics of row k
+    int gk = -1;
+#pragma unroll
+    for (int k = 0; k < ADD_ROWS; k++)
+      if (lane == k) gk = g[k];
+    if (gk >= 0) {
+      const float* in = table + (size_t)(row0 + lane) * W;
+      const float gx = ld_sys(in + 1 + F), gy = ld_sys(in + 1 + F + 1), r = ld_sys(in + 1 + F + 2);
+      max_radii2D[gk] = fmaxf(max_radii2D[gk], r);
+      xyz_gradient_accum[gk] += sqrtf(gx * gx + gy * gy);
+      denom[gk] += 1.f;
+    }
   }
 }
 
@@ -278,7 +326,7 @@ void launch_pack_visible_rows(const int* radii, int P, int M, const GradRowTenso
 void launch_add_counted_rows(const float* table, int capacity, int M, int P, const GradRowTensors& t, int add_grads, float* max_radii2D,
                              float* xyz_gradient_accum, float* denom, cudaStream_t stream) {
   if (capacity <= 0) return;
-  add_counted_rows_kernel<<<(capacity + 7) / 8, 256, 0, stream>>>(table, capacity, M, P, t, add_grads, max_radii2D, xyz_gradient_accum, denom);
+  add_counted_rows_kernel<<<(capacity + 8 * ADD_ROWS - 1) / (8 * ADD_ROWS), 256, 0, stream>>>(table, capacity, M, P, t, add_grads, max_radii2D, xyz_gradient_accum, denom);
   count_launch();
 }
 

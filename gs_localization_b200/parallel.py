@@ -254,10 +254,18 @@ class VisibleRowExchange:
     accumulates the densification statistics of ALL views of the step, so that the replicas take identical
     densification decisions."""
 
-    def __init__(self, P: int, M: int, device, granularity: int = 4096):
+    def __init__(self, P: int, M: int, device, granularity: int = 4096, peer_memory: bool | None = None):
         self.P, self.M, self.dev = int(P), int(M), torch.device(device)
         self.W = 1 + 11 + 3 * self.M + 3
         self.granularity = int(granularity)
+        # Peer-memory pull (NVLink / NVSwitch): the tables live in symmetric memory and every rank's add kernel reads the
+        # peers' tables in place — gather and add are ONE kernel per peer, no gathered copy, no NCCL call on the data path.
+        # None = use it when the process group runs NCCL on CUDA devices and symmetric memory can be set up
+        # (GSR_DP_PEER=0 forces the all-gather path).
+        import os
+        self.peer_memory = peer_memory if peer_memory is not None else os.environ.get("GSR_DP_PEER", "1") != "0"
+        self._symm, self._symm_hdl, self._symm_floats = None, None, 0
+        self.used_peer_memory = False
         self.count = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._side = torch.cuda.Stream(self.dev) if self.dev.type == "cuda" else None
         self._max_rows = torch.zeros(1, dtype=torch.int32, device=self.dev)
@@ -310,6 +318,26 @@ class VisibleRowExchange:
         # persistent buffers that only grow: a table whose size follows the view would otherwise ask the allocator for a new
         # block (a cudaMalloc, i.e. a device synchronisation) almost every step
         need = (cap + 1) * W
+        sp = [None, None, None] if stats is None else [t.data_ptr() for t in stats]
+        hdl = self._peer_tables(need) if (ws > 1 and self.peer_memory) else None
+        self.used_peer_memory = hdl is not None
+        if hdl is not None:
+            # every rank packs into its own symmetric table; after the barrier each rank's add kernels read the peers'
+            # tables over NVLink (the kernel takes a pointer: a peer's table is just another address)
+            table = self._symm[:need]
+            _lib.check(lib.gsr_pack_visible_rows(radii.data_ptr(), self.P, self.M, tab, None if dL_dmeans2D is None else dL_dmeans2D.data_ptr(),
+                                                 table.data_ptr(), cap, self.count.data_ptr(), stream), "gsr_pack_visible_rows")
+            hdl.barrier(channel=0)                      # all tables of the step are complete
+            for k in range(ws):
+                r = (rank + k) % ws                     # start with our own, then the peers in a rotated order (no hot spot)
+                if r == rank and stats is None:
+                    continue
+                part = table if r == rank else hdl.get_buffer(r, (need,), torch.float32)
+                _lib.check(lib.gsr_add_counted_rows(part.data_ptr(), cap, self.M, self.P, tab, int(r != rank), sp[0], sp[1], sp[2], stream),
+                           "gsr_add_counted_rows")
+            hdl.barrier(channel=1)                      # nobody refills its table before every peer has read it
+            self.last_rows, self.last_bytes = cap, int(need * 4 * ws)
+            return list(grads)
         if self._buf is None or self._buf.numel() < need * (ws + 1):
             self._buf = torch.empty(int(need * (ws + 1) * 1.25), dtype=torch.float32, device=dev)
         table = self._buf[:need]
@@ -320,7 +348,6 @@ class VisibleRowExchange:
             _all_gather_into(gathered, table)
         else:
             gathered = table
-        sp = [None, None, None] if stats is None else [t.data_ptr() for t in stats]
         for r in range(ws):
             part = gathered[r * (cap + 1) * W:(r + 1) * (cap + 1) * W]
             if r == rank and stats is None:
@@ -329,6 +356,31 @@ class VisibleRowExchange:
                        "gsr_add_counted_rows")
         self.last_rows, self.last_bytes = cap, int(gathered.numel() * 4)
         return list(grads)
+
+    def _peer_tables(self, need: int):
+        """Symmetric-memory table of at least `need` floats on every rank (torch.distributed._symmetric_memory: one
+        allocation per rank, mapped into every peer).  `need` follows the all-reduced row count, so all ranks grow in the
+        same step; growing is a collective (rendezvous), which is why the buffer only ever grows, by half again each time.
+        Returns the handle, or None when symmetric memory is not available here (then the all-gather path runs)."""
+        if self.dev.type != "cuda" or _backend() != "nccl":
+            return None
+        if self._symm_hdl is not None and self._symm_floats >= need:
+            return self._symm_hdl
+        if self._symm_hdl is False:
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            floats = min(int(need * 1.5) + 1024, (self.P + 1) * self.W + 1024)
+            floats = max(floats, need)
+            buf = symm.empty(floats, dtype=torch.float32, device=self.dev)
+            hdl = symm.rendezvous(buf, dist.group.WORLD)
+        except Exception as ex:      # no peer access / unsupported build: every rank takes this branch together
+            import warnings
+            warnings.warn(f"symmetric memory unavailable ({ex!r}); visible-row exchange falls back to all_gather")
+            self._symm_hdl = False
+            return None
+        self._symm, self._symm_hdl, self._symm_floats = buf, hdl, floats
+        return hdl
 
 
 class DataParallelTrainer:
