@@ -357,6 +357,10 @@ class VisibleRowExchange:
         self.last_rows, self.last_bytes = cap, int(gathered.numel() * 4)
         return list(grads)
 
+    def peer_path_expected(self) -> bool:
+        """Will `exchange` pull over peer memory?  (Known for sure after the first exchange; before it, from the setup.)"""
+        return bool(self.peer_memory) and self._symm_hdl is not False and self.dev.type == "cuda" and _backend() == "nccl"
+
     def _peer_tables(self, need: int):
         """Symmetric-memory table of at least `need` floats on every rank (torch.distributed._symmetric_memory: one
         allocation per rank, mapped into every peer).  `need` follows the all-reduced row count, so all ranks grow in the
@@ -392,11 +396,14 @@ class DataParallelTrainer:
     cannot overlap the forward of step t+1: that forward reads the parameters the optimiser step of t writes."""
 
     # An all-reduce moves 2 (N-1)/N x the arena whatever the views see, and on NVSwitch it is reduced inside the switch
-    # (measured 8 x B200: 744 MB in 2.6 ms, 507 GB/s bus); the visible-row all-gather moves (N-1) x the LARGEST view's table
-    # into every GPU at about 0.4 of that rate (182 GB/s bus).  "auto" compares the two per step, with the row count that
-    # is known before the exchange starts: sparse wins while N x visible fraction is small (2 GPUs at C4: 1.0 ms vs 2.2 ms),
-    # dense once the views of a step cover most of the map (8 GPUs at C4: 2.6 ms vs 5.6 ms).
+    # (measured 8 x B200: 708 MB in 1.74 ms, 712 GB/s bus; 2 x B200: 549 GB/s).  The visible-row exchange moves (N-1) x the
+    # view's table into every GPU: by peer-memory pull at about 400 GB/s (8 x B200: 7 x 72 MB in 1.6 ms, 7 x 145 MB in
+    # 2.85 ms; 2 x B200: 145 MB in 0.70 ms), by all-gather + add at about 0.4 of the all-reduce's rate (8 x B200: 7 x 145 MB
+    # in 4.6 ms).  "auto" compares the two per step with the row count that is known before the exchange starts: sparse
+    # wins while N x visible fraction is small (2 GPUs at C4: 0.5-0.7 ms vs 1.3 ms), dense once the views of a step cover
+    # most of the map (8 GPUs at C4, largest view 19 %: 1.7 ms vs 2.9 ms).  tests/tools/exchange_peer_probe.py.
     ALLGATHER_RATE_VS_ALLREDUCE = 0.4
+    PEER_PULL_RATE_VS_ALLREDUCE = 0.6
 
     def __init__(self, model, opt, mode: str = "auto", extent: float = 1.0):
         assert mode in ("dense", "sparse", "auto")
@@ -425,7 +432,8 @@ class DataParallelTrainer:
             rows = ex.max_rows(radii)                  # exact, already on the host (exchanged under the backward)
             sparse_bytes = (ws - 1) * rows * ex.W * 4
             dense_bytes = 2.0 * (ws - 1) / max(ws, 1) * sum(t.numel() for t in g) * 4
-            mode = "sparse" if ws == 1 or sparse_bytes < dense_bytes * self.ALLGATHER_RATE_VS_ALLREDUCE else "dense"
+            rate = self.PEER_PULL_RATE_VS_ALLREDUCE if ex.peer_path_expected() else self.ALLGATHER_RATE_VS_ALLREDUCE
+            mode = "sparse" if ws == 1 or sparse_bytes < dense_bytes * rate else "dense"
         self.last_choice = mode
         if mode == "sparse":
             ex = self._sparse()
