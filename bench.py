@@ -529,15 +529,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)", 1965.0
 
 
+PROFILED_SOURCES = ("preprocess.cu", "binning.cu", "render.cu", "backward_pre.cu", "api.cu", "gsr_common.cuh", "gsr_kernels.cuh")
+
+
 def kernel_source_sha256():
-    """Hash of the kernel sources the timed library was built from: a committed ncu profile is only used if it was
-    captured on exactly these sources."""
-    import glob
+    """Hash of the sources of the kernels the ncu profile covers (the rasterizer's forward and backward; not the optimiser,
+    loss, kNN or exchange kernels, which are not in it): a committed profile is only used if it was captured on exactly
+    these sources."""
     import hashlib
     h = hashlib.sha256()
-    files = sorted(glob.glob(os.path.join(ROOT, "gs_localization_b200", "csrc", "*.cu")) +
-                   glob.glob(os.path.join(ROOT, "gs_localization_b200", "csrc", "*.cuh")) +
-                   [os.path.join(ROOT, "include", "gsr_b200.h")])
+    files = sorted(os.path.join(ROOT, "gs_localization_b200", "csrc", f) for f in PROFILED_SOURCES) + [os.path.join(ROOT, "include", "gsr_b200.h")]
     for f in files:
         h.update(os.path.basename(f).encode())
         h.update(open(f, "rb").read())

@@ -276,19 +276,29 @@ __global__ void __launch_bounds__(256) add_counted_rows_kernel(const float* __re
   const int n = min(__float_as_int(ld_sys(table + (size_t)capacity * W)), capacity);
   const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ADD_ROWS, lane = threadIdx.x & 31;
   if (row0 >= n) return;
+  // ids, gradient columns and the three statistics columns are requested together (a column's address depends on the
+  // row index only, not on the id): ONE round trip to the peer per group of rows
   int g[ADD_ROWS];
 #pragma unroll
   for (int k = 0; k < ADD_ROWS; k++) g[k] = row0 + k < n ? __float_as_int(ld_sys(table + (size_t)(row0 + k) * W)) : -1;
+  constexpr int MAX_PASSES = 2;                 // 1 + F + 3 = W <= 65 floats for SH degree <= 3 (M <= 16): columns 0 .. F + 2 in two passes
+  const bool two_pass = F + 3 <= MAX_PASSES * 32;
+  const int width[5] = {3, 3 * M, 1, 3, 4};
+  float v[MAX_PASSES][ADD_ROWS];
+#pragma unroll
+  for (int ps = 0; ps < MAX_PASSES; ps++) {
+    const int c = ps * 32 + lane;
+    const bool want = two_pass ? (c < F + 3 && (add_grads || c >= F)) : (add_grads && c < F);
+#pragma unroll
+    for (int k = 0; k < ADD_ROWS; k++) v[ps][k] = (want && row0 + k < n) ? ld_sys(table + (size_t)(row0 + k) * W + 1 + c) : 0.f;
+  }
 #pragma unroll
   for (int k = 0; k < ADD_ROWS; k++)
     if (g[k] >= P) g[k] = -1;
   if (add_grads) {
-    const int width[5] = {3, 3 * M, 1, 3, 4};
-    for (int c0 = 0; c0 < F; c0 += 32) {
-      const int c = c0 + lane;
-      float v[ADD_ROWS];
 #pragma unroll
-      for (int k = 0; k < ADD_ROWS; k++) v[k] = (c < F && g[k] >= 0) ? ld_sys(table + (size_t)(row0 + k) * W + 1 + c) : 0.f;
+    for (int ps = 0; ps < MAX_PASSES; ps++) {
+      const int c = ps * 32 + lane;
       if (c < F) {
         int ten, w;
         row_column(c, M, ten, w);
@@ -297,20 +307,42 @@ __global__ void __launch_bounds__(256) add_counted_rows_kernel(const float* __re
         // sum flushes to zero), but nothing comes back to the SM — no read-modify-write round trip per row.
 #pragma unroll
         for (int k = 0; k < ADD_ROWS; k++)
-          if (g[k] >= 0) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(t.g[ten] + (size_t)g[k] * width[ten] + w), "f"(v[k]) : "memory");
+          if (g[k] >= 0) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(t.g[ten] + (size_t)g[k] * width[ten] + w), "f"(v[ps][k]) : "memory");
+      }
+    }
+    for (int c0 = MAX_PASSES * 32; c0 < F; c0 += 32) {      // rows wider than 64 columns (not reachable with SH degree <= 3)
+      const int c = c0 + lane;
+      if (c < F) {
+        int ten, w;
+        row_column(c, M, ten, w);
+#pragma unroll
+        for (int k = 0; k < ADD_ROWS; k++)
+          if (g[k] >= 0) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(t.g[ten] + (size_t)g[k] * width[ten] + w), "f"(ld_sys(table + (size_t)(row0 + k) * W + 1 + c)) : "memory");
       }
     }
   }
-  if (max_radii2D && lane < ADD_ROWS) {     // lane k: the statistics of row k
+  if (max_radii2D) {
+    // densification statistics of row k on lane k: its (gx, gy, radius) sit in the lanes that loaded columns F .. F + 2
+    float sx = 0.f, sy = 0.f, sr = 0.f;
     int gk = -1;
 #pragma unroll
-    for (int k = 0; k < ADD_ROWS; k++)
-      if (lane == k) gk = g[k];
-    if (gk >= 0) {
-      const float* in = table + (size_t)(row0 + lane) * W;
-      const float gx = ld_sys(in + 1 + F), gy = ld_sys(in + 1 + F + 1), r = ld_sys(in + 1 + F + 2);
-      max_radii2D[gk] = fmaxf(max_radii2D[gk], r);
-      xyz_gradient_accum[gk] += sqrtf(gx * gx + gy * gy);
+    for (int k = 0; k < ADD_ROWS; k++) {
+      float x, y, r;
+      if (two_pass) {
+        const float x0 = __shfl_sync(0xffffffffu, v[0][k], F & 31), x1 = __shfl_sync(0xffffffffu, v[1][k], F & 31);
+        const float y0 = __shfl_sync(0xffffffffu, v[0][k], (F + 1) & 31), y1 = __shfl_sync(0xffffffffu, v[1][k], (F + 1) & 31);
+        const float r0 = __shfl_sync(0xffffffffu, v[0][k], (F + 2) & 31), r1 = __shfl_sync(0xffffffffu, v[1][k], (F + 2) & 31);
+        x = F < 32 ? x0 : x1, y = F + 1 < 32 ? y0 : y1, r = F + 2 < 32 ? r0 : r1;
+      } else {
+        const float* in = table + (size_t)(row0 + k) * W;
+        const bool have = row0 + k < n;
+        x = have ? ld_sys(in + 1 + F) : 0.f, y = have ? ld_sys(in + 1 + F + 1) : 0.f, r = have ? ld_sys(in + 1 + F + 2) : 0.f;
+      }
+      if (lane == k) sx = x, sy = y, sr = r, gk = g[k];
+    }
+    if (lane < ADD_ROWS && gk >= 0) {
+      max_radii2D[gk] = fmaxf(max_radii2D[gk], sr);
+      xyz_gradient_accum[gk] += sqrtf(sx * sx + sy * sy);
       denom[gk] += 1.f;
     }
   }

@@ -45,7 +45,8 @@ kernels = [dict(name=k, launches=a["n"], us_per_launch=round(a["us"] / a["n"], 3
                 dram_bytes_per_launch=round((a["rd"] + a["wr"]) / a["n"]), registers=a["regs"],
                 issue_active_pct=round(a["issue"] / a["n"], 2), warps_active_pct=round(a["warps"] / a["n"], 2)) for k, a in sorted(agg.items())]
 git = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
-dirty = subprocess.run(["git", "-C", ROOT, "status", "--porcelain", "--", "gs_localization_b200/csrc", "include"], capture_output=True, text=True).stdout.strip()
+dirty = subprocess.run(["git", "-C", ROOT, "status", "--porcelain", "--", *["gs_localization_b200/csrc/" + f for f in bench.PROFILED_SOURCES], "include"],
+                       capture_output=True, text=True).stdout.strip()
 doc = {"_comment": "per-launch averages from one ncu --set full --clock-control none capture of tests/tools/stage_probe.py (headline workload); "
                    "times are under the profiler (cold caches, serialised): use the byte and instruction counts, not the times",
        "source_sha256": bench.kernel_source_sha256(), "git": git + ("+uncommitted kernel changes" if dirty else ""),
