@@ -62,6 +62,16 @@ def _backend() -> str:
     return dist.get_backend() if dist.is_available() and dist.is_initialized() else ""
 
 
+def _broadcast(t: torch.Tensor, src: int = 0):
+    """dist.broadcast in place; with the gloo backend CUDA tensors go through the host."""
+    if t.is_cuda and _backend() == "gloo":
+        h = t.cpu()
+        dist.broadcast(h, src)
+        t.copy_(h)
+    else:
+        dist.broadcast(t, src)
+
+
 def _all_reduce(t: torch.Tensor, op=None):
     """dist.all_reduce; with the gloo backend (CPU tests, two processes sharing one GPU) CUDA tensors go through the host."""
     op = dist.ReduceOp.SUM if op is None else op
@@ -466,10 +476,35 @@ class DataParallelTrainer:
         if self.mode in ("sparse", "auto"):
             self._sparse().begin(radii)
 
+    def structural_step(self, iteration: int) -> bool:
+        """Does `apply_gradients` clone / split / prune or reset opacities at this iteration (gaussian_model.apply_gradients)?"""
+        opt = self.opt
+        if iteration >= opt.densify_until_iter:
+            return False
+        return (iteration > opt.densify_from_iter and iteration % opt.densification_interval == 0) or iteration % opt.opacity_reset_interval == 0
+
+    def resync(self):
+        """Rank 0's replica (parameters, Adam moments, densification statistics) to every rank.
+        The dense all-reduce gives every rank the same bits, and so does the visible-row exchange at two ranks; with three
+        or more ranks it adds the tables in a different order on each rank, so replicas differ in the last ulp — harmless for
+        the optimiser, but densification compares per-Gaussian statistics with thresholds, and ONE Gaussian deciding
+        differently on one rank changes P there.  Called before every structural step (a few GB once per
+        densification interval), it makes those decisions identical by construction."""
+        rank, ws = world()
+        if ws <= 1:
+            return
+        m = self.model
+        tensors = list(m._params()) + list(m._state["m"]) + list(m._state["v"]) + [m.max_radii2D, m.xyz_gradient_accum, m.denom]
+        for t in tensors:
+            _broadcast(t, 0)
+        m._refresh_activations()
+
     def step(self, cam, gt_image, bg, iteration: int, pseudo_depth=None, gt_depth=None):
         m, opt = self.model, self.opt
         loss, g, g2d, out = m.compute_gradients(cam, gt_image, bg, opt, iteration, pseudo_depth, gt_depth, after_forward=self.after_forward)
         want_stats = iteration < opt.densify_until_iter
         self.reduce(g, g2d, out["radii"], want_stats)
+        if self.structural_step(iteration) and world()[1] > 2 and self.last_choice == "sparse":
+            self.resync()
         out["densify"] = m.apply_gradients(g, None, None, opt, iteration, self.extent, stats_done=True)
         return loss, out

@@ -105,3 +105,46 @@ def test_sparse_gradient_exchange_equals_dense_allreduce():
         err, rows, F = out[r]
         assert err < 1e-6 and F == 3 + 12 + 1 + 3 + 4
         assert rows % 64 == 0 and 64 <= rows <= 256                       # padded to the larger rank's visible count
+
+
+class _Replica:
+    """The part of GaussianModel that DataParallelTrainer.resync touches."""
+
+    def __init__(self, rank):
+        g = torch.Generator().manual_seed(5)
+        mk = lambda *s: torch.randn(*s, generator=g)
+        self.p = [mk(40, 3), mk(40, 16, 3), mk(40, 1), mk(40, 3), mk(40, 4)]
+        self._state = {"m": [mk(*t.shape) for t in self.p], "v": [mk(*t.shape).abs() for t in self.p]}
+        self.max_radii2D, self.xyz_gradient_accum, self.denom = mk(40).abs(), mk(40, 1).abs(), mk(40, 1).abs()
+        if rank:                                   # the drift of a replica: last-ulp differences everywhere
+            for t in self.p + self._state["m"] + self._state["v"] + [self.max_radii2D, self.xyz_gradient_accum, self.denom]:
+                t.mul_(1.0 + 1.2e-7 * rank)
+        self.refreshed = 0
+
+    def _params(self):
+        return self.p
+
+    def _refresh_activations(self):
+        self.refreshed += 1
+
+
+def _resync(rank, world):
+    import types
+    opt = types.SimpleNamespace(densify_until_iter=15_000, densify_from_iter=500, densification_interval=100, opacity_reset_interval=3000)
+    model = _Replica(rank)
+    trainer = parallel.DataParallelTrainer(model, opt, mode="sparse")
+    structural = [it for it in (100, 500, 600, 650, 3000, 14_900, 15_000, 15_100) if trainer.structural_step(it)]
+    before = model.p[1].clone()
+    trainer.resync()
+    flat = torch.cat([t.reshape(-1) for t in model.p + model._state["m"] + model._state["v"] + [model.max_radii2D, model.xyz_gradient_accum, model.denom]])
+    return structural, bool((before != model.p[1]).any()), flat.tolist(), model.refreshed
+
+
+def test_resync_makes_replicas_identical_before_structural_steps():
+    """Three ranks whose replicas differ in the last ulp (what the visible-row exchange leaves at >= 3 ranks) are bit-identical
+    after DataParallelTrainer.resync; structural_step names exactly the densification / opacity-reset iterations."""
+    out = _spawn(_resync, world=3)
+    assert out[0][0] == [600, 3000, 14_900]
+    assert out[0][1] is False and out[1][1] is True and out[2][1] is True      # rank 0 is the source
+    assert out[0][2] == out[1][2] == out[2][2]
+    assert out[0][3] == out[1][3] == 1
