@@ -499,12 +499,17 @@ class DataParallelTrainer:
             _broadcast(t, 0)
         m._refresh_activations()
 
+    def before_apply(self, iteration: int):
+        """Call between `reduce` and `GaussianModel.apply_gradients`: re-synchronises the replicas when this iteration is a
+        structural step and the ranks may differ in the last ulp (see `resync`)."""
+        if self.structural_step(iteration) and world()[1] > 2 and self.last_choice == "sparse":
+            self.resync()
+
     def step(self, cam, gt_image, bg, iteration: int, pseudo_depth=None, gt_depth=None):
         m, opt = self.model, self.opt
         loss, g, g2d, out = m.compute_gradients(cam, gt_image, bg, opt, iteration, pseudo_depth, gt_depth, after_forward=self.after_forward)
         want_stats = iteration < opt.densify_until_iter
         self.reduce(g, g2d, out["radii"], want_stats)
-        if self.structural_step(iteration) and world()[1] > 2 and self.last_choice == "sparse":
-            self.resync()
+        self.before_apply(iteration)
         out["densify"] = m.apply_gradients(g, None, None, opt, iteration, self.extent, stats_done=True)
         return loss, out

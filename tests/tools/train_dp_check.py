@@ -48,6 +48,7 @@ for mode in ("sparse", "dense", "auto"):
         trainer.reduce(g, g2d, out["radii"], it < args.densify_until_iter)
         errs = [float((a - b).norm() / (b.norm() + 1e-30)) for a, b in zip(g, ref)]
         worst_sum = max(worst_sum, max(errs))
+        trainer.before_apply(it)
         info = model.apply_gradients(g, None, None, args, it, 4.0, stats_done=True)
         if info:
             events.append((it, info["cloned"], info["split"], info["pruned"], info["after"]))
@@ -61,7 +62,10 @@ for mode in ("sparse", "dense", "auto"):
         lo, hi = chk.clone(), chk.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        same = bool(((hi - lo).abs() <= 1e-9 * hi.abs().clamp_min(1.0)).all())
+        # two ranks / dense all-reduce: every rank holds the same bits.  Visible rows at >= 3 ranks: tables are added in a
+        # per-rank order, replicas differ in the last ulp between re-synchronisations — P must still be identical
+        tol = 1e-9 if (world <= 2 or trainer.last_choice == "dense") else 1e-5
+        same = bool(hi[0] == lo[0]) and bool(((hi - lo).abs() <= tol * hi.abs().clamp_min(1.0)).all())
         if not same:
             ok_all = False
             if rank == 0:
