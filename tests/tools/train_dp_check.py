@@ -59,12 +59,15 @@ for mode in ("sparse", "dense", "auto"):
         for t in list(model._params()) + [model.xyz_gradient_accum, model.denom, model.max_radii2D]:
             chk += [t.double().sum().cpu(), t.double().abs().sum().cpu()]
         chk = torch.stack(chk)
+        if not same_gpu:
+            chk = chk.to(dev)                           # NCCL reduces device tensors
         lo, hi = chk.clone(), chk.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         # two ranks / dense all-reduce: every rank holds the same bits.  Visible rows at >= 3 ranks: tables are added in a
         # per-rank order, replicas differ in the last ulp between re-synchronisations — P must still be identical
-        tol = 1e-9 if (world <= 2 or trainer.last_choice == "dense") else 1e-5
+        # (mode "auto" may have exchanged sparsely in an earlier step: the dense all-reduce of a later one does not undo that)
+        tol = 1e-9 if (world <= 2 or trainer.mode == "dense") else 1e-5
         same = bool(hi[0] == lo[0]) and bool(((hi - lo).abs() <= tol * hi.abs().clamp_min(1.0)).all())
         if not same:
             ok_all = False
