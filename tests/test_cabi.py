@@ -133,3 +133,20 @@ def test_compiled_binding_loads_and_matches_abi():
         C.rasterize_gaussians(torch.zeros(3), torch.zeros(4, 3), torch.Tensor([]), torch.zeros(4, 1), torch.zeros(4, 3),
                               torch.zeros(4, 4), 1.0, torch.Tensor([]), torch.eye(4), torch.eye(4), 1.0, 1.0, 8, 8,
                               torch.zeros(4, 1, 3), 0, torch.zeros(3), False, False)
+
+
+def test_committed_ncu_profile_matches_the_kernel_sources():
+    """bench.py's roofline block takes warp-instruction and DRAM-byte counts from profiles/r2_roofline_profile.json and only if
+    that capture was taken on exactly the rasterizer sources in the tree (bench.kernel_source_sha256).  A kernel change
+    without a new capture must not go unnoticed: the bench line would silently lose those fields."""
+    import json
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    prof, note = bench.load_profile()
+    assert prof is not None, note
+    d = json.load(open(bench.PROFILE_JSON))
+    names = " ".join(k["name"] for k in d["kernels"])
+    for kernel in ("render_fwd_kernel", "render_bwd_kernel", "preprocess_cull_kernel", "preprocess_fwd_kernel", "preprocess_bwd_kernel",
+                   "scan_tiles_kernel", "scatter_kernel", "tile_sort_kernel", "color_fwd_kernel"):
+        assert kernel in names, kernel
