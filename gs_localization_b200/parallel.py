@@ -422,6 +422,17 @@ class DataParallelTrainer:
         self.exchange_bytes = 0
         self.last_choice = None
 
+    @classmethod
+    def choose_mode(cls, ws: int, rows: int, row_floats: int, arena_floats: int, peer_pull: bool) -> str:
+        """"sparse" or "dense" for one step: (N-1) tables of `rows` rows into every GPU against an all-reduce of the arena
+        (2 (N-1)/N of its bytes on the wire), weighted by the measured rates of the two paths."""
+        if ws <= 1:
+            return "sparse"
+        sparse_bytes = (ws - 1) * rows * row_floats * 4
+        dense_bytes = 2.0 * (ws - 1) / ws * arena_floats * 4
+        rate = cls.PEER_PULL_RATE_VS_ALLREDUCE if peer_pull else cls.ALLGATHER_RATE_VS_ALLREDUCE
+        return "sparse" if sparse_bytes < dense_bytes * rate else "dense"
+
     def _sparse(self):
         m = self.model
         P, M = int(m._xyz.shape[0]), int(m._features.shape[1])
@@ -440,10 +451,7 @@ class DataParallelTrainer:
         if mode == "auto":
             ex = self._sparse()
             rows = ex.max_rows(radii)                  # exact, already on the host (exchanged under the backward)
-            sparse_bytes = (ws - 1) * rows * ex.W * 4
-            dense_bytes = 2.0 * (ws - 1) / max(ws, 1) * sum(t.numel() for t in g) * 4
-            rate = self.PEER_PULL_RATE_VS_ALLREDUCE if ex.peer_path_expected() else self.ALLGATHER_RATE_VS_ALLREDUCE
-            mode = "sparse" if ws == 1 or sparse_bytes < dense_bytes * rate else "dense"
+            mode = self.choose_mode(ws, rows, ex.W, sum(t.numel() for t in g), ex.peer_path_expected())
         self.last_choice = mode
         if mode == "sparse":
             ex = self._sparse()

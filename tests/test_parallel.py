@@ -148,3 +148,19 @@ def test_resync_makes_replicas_identical_before_structural_steps():
     assert out[0][1] is False and out[1][1] is True and out[2][1] is True      # rank 0 is the source
     assert out[0][2] == out[1][2] == out[2][2]
     assert out[0][3] == out[1][3] == 1
+
+
+def test_auto_mode_follows_the_measured_crossovers():
+    """DataParallelTrainer.choose_mode on the cases measured on B200 (DESIGN section 8, C4-sized map: 3M Gaussians, 63-float table
+    rows, 59-float arena rows): the peer pull wins at 2 GPUs up to the largest view and at 8 GPUs up to ~9 % visible rows;
+    all-gather + add loses to the all-reduce earlier."""
+    P, W, A = 3_000_000, 63, 3_000_000 * 59
+    choose = parallel.DataParallelTrainer.choose_mode
+    assert choose(1, int(0.19 * P), W, A, True) == "sparse"
+    assert choose(2, int(0.19 * P), W, A, True) == "sparse"          # 0.70 ms vs 1.29 ms
+    assert choose(2, int(0.19 * P), W, A, False) == "sparse"         # 1.26 ms vs 1.29 ms (all-gather path, barely)
+    assert choose(4, int(0.19 * P), W, A, True) == "sparse"          # bench train_dp at 4 GPUs: 1106 vs 864 views/s
+    assert choose(8, int(0.095 * P), W, A, True) == "sparse"         # 1.62 ms vs 1.74 ms
+    assert choose(8, int(0.19 * P), W, A, True) == "dense"           # 2.85 ms vs 1.74 ms
+    assert choose(8, int(0.095 * P), W, A, False) == "dense"         # 2.57 ms vs 1.74 ms
+    assert choose(8, int(0.035 * P), W, A, False) == "sparse"        # 1.15 ms vs 1.74 ms
